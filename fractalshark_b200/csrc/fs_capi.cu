@@ -1,0 +1,663 @@
+// fs_capi.cu -- C-ABI (include/fs_gpu.h) over the sm_100a kernels: renderer lifecycle, table upload
+// with generation-number caching, kernel dispatch from runtime tags, result extraction.
+//
+// Mirrors the host half of the reference boundary (row a9 of SURVEY.md section 8):
+//   InitializeMemory  GPU_Render.cu:232-407      InitializePerturb  GPU_Render.cu:431-501
+//   ClearMemory       GPU_Render.cu:212-225      Render             GPU_Render.cu:617-847
+//   RenderPerturbLAv2 GPU_Render.cu:995-1188     RenderCurrent      GPU_Render.cu:556-581
+//   RunAntialiasing   GPU_Render.cu:1695-1757    ExtractItersAndColors GPU_Render.cu:1759-1805
+//   table upload      Perturb.cuh:20-80, GPU_LAReference.h:78-162
+#include "../../include/fs_gpu.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "fs_direct.cuh"
+#include "fs_lav2.cuh"
+#include "fs_post.cuh"
+
+using namespace fs;
+
+namespace {
+
+constexpr uint32_t NB_THREADS_W = 16; // GPU_Render.h:116-120
+constexpr uint32_t NB_THREADS_H = 8;
+
+// ---- reference wire layouts (natural alignment reproduces the reference structs; sizes asserted) ----
+template <class Num, class IterT> struct WireLA {
+    typename Num::Cplx Ref, ZCoeff, CCoeff;
+    typename Num::Real LAThreshold, LAThresholdC, MinMag;
+    IterT StepLength, NextStageLAIndex;
+};
+template <class Num, class IterT> struct WireAT {
+    IterT StepLength;
+    typename Num::Real ThresholdC, SqrEscapeRadius;
+    typename Num::Cplx RefC, ZCoeff, CCoeff, InvZCoeff, CCoeffSqrInvZCoeff, CCoeffInvZCoeff;
+    typename Num::Real CCoeffNormSqr, RefCNormSqr, factor;
+};
+// sizes measured from the reference headers with nvcc 12.9
+static_assert(sizeof(WireLA<NumHdr<float>, uint32_t>) == 68 && sizeof(WireLA<NumHdr<float>, uint64_t>) == 80, "LAInfoDeep");
+static_assert(sizeof(WireLA<NumPlain<float>, uint32_t>) == 44 && sizeof(WireLA<NumPlain<float>, uint64_t>) == 56, "LAInfoDeep");
+static_assert(sizeof(WireLA<NumPlain<double>, uint32_t>) == 80 && sizeof(WireLA<NumPlain<double>, uint64_t>) == 88, "LAInfoDeep");
+static_assert(sizeof(WireLA<NumHdr<double>, uint32_t>) == 128 && sizeof(WireLA<NumHdr<double>, uint64_t>) == 136, "LAInfoDeep");
+static_assert(sizeof(WireAT<NumHdr<float>, uint32_t>) == 116 && sizeof(WireAT<NumHdr<float>, uint64_t>) == 120, "ATInfo");
+static_assert(sizeof(WireAT<NumPlain<float>, uint32_t>) == 72 && sizeof(WireAT<NumPlain<float>, uint64_t>) == 80, "ATInfo");
+static_assert(sizeof(WireAT<NumPlain<double>, uint32_t>) == 144 && sizeof(WireAT<NumHdr<double>, uint32_t>) == 232, "ATInfo");
+
+struct DeviceBlob {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct OrbitDev {
+    DeviceBlob data;
+    uint64_t compressed = 0, uncompressed = 0, period = 0;
+    int numeric = -1, pextras = 0;
+    uint64_t generation = 0;
+    bool valid = false;
+};
+
+struct LaDev {
+    DeviceBlob las, stages;
+    uint64_t num_las = 0, num_stages = 0, stage_count = 0;
+    int use_at = 0, is_valid = 0;
+    int numeric = -1;
+    uint32_t iter_bytes = 0;
+    alignas(16) unsigned char at[256]; // AtDev<Num,IterT> image
+    bool present = false;
+};
+
+} // namespace
+
+struct fs_renderer {
+    int device = 0;
+    cudaStream_t compute = nullptr, display = nullptr;
+    void *iter_buf = nullptr;
+    Reduction *red_dev = nullptr;
+    Color16 *color_buf = nullptr;
+    Color16 *pal_dev = nullptr;
+    uint32_t pal_iters = 0, aux_depth = 0;
+    const void *cached_pal_host = nullptr;
+    uint64_t cached_pal_gen = 0;
+    uint32_t width = 0, height = 0, aa = 0, iter_bytes = 0;
+    uint32_t w_block = 0, h_block = 0, color_w = 0, color_h = 0;
+    size_t n_cu = 0, n_color_cu = 0;
+    uint32_t row_begin = 0, row_end = 0;
+    unsigned int *tile_counter = nullptr;
+    unsigned long long *step_counter = nullptr;
+    bool count_steps = false;
+    OrbitDev orbit1, orbit2;
+    LaDev la;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool timed = false;
+    uint64_t launches = 0;
+    int num_sms = 148;
+    fs_done_callback cb = nullptr;
+    void *cb_user = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void free_blob(fs_renderer *r, DeviceBlob &b) {
+    if (b.ptr) cudaFreeAsync(b.ptr, r->compute);
+    b.ptr = nullptr;
+    b.bytes = 0;
+}
+
+void reset_perturb(fs_renderer *r) {
+    free_blob(r, r->orbit1.data);
+    free_blob(r, r->orbit2.data);
+    r->orbit1 = OrbitDev{};
+    r->orbit2 = OrbitDev{};
+    free_blob(r, r->la.las);
+    free_blob(r, r->la.stages);
+    r->la = LaDev{};
+}
+
+void reset_buffers(fs_renderer *r) {
+    if (r->iter_buf) cudaFreeAsync(r->iter_buf, r->compute);
+    if (r->red_dev) cudaFreeAsync(r->red_dev, r->compute);
+    if (r->color_buf) cudaFreeAsync(r->color_buf, r->compute);
+    r->iter_buf = nullptr;
+    r->red_dev = nullptr;
+    r->color_buf = nullptr;
+}
+
+bool memory_initialized(const fs_renderer *r) { return r->iter_buf && r->red_dev && r->color_buf; }
+
+size_t orbit_elem_bytes(int numeric, int pextras) {
+    size_t base;
+    switch (numeric) {
+    case FS_NUM_F32: base = 8; break;
+    case FS_NUM_F64: base = 16; break;
+    case FS_NUM_2X32: base = 16; break;
+    case FS_NUM_HDR32: base = 16; break;
+    case FS_NUM_HDR64: base = 32; break;
+    case FS_NUM_HDR2X32: base = 24; break;
+    default: return 0;
+    }
+    // Bad / CompressionIndex prefix is 8 bytes (GPU_ReferenceIter.h:10-49)
+    return pextras == FS_PEXTRAS_DISABLE ? base : base + 8;
+}
+
+uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, uint64_t generation, const fs_orbit *src) {
+    const size_t eb = orbit_elem_bytes(numeric, pextras);
+    if (eb == 0) return FS_ERROR_UNSUPPORTED;
+    free_blob(r, dst.data);
+    dst = OrbitDev{};
+    const size_t bytes = eb * src->compressed_count;
+    cudaError_t err = cudaMallocAsync(&dst.data.ptr, bytes ? bytes : 16, r->compute);
+    if (err != cudaSuccess) return err;
+    dst.data.bytes = bytes;
+    err = cudaMemcpyAsync(dst.data.ptr, src->elements, bytes, cudaMemcpyDefault, r->compute);
+    if (err != cudaSuccess) return err;
+    dst.compressed = src->compressed_count;
+    dst.uncompressed = src->uncompressed_count;
+    dst.period = src->period_maybe_zero;
+    dst.numeric = numeric;
+    dst.pextras = pextras;
+    dst.generation = generation;
+    dst.valid = true;
+    return 0;
+}
+
+// Repack LAInfoDeep[] (reference layout) into 16-byte-aligned LaRec[] and ATInfo into AtDev.
+template <class Num, class IterT> uint32_t upload_la_typed(fs_renderer *r, const fs_la_reference *src) {
+    using W = WireLA<Num, IterT>;
+    using D = LaRec<Num, IterT>;
+    LaDev &la = r->la;
+    std::vector<D> host(src->num_las ? src->num_las : 1);
+    const unsigned char *p = static_cast<const unsigned char *>(src->las);
+    for (uint64_t i = 0; i < src->num_las; i++) {
+        W w;
+        memcpy(&w, p + i * sizeof(W), sizeof(W));
+        D d;
+        memset(&d, 0, sizeof(D));
+        d.Ref = w.Ref; d.ZCoeff = w.ZCoeff; d.CCoeff = w.CCoeff;
+        d.LAThreshold = w.LAThreshold; d.LAThresholdC = w.LAThresholdC;
+        d.StepLength = w.StepLength; d.NextStageLAIndex = w.NextStageLAIndex;
+        host[i] = d;
+    }
+    cudaError_t err = cudaMallocAsync(&la.las.ptr, host.size() * sizeof(D), r->compute);
+    if (err != cudaSuccess) return err;
+    la.las.bytes = host.size() * sizeof(D);
+    err = cudaMemcpyAsync(la.las.ptr, host.data(), la.las.bytes, cudaMemcpyHostToDevice, r->compute);
+    if (err != cudaSuccess) return err;
+    const size_t sbytes = (src->num_stages ? src->num_stages : 1) * sizeof(StageRec<IterT>);
+    err = cudaMallocAsync(&la.stages.ptr, sbytes, r->compute);
+    if (err != cudaSuccess) return err;
+    la.stages.bytes = sbytes;
+    if (src->num_stages) {
+        err = cudaMemcpyAsync(la.stages.ptr, src->stages, src->num_stages * sizeof(StageRec<IterT>), cudaMemcpyHostToDevice, r->compute);
+        if (err != cudaSuccess) return err;
+    }
+    // the staging vector must outlive the async copy (pageable source: the runtime stages it before
+    // returning, but be explicit)
+    err = cudaStreamSynchronize(r->compute);
+    if (err != cudaSuccess) return err;
+    AtDev<Num, IterT> at;
+    memset(&at, 0, sizeof(at));
+    if (src->at) {
+        WireAT<Num, IterT> w;
+        memcpy(&w, src->at, sizeof(w));
+        at.StepLength = w.StepLength; at.ThresholdC = w.ThresholdC; at.SqrEscapeRadius = w.SqrEscapeRadius;
+        at.RefC = w.RefC; at.CCoeff = w.CCoeff; at.InvZCoeff = w.InvZCoeff;
+    }
+    static_assert(sizeof(at) <= sizeof(la.at), "AT image");
+    memcpy(la.at, &at, sizeof(at));
+    la.num_las = src->num_las;
+    la.num_stages = src->num_stages;
+    la.stage_count = src->la_stage_count;
+    la.use_at = src->use_at && src->at;
+    la.is_valid = src->is_valid;
+    la.present = true;
+    return 0;
+}
+
+template <class F> uint32_t dispatch_num_iter(int numeric, uint32_t iter_bytes, F &&f) {
+    const bool u64 = iter_bytes == 8;
+    switch (numeric) {
+    case FS_NUM_F32: return u64 ? f(NumPlain<float>{}, uint64_t{}) : f(NumPlain<float>{}, uint32_t{});
+    case FS_NUM_F64: return u64 ? f(NumPlain<double>{}, uint64_t{}) : f(NumPlain<double>{}, uint32_t{});
+    case FS_NUM_HDR32: return u64 ? f(NumHdr<float>{}, uint64_t{}) : f(NumHdr<float>{}, uint32_t{});
+    case FS_NUM_HDR64: return u64 ? f(NumHdr<double>{}, uint64_t{}) : f(NumHdr<double>{}, uint32_t{});
+    default: return FS_ERROR_UNSUPPORTED;
+    }
+}
+
+uint32_t upload_la(fs_renderer *r, int numeric, uint32_t iter_bytes, const fs_la_reference *src) {
+    free_blob(r, r->la.las);
+    free_blob(r, r->la.stages);
+    r->la = LaDev{};
+    const uint32_t rc = dispatch_num_iter(numeric, iter_bytes, [&](auto num, auto it) -> uint32_t {
+        return upload_la_typed<decltype(num), decltype(it)>(r, src);
+    });
+    if (rc == 0) {
+        r->la.numeric = numeric;
+        r->la.iter_bytes = iter_bytes;
+    }
+    return rc;
+}
+
+// persistent grid: one 256-thread CTA per resident slot
+template <class K> int resident_ctas(fs_renderer *r, K kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * r->num_sms;
+}
+
+void begin_render(fs_renderer *r) {
+    cudaMemsetAsync(r->tile_counter, 0, sizeof(unsigned int), r->compute);
+    cudaEventRecord(r->ev_start, r->compute);
+}
+uint32_t end_render(fs_renderer *r) {
+    cudaEventRecord(r->ev_stop, r->compute);
+    r->timed = true;
+    r->launches++;
+    return cudaGetLastError();
+}
+
+void rows(const fs_renderer *r, int &b, int &e) {
+    if (r->row_end > r->row_begin) {
+        b = (int)r->row_begin;
+        e = (int)(r->row_end < r->height ? r->row_end : r->height);
+    } else {
+        b = 0;
+        e = (int)r->height;
+    }
+}
+
+template <class T> T load_pod(const void *p) {
+    T v;
+    memcpy(&v, p, sizeof(T));
+    return v;
+}
+
+template <class Num, class IterT>
+uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, const void *cx, const void *cy, uint64_t n_iter) {
+    using Real = typename Num::Real;
+    Lav2Args<Num, IterT> A;
+    memset(&A, 0, sizeof(A));
+    A.out = static_cast<IterT *>(r->iter_buf);
+    A.orbit = r->orbit1.data.ptr;
+    A.orbit_count = (IterT)r->orbit1.uncompressed;
+    const bool have_la = r->la.present && r->la.numeric == r->orbit1.numeric && r->la.iter_bytes == sizeof(IterT);
+    if (have_la) {
+        A.las = static_cast<const LaRec<Num, IterT> *>(r->la.las.ptr);
+        A.stages = static_cast<const StageRec<IterT> *>(r->la.stages.ptr);
+        memcpy(&A.at, r->la.at, sizeof(A.at));
+        A.la_stage_count = (IterT)r->la.stage_count;
+        A.la_valid = r->la.is_valid;
+        A.use_at = r->la.use_at;
+    }
+    A.width = (int)r->width;
+    A.height = (int)r->height;
+    A.pitch = (int)(r->w_block * NB_THREADS_W);
+    rows(r, A.row_begin, A.row_end);
+    A.dx = load_pod<Real>(dx);
+    A.dy = load_pod<Real>(dy);
+    A.centerX = load_pod<Real>(cx);
+    A.centerY = load_pod<Real>(cy);
+    A.n_iterations = (IterT)n_iter;
+    A.tile_counter = r->tile_counter;
+    A.step_counter = r->count_steps ? r->step_counter : nullptr;
+    begin_render(r);
+    switch (mode) {
+    case FS_LAV2_FULL: {
+        auto k = lav2_kernel<Num, IterT, Lav2Mode::Full>;
+        k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A);
+    } break;
+    case FS_LAV2_PO: {
+        auto k = lav2_kernel<Num, IterT, Lav2Mode::PO>;
+        k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A);
+    } break;
+    case FS_LAV2_LAO: {
+        auto k = lav2_kernel<Num, IterT, Lav2Mode::LAO>;
+        k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A);
+    } break;
+    default: return FS_ERROR_UNSUPPORTED;
+    }
+    return end_render(r);
+}
+
+template <class M, class IterT, int P>
+void launch_direct_p(fs_renderer *r, const DirectArgs<M, IterT> &A) {
+    auto k = direct_kernel<M, IterT, P>;
+    k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A);
+}
+
+template <class M, class IterT>
+uint32_t launch_direct(fs_renderer *r, const void *cx, const void *cy, const void *dx, const void *dy, uint64_t n_iter, int prec) {
+    // the reference launches nothing for precisions other than 1/4/8/16 (GPU_Render.cu:633-668)
+    if (prec != 1 && prec != 4 && prec != 8 && prec != 16) return 0;
+    DirectArgs<M, IterT> A;
+    memset(&A, 0, sizeof(A));
+    A.out = static_cast<IterT *>(r->iter_buf);
+    A.width = (int)r->width;
+    A.height = (int)r->height;
+    A.pitch = (int)(r->w_block * NB_THREADS_W);
+    rows(r, A.row_begin, A.row_end);
+    A.cx = load_pod<M>(cx); A.cy = load_pod<M>(cy); A.dx = load_pod<M>(dx); A.dy = load_pod<M>(dy);
+    A.n_iterations = (IterT)n_iter;
+    A.tile_counter = r->tile_counter;
+    A.step_counter = r->count_steps ? r->step_counter : nullptr;
+    begin_render(r);
+    switch (prec) {
+    case 1: launch_direct_p<M, IterT, 1>(r, A); break;
+    case 4: launch_direct_p<M, IterT, 4>(r, A); break;
+    case 8: launch_direct_p<M, IterT, 8>(r, A); break;
+    default: launch_direct_p<M, IterT, 16>(r, A); break;
+    }
+    return end_render(r);
+}
+
+template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaStream_t stream) {
+    reduction_init_kernel<IterT><<<1, 1, 0, stream>>>(r->red_dev);
+    const int pitch = (int)(r->w_block * NB_THREADS_W);
+    const int grid = r->num_sms * 8;
+    const IterT *it = static_cast<const IterT *>(r->iter_buf);
+#define FS_POST(AA) post_kernel<IterT, AA><<<grid, 256, 0, stream>>>(it, pitch, r->color_buf, r->pal_dev, r->pal_iters, r->aux_depth, (int)r->color_w, (int)r->color_h, (IterT)n_iter, r->red_dev)
+    switch (r->aa) {
+    case 1: FS_POST(1); break;
+    case 2: FS_POST(2); break;
+    case 3: FS_POST(3); break;
+    default: FS_POST(4); break;
+    }
+#undef FS_POST
+    r->launches += 2;
+    return cudaGetLastError();
+}
+
+void CUDART_CB done_trampoline(void *p) {
+    fs_renderer *r = static_cast<fs_renderer *>(p);
+    if (r->cb) r->cb(r->cb_user);
+}
+
+} // namespace
+
+extern "C" {
+
+uint32_t fs_test_cuda_is_working(void) {
+    // GPU_Render.cu:100-123 (returns a bool-like value: 1 = working)
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return 0;
+    if (cudaSetDevice(0) != cudaSuccess) return 0;
+    if (cudaFree(nullptr) != cudaSuccess) return 0;
+    return 1;
+}
+
+fs_renderer *fs_create(int32_t device) {
+    fs_renderer *r = new (std::nothrow) fs_renderer();
+    if (r) r->device = device;
+    return r;
+}
+
+void fs_destroy(fs_renderer *r) {
+    if (!r) return;
+    DeviceGuard g(r->device);
+    if (r->compute) {
+        reset_perturb(r);
+        reset_buffers(r);
+        if (r->pal_dev) cudaFreeAsync(r->pal_dev, r->compute);
+        if (r->tile_counter) cudaFreeAsync(r->tile_counter, r->compute);
+        if (r->step_counter) cudaFreeAsync(r->step_counter, r->compute);
+        cudaStreamSynchronize(r->compute);
+        cudaStreamDestroy(r->compute);
+        if (r->display) cudaStreamDestroy(r->display);
+        if (r->ev_start) cudaEventDestroy(r->ev_start);
+        if (r->ev_stop) cudaEventDestroy(r->ev_stop);
+    }
+    delete r;
+}
+
+uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, uint32_t h, uint32_t antialiasing,
+                              const fs_color16 *pal, uint32_t pal_iters, uint32_t aux_depth, uint64_t pal_gen,
+                              int32_t expected_reuse) {
+    if (!r || (iter_bytes != 4 && iter_bytes != 8)) return FS_ERROR_UNSUPPORTED;
+    cudaError_t err = cudaSetDevice(r->device);
+    if (err != cudaSuccess) return err;
+    r->aux_depth = aux_depth;
+    if (!r->compute) {
+        int lo, hi;
+        err = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (err != cudaSuccess) return err;
+        err = cudaStreamCreateWithPriority(&r->compute, cudaStreamNonBlocking, lo);
+        if (err != cudaSuccess) return err;
+        err = cudaStreamCreateWithPriority(&r->display, cudaStreamNonBlocking, hi);
+        if (err != cudaSuccess) return err;
+        cudaEventCreate(&r->ev_start);
+        cudaEventCreate(&r->ev_stop);
+        cudaDeviceGetAttribute(&r->num_sms, cudaDevAttrMultiProcessorCount, r->device);
+        err = cudaMallocAsync(&r->tile_counter, sizeof(unsigned int), r->compute);
+        if (err != cudaSuccess) return err;
+        err = cudaMallocAsync(&r->step_counter, sizeof(unsigned long long), r->compute);
+        if (err != cudaSuccess) return err;
+        cudaMemsetAsync(r->step_counter, 0, sizeof(unsigned long long), r->compute);
+    }
+    if (r->cached_pal_host != pal || r->cached_pal_gen != pal_gen) {
+        if (r->pal_dev) cudaFreeAsync(r->pal_dev, r->compute);
+        r->pal_dev = nullptr;
+        r->pal_iters = pal_iters;
+        r->cached_pal_host = pal;
+        err = cudaMallocAsync(&r->pal_dev, (pal_iters ? pal_iters : 1) * sizeof(Color16), r->compute);
+        if (err != cudaSuccess) return err;
+        if (pal && pal_iters) {
+            err = cudaMemcpyAsync(r->pal_dev, pal, pal_iters * sizeof(Color16), cudaMemcpyHostToDevice, r->compute);
+            if (err != cudaSuccess) return err;
+        }
+        r->cached_pal_gen = pal_gen;
+    }
+    if (r->width == w && r->height == h && r->aa == antialiasing && r->iter_bytes == iter_bytes && expected_reuse)
+        return 0;
+    if (antialiasing > 4 || antialiasing < 1) return FS_ERROR_3_BAD_ANTIALIASING;
+    if (w % antialiasing != 0) return FS_ERROR_4_WIDTH_NOT_MULTIPLE_OF_AA;
+    if (h % antialiasing != 0) return FS_ERROR_5_HEIGHT_NOT_MULTIPLE_OF_AA;
+
+    r->w_block = w / NB_THREADS_W + (w % NB_THREADS_W != 0);
+    r->h_block = h / NB_THREADS_H + (h % NB_THREADS_H != 0);
+    r->width = w;
+    r->height = h;
+    r->aa = antialiasing;
+    r->iter_bytes = iter_bytes;
+    r->n_cu = (size_t)r->w_block * NB_THREADS_W * r->h_block * NB_THREADS_H;
+    r->color_w = w / antialiasing;
+    r->color_h = h / antialiasing;
+    const uint32_t wcb = r->color_w / NB_THREADS_W + (r->color_w % NB_THREADS_W != 0);
+    const uint32_t hcb = r->color_h / NB_THREADS_H + (r->color_h % NB_THREADS_H != 0);
+    r->n_color_cu = (size_t)wcb * NB_THREADS_W * hcb * NB_THREADS_H;
+    r->row_begin = r->row_end = 0;
+
+    // geometry change drops cached orbit/LA uploads (ResetPerturb::Yes, GPU_Render.cu:358)
+    reset_perturb(r);
+    reset_buffers(r);
+    err = cudaMallocAsync(&r->iter_buf, r->n_cu * iter_bytes, r->compute);
+    if (err != cudaSuccess) return err;
+    err = cudaMallocAsync(&r->red_dev, sizeof(Reduction), r->compute);
+    if (err != cudaSuccess) return err;
+    err = cudaMallocAsync(&r->color_buf, r->n_color_cu * sizeof(Color16), r->compute);
+    if (err != cudaSuccess) return err;
+    fs_clear_memory(r);
+    return 0;
+}
+
+uint32_t fs_initialize_perturb(fs_renderer *r, uint32_t iter_bytes, int32_t numeric1, int32_t pextras,
+                               uint64_t generation1, const fs_orbit *perturb1, int32_t numeric2, uint64_t generation2,
+                               const fs_orbit *perturb2, const fs_la_reference *la) {
+    if (!r || !r->compute) return FS_ERROR_6_NO_ORBIT;
+    DeviceGuard g(r->device);
+    bool install_la = false;
+    const uint64_t have1 = r->orbit1.valid ? r->orbit1.generation : 0;
+    const uint64_t have2 = r->orbit2.valid ? r->orbit2.generation : 0;
+    if (generation1 != have1 || generation2 != have2) reset_perturb(r);
+    if (generation1 != (r->orbit1.valid ? r->orbit1.generation : 0)) {
+        if (!perturb1) return FS_ERROR_6_NO_ORBIT;
+        const uint32_t rc = upload_orbit(r, r->orbit1, numeric1, pextras, generation1, perturb1);
+        if (rc) return rc;
+        install_la = true;
+    }
+    if (generation2 != (r->orbit2.valid ? r->orbit2.generation : 0)) {
+        if (!perturb2) return FS_ERROR_6_NO_ORBIT;
+        const uint32_t rc = upload_orbit(r, r->orbit2, numeric2, pextras, generation2, perturb2);
+        if (rc) return rc;
+        install_la = true;
+    }
+    if (install_la && la) {
+        const uint32_t rc = upload_la(r, numeric1, iter_bytes, la);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+void fs_clear_memory(fs_renderer *r) {
+    if (!r || !r->compute) return;
+    DeviceGuard g(r->device);
+    if (r->iter_buf) cudaMemsetAsync(r->iter_buf, 0, r->n_cu * r->iter_bytes, r->compute);
+    if (r->red_dev) cudaMemsetAsync(r->red_dev, 0, r->iter_bytes, r->compute);
+    if (r->color_buf) cudaMemsetAsync(r->color_buf, 0, r->n_color_cu * sizeof(Color16), r->compute);
+}
+
+uint32_t fs_render(fs_renderer *r, uint32_t algorithm, int32_t numeric, const void *cx, const void *cy,
+                   const void *dx, const void *dy, uint64_t n_iterations, int32_t iteration_precision) {
+    (void)algorithm;
+    if (!r || !memory_initialized(r)) return 0; // GPU_Render.cu:626-628
+    DeviceGuard g(r->device);
+    const bool u64 = r->iter_bytes == 8;
+    switch (numeric) {
+    case FS_NUM_F32:
+        return u64 ? launch_direct<float, uint64_t>(r, cx, cy, dx, dy, n_iterations, iteration_precision)
+                   : launch_direct<float, uint32_t>(r, cx, cy, dx, dy, n_iterations, iteration_precision);
+    case FS_NUM_F64:
+        return u64 ? launch_direct<double, uint64_t>(r, cx, cy, dx, dy, n_iterations, iteration_precision)
+                   : launch_direct<double, uint32_t>(r, cx, cy, dx, dy, n_iterations, iteration_precision);
+    default: return FS_ERROR_UNSUPPORTED;
+    }
+}
+
+uint32_t fs_render_perturb_lav2(fs_renderer *r, uint32_t algorithm, int32_t numeric, int32_t mode, int32_t pextras,
+                                const void *cx, const void *cy, const void *dx, const void *dy, const void *center_x,
+                                const void *center_y, uint64_t n_iterations) {
+    (void)algorithm; (void)cx; (void)cy;
+    if (!r || !memory_initialized(r)) return 0; // GPU_Render.cu:1007-1009
+    DeviceGuard g(r->device);
+    if (!r->orbit1.valid || r->orbit1.numeric != numeric || r->orbit1.pextras != pextras) return FS_ERROR_6_NO_ORBIT;
+    if (pextras != FS_PEXTRAS_DISABLE) return FS_ERROR_UNSUPPORTED;
+    return dispatch_num_iter(numeric, r->iter_bytes, [&](auto num, auto it) -> uint32_t {
+        return launch_lav2<decltype(num), decltype(it)>(r, mode, dx, dy, center_x, center_y, n_iterations);
+    });
+}
+
+uint32_t fs_render_perturb_bla(fs_renderer *r, uint32_t algorithm, int32_t numeric, const fs_orbit *results,
+                               const fs_blas *blas, const void *cx, const void *cy, const void *dx, const void *dy,
+                               const void *center_x, const void *center_y, uint64_t n_iterations,
+                               int32_t iteration_precision) {
+    (void)algorithm; (void)numeric; (void)results; (void)blas; (void)cx; (void)cy; (void)dx; (void)dy;
+    (void)center_x; (void)center_y; (void)n_iterations; (void)iteration_precision;
+    if (!r || !memory_initialized(r)) return 0;
+    return FS_ERROR_UNSUPPORTED;
+}
+
+uint32_t fs_render_perturb_bla_scaled(fs_renderer *r, uint32_t algorithm, int32_t numeric,
+                                      const fs_orbit *double_perturb, const fs_orbit *float_perturb, const void *cx,
+                                      const void *cy, const void *dx, const void *dy, const void *center_x,
+                                      const void *center_y, uint64_t n_iterations, int32_t iteration_precision) {
+    (void)algorithm; (void)numeric; (void)double_perturb; (void)float_perturb; (void)cx; (void)cy; (void)dx; (void)dy;
+    (void)center_x; (void)center_y; (void)n_iterations; (void)iteration_precision;
+    if (!r || !memory_initialized(r)) return 0;
+    return FS_ERROR_UNSUPPORTED;
+}
+
+uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buffer, fs_color16 *color_buffer,
+                           fs_reduction *reduction_results, int32_t progressive) {
+    if (!r || !memory_initialized(r)) return 0; // GPU_Render.cu:563-565
+    DeviceGuard g(r->device);
+    cudaStream_t stream = progressive ? r->display : r->compute;
+    uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream) : run_post<uint32_t>(r, n_iterations, stream);
+    if (rc) return rc;
+    cudaError_t err = cudaSuccess;
+    if (iter_buffer) {
+        err = cudaMemcpyAsync(iter_buffer, r->iter_buf, r->n_cu * r->iter_bytes, cudaMemcpyDefault, stream);
+        if (err != cudaSuccess) return err;
+    }
+    if (color_buffer) {
+        err = cudaMemcpyAsync(color_buffer, r->color_buf, r->n_color_cu * sizeof(Color16), cudaMemcpyDefault, stream);
+        if (err != cudaSuccess) return err;
+    }
+    if (reduction_results) {
+        err = cudaMemcpyAsync(reduction_results, r->red_dev, sizeof(Reduction), cudaMemcpyDefault, stream);
+        if (err != cudaSuccess) return err;
+    }
+    return 0;
+}
+
+uint32_t fs_sync_compute_stream(fs_renderer *r) { DeviceGuard g(r->device); return cudaStreamSynchronize(r->compute); }
+uint32_t fs_sync_display_stream(fs_renderer *r) { DeviceGuard g(r->device); return cudaStreamSynchronize(r->display); }
+uint32_t fs_query_compute_stream(fs_renderer *r) { DeviceGuard g(r->device); return cudaStreamQuery(r->compute); }
+
+uint32_t fs_enqueue_compute_done_callback(fs_renderer *r, fs_done_callback fn, void *user) {
+    DeviceGuard g(r->device);
+    r->cb = fn;
+    r->cb_user = user;
+    return cudaLaunchHostFunc(r->compute, done_trampoline, r);
+}
+
+const char *fs_convert_error_to_string(uint32_t err) {
+    // GPU_Render.cu:1820-1823 forwards everything to cudaGetErrorString; FractalSharkError values get names here.
+    switch (err) {
+    case FS_ERROR_3_BAD_ANTIALIASING: return "FractalSharkError 10002: antialiasing must be 1..4";
+    case FS_ERROR_4_WIDTH_NOT_MULTIPLE_OF_AA: return "FractalSharkError 10003: width not a multiple of antialiasing";
+    case FS_ERROR_5_HEIGHT_NOT_MULTIPLE_OF_AA: return "FractalSharkError 10004: height not a multiple of antialiasing";
+    case FS_ERROR_6_NO_ORBIT: return "FractalSharkError 10005: no reference orbit uploaded for this type";
+    case FS_ERROR_7_NO_LA: return "FractalSharkError 10006: no LA reference uploaded for this type";
+    case FS_ERROR_UNSUPPORTED: return "fs_gpu: unsupported numeric/extras/iteration-width combination";
+    default: return cudaGetErrorString(static_cast<cudaError_t>(err));
+    }
+}
+
+uint32_t fs_get_width(const fs_renderer *r) { return r->width; }
+uint32_t fs_get_height(const fs_renderer *r) { return r->height; }
+
+uint32_t fs_set_row_range(fs_renderer *r, uint32_t row_begin, uint32_t row_end) {
+    r->row_begin = row_begin;
+    r->row_end = row_end;
+    return 0;
+}
+
+uint32_t fs_last_render_ms(fs_renderer *r, float *ms) {
+    if (!r || !r->timed) return cudaErrorNotReady;
+    DeviceGuard g(r->device);
+    cudaError_t err = cudaEventSynchronize(r->ev_stop);
+    if (err != cudaSuccess) return err;
+    return cudaEventElapsedTime(ms, r->ev_start, r->ev_stop);
+}
+
+uint32_t fs_enable_step_counter(fs_renderer *r, int32_t enable) {
+    if (!r || !r->compute) return FS_ERROR_UNSUPPORTED;
+    DeviceGuard g(r->device);
+    r->count_steps = enable != 0;
+    return cudaMemsetAsync(r->step_counter, 0, sizeof(unsigned long long), r->compute);
+}
+
+uint32_t fs_read_step_counter(fs_renderer *r, uint64_t *steps) {
+    if (!r || !r->compute) return FS_ERROR_UNSUPPORTED;
+    DeviceGuard g(r->device);
+    unsigned long long v = 0;
+    cudaError_t err = cudaMemcpyAsync(&v, r->step_counter, sizeof(v), cudaMemcpyDeviceToHost, r->compute);
+    if (err != cudaSuccess) return err;
+    err = cudaStreamSynchronize(r->compute);
+    *steps = v;
+    return err;
+}
+
+void *fs_device_iter_buffer(fs_renderer *r) { return r ? r->iter_buf : nullptr; }
+uint64_t fs_kernel_launch_count(const fs_renderer *r) { return r ? r->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,76 @@
+// fs_direct.cuh -- direct (non-perturbed) escape-time kernels, row a6 of SURVEY.md section 8.
+//
+// What: FractalSharkGpuLib/LowPrecisionKernels.cuh:290-382 (mandel_1x_double) and :680-790
+// (mandel_1x_float): z <- z^2 + c with round-down FMAs, P iterations per bailout test,
+// n_iterations -= P-1, output row flipped (Y -> height-Y-1).  Rounding sequence as compiled for the
+// reference (sm_100a SASS): x0 = fma(X, dx, cx); per step  t = fma_rd(-y, y, x0);
+// y' = fma_rd(x+x, y, y0); x' = fma_rd(x, x, t); bailout on fma(x, x, y*y) < 4.
+//
+// How: same persistent warp-tile queue as the perturbation kernel (fs_lav2.cuh).
+#pragma once
+#include "fs_types.cuh"
+
+namespace fs {
+
+template <class M> struct DirectOps;
+template <> struct DirectOps<float> {
+    FS_D static float fma_rd(float a, float b, float c) { return __fmaf_rd(a, b, c); }
+    FS_D static float from_int(int x) { return (float)x; }
+};
+template <> struct DirectOps<double> {
+    FS_D static double fma_rd(double a, double b, double c) { return __fma_rd(a, b, c); }
+    FS_D static double from_int(int x) { return (double)x; }
+};
+
+template <class M, class IterT> struct DirectArgs {
+    IterT *out;
+    int width, height, pitch;
+    int row_begin, row_end;
+    M cx, cy, dx, dy;
+    IterT n_iterations;
+    unsigned int *tile_counter;
+    unsigned long long *step_counter;
+};
+
+template <class M, class IterT, int P>
+__global__ void __launch_bounds__(256) direct_kernel(const DirectArgs<M, IterT> A) {
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = (A.width + 7) >> 3;
+    const int tiles_y = (A.row_end - A.row_begin + 3) >> 2;
+    const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    const IterT n_iter = A.n_iterations - (IterT)(P - 1);
+    unsigned long long steps = 0;
+
+    for (;;) {
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(A.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const int X = (int)(tile % tiles_x) * 8 + (lane & 7);
+        const int Y = A.row_begin + (int)(tile / tiles_x) * 4 + (lane >> 3);
+        if (X >= A.width || Y >= A.row_end) continue;
+
+        const M x0 = fma_(DirectOps<M>::from_int(X), A.dx, A.cx);
+        const M y0 = fma_(DirectOps<M>::from_int(Y), A.dy, A.cy);
+        M x = 0, y = 0;
+        IterT iter = 0;
+        while (fma_(x, x, y * y) < M(4) && iter < n_iter) {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const M x2 = x + x;
+                const M t = DirectOps<M>::fma_rd(-y, y, x0);
+                y = DirectOps<M>::fma_rd(x2, y, y0);
+                x = DirectOps<M>::fma_rd(x, x, t);
+            }
+            iter += P;
+        }
+        steps += iter;
+        A.out[(size_t)(A.height - Y - 1) * A.pitch + X] = iter;
+    }
+    if (A.step_counter) {
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if (lane == 0 && steps) atomicAdd(A.step_counter, steps);
+    }
+}
+
+} // namespace fs

@@ -1,0 +1,244 @@
+// fs_lav2.cuh -- the perturbation + LAv2 render kernel (row a1/a2/a3 of SURVEY.md section 8).
+//
+// Algorithm (what): FractalSharkGpuLib/LAKernel.cuh:3-315 -- AT shortcut, multi-stage LA skipping,
+// then plain perturbation with rebasing; table access per FractalSharkLib/GPU_LAReference.h:241-303,
+// GPU_LAInfoDeep.h:90-123, HpSharkFloatLib/ATInfo.h:155-188, FractalSharkGpuLib/Perturb.cuh:146-232.
+//
+// Execution (how, B200-first): a persistent grid of warps (SM count x resident warps) pulls 8x4-pixel
+// tiles from an atomic queue, so escape-count divergence costs at most one warp-tile, never a wave
+// tail; LA records and orbit elements are repacked to 16-byte-aligned records and fetched with
+// 128-bit loads; all exponent alignment is integer ALU work (no MUFU).  The reference launches one
+// 16x8 CTA per screen block with 32-bit field loads and scalbnf-based alignment.
+#pragma once
+#include "fs_num.cuh"
+
+namespace fs {
+
+enum class Lav2Mode : int { Full = 1, PO = 2, LAO = 3 }; // RenderAlgorithm.h:12-17
+
+// ---- device-side table records (our own layout; filled by the upload code in fs_capi.cu) ------
+template <class Num, class IterT> struct alignas(16) LaRec {
+    typename Num::Cplx Ref;
+    typename Num::Cplx ZCoeff;
+    typename Num::Cplx CCoeff;
+    typename Num::Real LAThreshold;
+    typename Num::Real LAThresholdC;
+    IterT StepLength;
+    IterT NextStageLAIndex;
+};
+
+template <class IterT> struct StageRec {
+    IterT LAIndex;
+    IterT MacroItCount;
+};
+
+template <class Num, class IterT> struct AtDev {
+    IterT StepLength;
+    typename Num::Real ThresholdC;
+    typename Num::Real SqrEscapeRadius;
+    typename Num::Cplx RefC;
+    typename Num::Cplx CCoeff;
+    typename Num::Cplx InvZCoeff;
+};
+
+template <class Num, class IterT> struct Lav2Args {
+    IterT *out;              // iteration buffer, row pitch = roundup16(width)
+    const void *orbit;       // reference-layout orbit elements (GPU_ReferenceIter.h:119-125)
+    IterT orbit_count;       // uncompressed entries
+    const LaRec<Num, IterT> *las;
+    const StageRec<IterT> *stages;
+    AtDev<Num, IterT> at;
+    IterT la_stage_count;
+    int la_valid;
+    int use_at;
+    int width, height, pitch;
+    int row_begin, row_end;  // rows [row_begin,row_end) rendered by this device (multi-GPU sharding)
+    typename Num::Real dx, dy, centerX, centerY;
+    IterT n_iterations;
+    unsigned int *tile_counter;
+    unsigned long long *step_counter; // optional: executed perturbation/LA/AT steps (bench roofline)
+};
+
+// ---- orbit element fetch ----------------------------------------------------------------------
+template <class Num> struct OrbitIO;
+
+template <> struct OrbitIO<NumPlain<float>> {
+    static constexpr int kBytes = 8;
+    FS_D static void load(const void *base, uint64_t i, float &x, float &y) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(base) + i);
+        x = v.x; y = v.y;
+    }
+};
+template <> struct OrbitIO<NumPlain<double>> {
+    static constexpr int kBytes = 16;
+    FS_D static void load(const void *base, uint64_t i, double &x, double &y) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(base) + i);
+        x = v.x; y = v.y;
+    }
+};
+// HDRx32 element = {x.mant, x.exp, y.exp, y.mant}: x Left-order, y Right-order. One LDG.128.
+template <> struct OrbitIO<NumHdr<float>> {
+    static constexpr int kBytes = 16;
+    FS_D static void load(const void *base, uint64_t i, Hdr<float> &x, Hdr<float> &y) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base) + i);
+        x.m = __uint_as_float(v.x); x.e = (int)v.y;
+        y.e = (int)v.z; y.m = __uint_as_float(v.w);
+    }
+};
+// HDR-double element (32 B) = {x.mant f64, x.exp, pad | y.exp, pad, y.mant f64}. Two LDG.128.
+template <> struct OrbitIO<NumHdr<double>> {
+    static constexpr int kBytes = 32;
+    FS_D static void load(const void *base, uint64_t i, Hdr<double> &x, Hdr<double> &y) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(base) + 2 * i;
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        x.m = __hiloint2double((int)a.y, (int)a.x); x.e = (int)a.z;
+        y.e = (int)b.x; y.m = __hiloint2double((int)b.w, (int)b.z);
+    }
+};
+
+// ---- small vocabulary shims so the kernel reads the same for plain and HDR numbers ------------
+template <class Num> FS_D bool c_is_ge(typename Num::Real a, typename Num::Real b) { return ge_pr(a, b); }
+
+template <class Num, class IterT, Lav2Mode Mode>
+__global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A) {
+    using Real = typename Num::Real;
+    using Cplx = typename Num::Cplx;
+    using LA = LaRec<Num, IterT>;
+
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = (A.width + 7) >> 3;
+    const int tiles_y = (A.row_end - A.row_begin + 3) >> 2;
+    const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    unsigned long long steps = 0;
+
+    for (;;) {
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(A.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+
+        const int X = (int)(tile % tiles_x) * 8 + (lane & 7);
+        const int Y = A.row_begin + (int)(tile / tiles_x) * 4 + (lane >> 3);
+        if (X >= A.width || Y >= A.row_end) continue;
+
+        IterT iter = 0;
+        IterT RefIteration = 0;
+        // LAKernel.cuh:41-42 (no reduction of the deltas here)
+        const Real dcX = sub(mul(A.dx, Num::from_int(X)), A.centerX);
+        const Real dcY = sub(mul(Num::neg(A.dy), Num::from_int(Y)), A.centerY);
+        const Cplx dc = Num::c_make(dcX, dcY);
+        Cplx dz = Num::c_zero();
+
+        if constexpr (Mode == Lav2Mode::Full || Mode == Lav2Mode::LAO) {
+            // ---- AT (ATInfo.h:128-188) ----
+            if (A.la_valid && A.use_at && le_pr(cheb(dc), A.at.ThresholdC)) {
+                const IterT at_max = A.n_iterations / A.at.StepLength;
+                Cplx c = add(mul(dc, A.at.CCoeff), A.at.RefC);
+                reduce(c);
+                Cplx z = Num::c_zero();
+                IterT i = 0;
+                for (; i < at_max; i++) {
+                    // nvcc shares re*re / im*im between norm_squared and z*z in the reference build:
+                    //   nsq = rr + ii ; z2.re = rr - ii ; z2.im = fma(re, im, re*im)
+                    const auto rr = z.re * z.re;
+                    const auto ii = z.im * z.im;
+                    Real nsq;
+                    if constexpr (Num::kHdr) { nsq.m = rr + ii; nsq.e = z.e << 1; reduce(nsq); }
+                    else { nsq = rr + ii; }
+                    if (gt_pr(nsq, A.at.SqrEscapeRadius)) break;
+                    Cplx z2;
+                    z2.re = rr - ii;
+                    z2.im = fma_(z.re, z.im, z.re * z.im);
+                    if constexpr (Num::kHdr) z2.e = imax(z.e + z.e, MIN_BIG);
+                    z = add(z2, c);
+                }
+                steps += i;
+                dz = mul(z, A.at.InvZCoeff);
+                reduce(dz);
+                iter = i * A.at.StepLength;
+            }
+
+            // ---- LA stages (LAKernel.cuh:91-127) ----
+            IterT stage = A.la_valid ? A.la_stage_count : 0;
+            while (stage > 0) {
+                stage--;
+                const IterT LAIndex = A.stages[stage].LAIndex;
+                // isLAStageInvalid  GPU_LAReference.h:241-255
+                if (ge_pr(cheb(dc), A.las[LAIndex].LAThresholdC)) continue;
+                const IterT MacroItCount = A.stages[stage].MacroItCount;
+                IterT j = RefIteration;
+
+                while (iter < A.n_iterations) {
+                    // getLA  GPU_LAReference.h:271-303
+                    const LA *rec = A.las + (LAIndex + j);
+                    const IterT l = rec->StepLength;
+                    bool unusable = true;
+                    Cplx newdz;
+                    if (iter + l <= A.n_iterations) {
+                        // Prepare  GPU_LAInfoDeep.h:90-105: newdz = dz * (2*Ref + dz), reduced
+                        newdz = mul(dz, add(Num::c_mul2(rec->Ref), dz));
+                        reduce(newdz);
+                        unusable = ge_pr(cheb(newdz), rec->LAThreshold);
+                    }
+                    if (unusable) {
+                        RefIteration = rec->NextStageLAIndex;
+                        break;
+                    }
+                    iter += l;
+                    steps++;
+                    // Evaluate  GPU_LAInfoDeep.h:120-123 ; getZ  LAstep.h:181-185
+                    dz = add(mul(newdz, rec->ZCoeff), mul(dc, rec->CCoeff));
+                    const Cplx z = add(rec[1].Ref, dz);
+                    j++;
+                    Real zn = cheb(z), dn = cheb(dz);
+                    reduce(zn);
+                    reduce(dn);
+                    if (lt_pr(zn, dn) || j >= MacroItCount) {
+                        dz = z;
+                        j = 0;
+                    }
+                }
+                if (iter >= A.n_iterations) break;
+            }
+        }
+
+        if constexpr (Mode == Lav2Mode::Full || Mode == Lav2Mode::PO) {
+            // ---- plain perturbation with rebasing (LAKernel.cuh:130-236) ----
+            Real dX = Num::c_re(dz), dY = Num::c_im(dz);
+            Real zx, zy;
+            OrbitIO<Num>::load(A.orbit, RefIteration, zx, zy);
+            const IterT last = A.orbit_count - 1;
+            for (;;) {
+                Num::perturb(dX, dY, zx, zy, dcX, dcY);
+                ++RefIteration;
+                OrbitIO<Num>::load(A.orbit, RefIteration, zx, zy);
+                const Real tX = add(zx, dX);
+                const Real tY = add(zy, dY);
+                const Real n2 = Num::norm2(tX, tY);
+                steps++;
+                if (lt_bailout(n2) && iter < A.n_iterations) {
+                    const Real d2 = Num::norm2(dX, dY);
+                    if (lt_pr(n2, d2) || RefIteration >= last) {
+                        dX = tX;
+                        dY = tY;
+                        RefIteration = 0;
+                        OrbitIO<Num>::load(A.orbit, 0, zx, zy);
+                    }
+                    ++iter;
+                } else {
+                    break;
+                }
+            }
+        }
+
+        A.out[(size_t)Y * A.pitch + X] = iter;
+    }
+
+    if (A.step_counter) {
+        // one atomic per warp
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if (lane == 0 && steps) atomicAdd(A.step_counter, steps);
+    }
+}
+
+} // namespace fs

@@ -1,0 +1,843 @@
+// fs_host.cpp -- host-side INPUT generation for the render path (libfshost.so): view coordinates,
+// the high-precision reference orbit and the LAv2 table, produced in the reference's wire layouts so
+// they can be handed to libfsgpu.so (or to the reference GPURenderer) unchanged.
+//
+// These are the callers' data formats either side of the hot path:
+//   coordinates  Fractal.cpp:1789-1844, 2831-2840 ; PointZoomBBConverter.cpp:271-312, 388-397
+//   orbit (ST)   RefOrbitCalc.cpp:415-647 ; PerturbationResults.cpp:812-868
+//   LA table     LAReference.cpp:28-207, 774-1074 ; LAInfoDeep.h:109-502 ; LAParameters.h:66-72
+// The reference builds these on the host with GMP + un-fused IEEE arithmetic (x86-64 baseline has no
+// FMA), so everything here is plain C++ compiled without -mfma; nothing in this file runs on the GPU.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../fs_types.cuh"
+#include "fs_gmp_min.h"
+
+using namespace fs;
+
+namespace {
+
+// --------------------------------------------------------------------------------------------
+// host numeric policies (un-fused)
+// --------------------------------------------------------------------------------------------
+template <class M> Hdr<M> h_from_mant(M mant) { // explicit HDRFloat(T mant): exp 0, Reduce (HDRFloat.h:206-212)
+    Hdr<M> r; r.m = mant; r.e = 0; reduce(r); return r;
+}
+template <class M> Hdr<M> h_from_int(int v) { return hdr_from<M>((M)v); } // HDRFloat(U number) (HDRFloat.h:295-325)
+template <class M> Hdr<M> h_mul_scalar(Hdr<M> a, M s) { return mul(a, h_from_mant<M>(s)); } // HDRFloat.h:853-868
+template <class M> Hdr<M> h_min_pr(Hdr<M> a, Hdr<M> b) { return cmp_pr(a, b) < 0 ? a : b; }
+
+template <class M> HdrC<M> hc_mul_unfused(HdrC<M> a, HdrC<M> b) { // HDRFloatComplex.h:267-283 on the host
+    HdrC<M> r;
+    r.re = (a.re * b.re) - (a.im * b.im);
+    r.im = (a.re * b.im) + (a.im * b.re);
+    r.e = imax(a.e + b.e, MIN_BIG);
+    return r;
+}
+template <class M> Hdr<M> hc_norm2_unfused(HdrC<M> a) { return hdr_make<M>(a.e << 1, a.re * a.re + a.im * a.im); }
+// plus_mutable(HDRFloat real)  HDRFloatComplex.h:350-382
+template <class M> HdrC<M> hc_add_real(HdrC<M> a, Hdr<M> real) {
+    const int d = a.e - real.e;
+    if (d >= EXP_DIFF_IGNORED) return a;
+    if (d >= 0) {
+        a.re = a.re + real.m * MT<M>::pow2(-d);
+    } else if (d > -EXP_DIFF_IGNORED) {
+        const M mulv = MT<M>::pow2(d);
+        a.e = real.e;
+        a.re = a.re * mulv + real.m;
+        a.im = a.im * mulv;
+    } else {
+        a.e = real.e;
+        a.re = real.m;
+        a.im = M(0);
+    }
+    return a;
+}
+// reciprocal  HDRFloatComplex.h:556-561
+template <class M> HdrC<M> hc_recip(HdrC<M> a) {
+    const M t = M(1.0f) / (a.re * a.re + a.im * a.im);
+    HdrC<M> r;
+    r.re = a.re * t;
+    r.im = -a.im * t;
+    r.e = imax(-a.e, MIN_BIG);
+    return r;
+}
+
+template <class M> struct HostHdr {
+    using Mant = M;
+    using Real = Hdr<M>;
+    using Cplx = HdrC<M>;
+    static constexpr bool kHdr = true;
+    static Real r_int(int v) { return h_from_int<M>(v); }
+    static Real r_scale(Real a, float s) { return h_mul_scalar<M>(a, (M)s); }
+    static Real r_mul(Real a, Real b) { return mul(a, b); }
+    static Real r_div(Real a, Real b) { return div(a, b); }
+    static Real r_min(Real a, Real b) { return h_min_pr(a, b); }
+    static int r_cmp(Real a, Real b) { return cmp_pr(a, b); }
+    static void r_reduce(Real &a) { reduce(a); }
+    static bool r_is_zero(Real a) { return a.m == M(0); }
+    static Cplx c_one() { Cplx c; c.re = M(1); c.im = M(0); c.e = 0; return c; }
+    static Cplx c_zero() { return hc_zero<M>(); }
+    static Cplx c_mul(Cplx a, Cplx b) { return hc_mul_unfused(a, b); }
+    static Cplx c_mul2(Cplx a) { return mul(a, hdr_make<M>(1, M(1))); }
+    static Cplx c_add(Cplx a, Cplx b) { return add(a, b); }
+    static Cplx c_add_one(Cplx a) { return hc_add_real(a, h_from_int<M>(1)); }
+    static void c_reduce(Cplx &a) { reduce(a); }
+    static Real c_cheb(Cplx a) { return cheb(a); }
+    static Real c_norm2(Cplx a) { return hc_norm2_unfused(a); }
+    static Cplx c_recip(Cplx a) { return hc_recip(a); }
+    static bool c_is_zero(Cplx a) { return a.re == M(0) && a.im == M(0); }
+    static Real at_lim(bool small_exp) {
+        Real lim = hdr_make<M>(32, M(1));
+        if (sizeof(M) == 8 && !small_exp) lim.e = 256; // LAInfoDeep.h:477-485
+        reduce(lim);
+        return lim;
+    }
+    static Real at_factor() { return hdr_from<M>((M)4294967296.0); } // ATInfo() ctor: HDRFloat(0x1.0p32)
+    static Real at_four() { return h_from_mant<M>(M(4.0f)); }
+    static Real r_square_reduced(Real a) { Real r = square(a); reduce(r); return r; }
+};
+
+template <class M> struct HostPlain {
+    using Mant = M;
+    using Real = M;
+    using Cplx = Cx<M>;
+    static constexpr bool kHdr = false;
+    static Real r_int(int v) { return (M)v; }
+    static Real r_scale(Real a, float s) { return a * (M)s; }
+    static Real r_mul(Real a, Real b) { return a * b; }
+    static Real r_div(Real a, Real b) { return a / b; }
+    static Real r_min(Real a, Real b) { return std::min(a, b); }
+    static int r_cmp(Real a, Real b) { return a > b ? 1 : (a < b ? -1 : 0); }
+    static void r_reduce(Real &) {}
+    static bool r_is_zero(Real a) { return a == M(0); }
+    static Cplx c_one() { Cplx c; c.re = M(1); c.im = M(0); return c; }
+    static Cplx c_zero() { Cplx c; c.re = M(0); c.im = M(0); return c; }
+    static Cplx c_mul(Cplx a, Cplx b) {
+        Cplx r;
+        r.re = (a.re * b.re) - (a.im * b.im);
+        r.im = (a.re * b.im) + (a.im * b.re);
+        return r;
+    }
+    static Cplx c_mul2(Cplx a) { a.re *= M(2); a.im *= M(2); return a; }
+    static Cplx c_add(Cplx a, Cplx b) { a.re += b.re; a.im += b.im; return a; }
+    static Cplx c_add_one(Cplx a) { a.re += M(1); return a; }
+    static void c_reduce(Cplx &) {}
+    static Real c_cheb(Cplx a) { const M x = fabs(a.re), y = fabs(a.im); return x > y ? x : y; }
+    static Real c_norm2(Cplx a) { return a.re * a.re + a.im * a.im; }
+    static Cplx c_recip(Cplx a) {
+        const M t = M(1) / (a.re * a.re + a.im * a.im);
+        Cplx r; r.re = a.re * t; r.im = -a.im * t; return r;
+    }
+    static bool c_is_zero(Cplx a) { return a.re == M(0) && a.im == M(0); }
+    static Real at_lim(bool) { return (M)4294967296.0f; }
+    static Real at_factor() { return (M)4294967296.0; }
+    static Real at_four() { return M(4); }
+    static Real r_square_reduced(Real a) { return a * a; }
+};
+
+// reference wire structs (same declarations as in fs_capi.cu; sizes asserted there)
+template <class N, class IterT> struct WireLA {
+    typename N::Cplx Ref, ZCoeff, CCoeff;
+    typename N::Real LAThreshold, LAThresholdC, MinMag;
+    IterT StepLength, NextStageLAIndex;
+};
+template <class N, class IterT> struct WireAT {
+    IterT StepLength;
+    typename N::Real ThresholdC, SqrEscapeRadius;
+    typename N::Cplx RefC, ZCoeff, CCoeff, InvZCoeff, CCoeffSqrInvZCoeff, CCoeffInvZCoeff;
+    typename N::Real CCoeffNormSqr, RefCNormSqr, factor;
+};
+template <class IterT> struct WireStage { IterT LAIndex, MacroItCount; };
+
+// LAParameters defaults (LAParameters.h:66-72): method 1, 2^-24, 2^-24, 2^-6, 2^-3, 2^-10, 2^-10
+struct LaParams {
+    float la_scale = ldexpf(1.f, -24), lac_scale = ldexpf(1.f, -24);
+    float stage0_thr2 = ldexpf(1.f, -6), thr2 = ldexpf(1.f, -3);
+};
+
+// --------------------------------------------------------------------------------------------
+// View
+// --------------------------------------------------------------------------------------------
+struct Mpf {
+    fs_mpf_t v;
+    explicit Mpf(unsigned long prec) { fs_mpf_init2(v, prec); }
+    Mpf(const Mpf &o) { fs_mpf_init2(v, (unsigned long)o.v->_mp_prec * 64); fs_mpf_set(v, o.v); }
+    Mpf &operator=(const Mpf &o) { fs_mpf_set(v, o.v); return *this; }
+    ~Mpf() { fs_mpf_clear(v); }
+};
+
+} // namespace
+
+struct fsh_view {
+    unsigned long prec;
+    Mpf minX, minY, maxX, maxY, cx, cy;
+    uint32_t w, h, aa;
+    explicit fsh_view(unsigned long p) : prec(p), minX(p), minY(p), maxX(p), maxY(p), cx(p), cy(p), w(0), h(0), aa(1) {}
+};
+
+struct fsh_orbit {
+    int numeric = 0;
+    std::vector<unsigned char> data;
+    uint64_t count = 0, period = 0;
+    size_t elem_bytes = 0;
+    unsigned char max_radius[16] = {0}; // Real, reduced
+    unsigned char x_low[16] = {0}, y_low[16] = {0};
+};
+
+struct fsh_la {
+    std::vector<unsigned char> las, stages, at;
+    uint64_t num_las = 0, num_stages = 0, stage_count = 0;
+    int use_at = 0, is_valid = 0;
+};
+
+namespace {
+
+// HDRFloat(mpf_t)  HDRFloat.h:366-389: mpf_get_d_2exp truncates, then the mantissa is cast to M
+template <class M> Hdr<M> hdr_from_mpf(const fs_mpf_struct *f) {
+    if (fs_mpf_sgn(f) == 0) return hdr_zero<M>();
+    long e = 0;
+    const double d = fs_mpf_get_d_2exp(&e, f);
+    Hdr<M> r;
+    r.m = (M)d;
+    r.e = (int32_t)e;
+    return r;
+}
+
+template <class N> struct FromMpf;
+template <class M> struct FromMpf<HostHdr<M>> {
+    static Hdr<M> raw(const fs_mpf_struct *f) { return hdr_from_mpf<M>(f); }
+    static Hdr<M> coord(const fs_mpf_struct *f) { Hdr<M> r = hdr_from_mpf<M>(f); reduce(r); return r; } // FillCoord
+};
+template <class M> struct FromMpf<HostPlain<M>> {
+    static M raw(const fs_mpf_struct *f) { return (M)fs_mpf_get_d(f); }
+    static M coord(const fs_mpf_struct *f) { return (M)fs_mpf_get_d(f); }
+};
+
+// orbit element writers: x Left-order, y Right-order for HDR (GPU_ReferenceIter.h:119-125)
+template <class N> struct ElemIO;
+template <class M> struct ElemIO<HostPlain<M>> {
+    static constexpr size_t kBytes = 2 * sizeof(M);
+    static void put(unsigned char *p, M x, M y) { memcpy(p, &x, sizeof(M)); memcpy(p + sizeof(M), &y, sizeof(M)); }
+    static void get(const unsigned char *p, M &x, M &y) { memcpy(&x, p, sizeof(M)); memcpy(&y, p + sizeof(M), sizeof(M)); }
+};
+template <> struct ElemIO<HostHdr<float>> {
+    static constexpr size_t kBytes = 16;
+    static void put(unsigned char *p, Hdr<float> x, Hdr<float> y) {
+        memcpy(p, &x.m, 4); memcpy(p + 4, &x.e, 4); memcpy(p + 8, &y.e, 4); memcpy(p + 12, &y.m, 4);
+    }
+    static void get(const unsigned char *p, Hdr<float> &x, Hdr<float> &y) {
+        memcpy(&x.m, p, 4); memcpy(&x.e, p + 4, 4); memcpy(&y.e, p + 8, 4); memcpy(&y.m, p + 12, 4);
+    }
+};
+template <> struct ElemIO<HostHdr<double>> {
+    static constexpr size_t kBytes = 32;
+    static void put(unsigned char *p, Hdr<double> x, Hdr<double> y) {
+        memset(p, 0, 32);
+        memcpy(p, &x.m, 8); memcpy(p + 8, &x.e, 4); memcpy(p + 16, &y.e, 4); memcpy(p + 24, &y.m, 8);
+    }
+    static void get(const unsigned char *p, Hdr<double> &x, Hdr<double> &y) {
+        memcpy(&x.m, p, 8); memcpy(&x.e, p + 8, 4); memcpy(&y.e, p + 16, 4); memcpy(&y.m, p + 24, 8);
+    }
+};
+
+// --------------------------------------------------------------------------------------------
+// Reference orbit, single-threaded GMP loop (RefOrbitCalc.cpp:447-623).
+// Periodicity test |z| < 2 * MaxRadius * |dz/dc| is evaluated in (double mantissa, int exponent)
+// arithmetic here; it decides only where the orbit stops.
+// --------------------------------------------------------------------------------------------
+struct XD { // extended double
+    double m; long e;
+};
+XD xd_norm(double m, long e) {
+    if (m == 0) return {0, -(1L << 40)};
+    int k; m = frexp(m, &k);
+    return {m, e + k};
+}
+XD xd_mul(XD a, XD b) { return xd_norm(a.m * b.m, a.e + b.e); }
+XD xd_add(XD a, XD b) {
+    if (a.m == 0) return b;
+    if (b.m == 0) return a;
+    if (a.e < b.e) std::swap(a, b);
+    const long d = a.e - b.e;
+    if (d > 200) return a;
+    return xd_norm(a.m + ldexp(b.m, (int)-d), a.e);
+}
+XD xd_neg(XD a) { a.m = -a.m; return a; }
+bool xd_lt_abs(XD a, XD b) { // |a| < |b|
+    if (b.m == 0) return false;
+    if (a.m == 0) return true;
+    if (a.e != b.e) return a.e < b.e;
+    return fabs(a.m) < fabs(b.m);
+}
+XD xd_absmax(XD a, XD b) { return xd_lt_abs(a, b) ? XD{fabs(b.m), b.e} : XD{fabs(a.m), a.e}; }
+XD xd_from_mpf(const fs_mpf_struct *f) {
+    if (fs_mpf_sgn(f) == 0) return {0, -(1L << 40)};
+    long e; const double d = fs_mpf_get_d_2exp(&e, f);
+    return {d, e};
+}
+
+template <class N> void compute_orbit(const fsh_view *v, fsh_orbit *o, uint64_t max_iters, bool periodicity) {
+    using IO = ElemIO<N>;
+    const unsigned long prec = v->prec;
+    Mpf zx(prec), zy(prec), zx2(prec), t1(prec), t2(prec), delta(prec);
+    o->elem_bytes = IO::kBytes;
+    o->data.clear();
+    o->data.reserve((size_t)std::min<uint64_t>(max_iters + 2, 1u << 22) * IO::kBytes);
+    auto push = [&](typename N::Real x, typename N::Real y) {
+        const size_t off = o->data.size();
+        o->data.resize(off + IO::kBytes);
+        IO::put(o->data.data() + off, x, y);
+        o->count++;
+    };
+    // MaxRadius = T{maxY - minY} / T{2.0f}, reduced (PerturbationResults.cpp:823-857)
+    fs_mpf_sub(delta.v, v->maxY.v, v->minY.v);
+    {
+        typename N::Real rad = FromMpf<N>::raw(delta.v);
+        rad = N::r_div(rad, N::kHdr ? N::r_int(2) : N::r_int(2));
+        N::r_reduce(rad);
+        memcpy(o->max_radius, &rad, sizeof(rad));
+        typename N::Real xl = FromMpf<N>::raw(v->cx.v), yl = FromMpf<N>::raw(v->cy.v);
+        memcpy(o->x_low, &xl, sizeof(xl));
+        memcpy(o->y_low, &yl, sizeof(yl));
+    }
+    const XD max_radius = xd_mul(xd_from_mpf(delta.v), XD{0.5, 0});
+    // entry 0 is the zero element (PerturbationResults.cpp:861-868)
+    if constexpr (N::kHdr) {
+        const typename N::Real zr = hdr_zero<typename N::Mant>();
+        push(zr, zr);
+    } else {
+        push(typename N::Real{}, typename N::Real{});
+    }
+    fs_mpf_set(zx.v, v->cx.v);
+    fs_mpf_set(zy.v, v->cy.v);
+    const double cxd = fs_mpf_get_d(v->cx.v), cyd = fs_mpf_get_d(v->cy.v);
+    XD dzdcX{0.5, 1}, dzdcY{0, -(1L << 40)};
+    o->period = 0;
+    for (uint64_t i = 0; i < max_iters; i++) {
+        fs_mpf_mul_2exp(zx2.v, zx.v, 1);
+        push(FromMpf<N>::raw(zx.v), FromMpf<N>::raw(zy.v));
+        if (periodicity) {
+            const XD zxd = xd_from_mpf(zx.v), zyd = xd_from_mpf(zy.v);
+            const XD n2 = xd_absmax(zxd, zyd);
+            const XD r0 = xd_absmax(dzdcX, dzdcY);
+            const XD n3 = xd_mul(xd_mul(max_radius, r0), XD{0.5, 2});
+            if (xd_lt_abs(n2, n3)) {
+                o->period = o->count;
+                break;
+            }
+            const XD ox = dzdcX;
+            dzdcX = xd_add(xd_mul(XD{0.5, 2}, xd_add(xd_mul(zxd, dzdcX), xd_neg(xd_mul(zyd, dzdcY)))), XD{0.5, 1});
+            dzdcY = xd_mul(XD{0.5, 2}, xd_add(xd_mul(zxd, dzdcY), xd_mul(zyd, ox)));
+        }
+        const double zxd0 = fs_mpf_get_d(zx.v), zyd0 = fs_mpf_get_d(zy.v);
+        fs_mpf_mul(t1.v, zx.v, zx.v);
+        fs_mpf_mul(t2.v, zy.v, zy.v);
+        fs_mpf_sub(zx.v, t1.v, t2.v);
+        fs_mpf_add(zx.v, zx.v, v->cx.v);
+        fs_mpf_mul(zy.v, zx2.v, zy.v);
+        fs_mpf_add(zy.v, zy.v, v->cy.v);
+        const double tx = zxd0 + cxd, ty = zyd0 + cyd;
+        if (tx * tx + ty * ty > 256.0) break;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// LA table construction (single-thread routine of the reference)
+// --------------------------------------------------------------------------------------------
+template <class N, class IterT> struct LaBuilder {
+    using Real = typename N::Real;
+    using Cplx = typename N::Cplx;
+    using LA = WireLA<N, IterT>;
+    using AT = WireAT<N, IterT>;
+    static constexpr int lowBound = 64;     // LAReference.h:56
+    static constexpr int periodDivisor = 2; // LAReference.cpp:17-19 (8 with orbit compression)
+    static constexpr int MaxLAStages = 1024;
+
+    const fsh_orbit *orbit;
+    LaParams P;
+    std::vector<LA> las;
+    std::vector<WireStage<IterT>> stages;
+    AT at;
+    bool use_at = false, is_valid = false;
+    IterT stage_count = 0;
+
+    Cplx orbit_at(uint64_t i) const { // PerturbationResults::GetComplex<SubType>
+        Real x, y;
+        ElemIO<N>::get(orbit->data.data() + i * ElemIO<N>::kBytes, x, y);
+        if constexpr (N::kHdr) return hc_from<typename N::Mant>(x, y);
+        else { Cplx c; c.re = x; c.im = y; return c; }
+    }
+
+    static LA la_blank() { LA l; memset(&l, 0, sizeof(l)); if constexpr (N::kHdr) {
+            l.Ref = N::c_zero(); l.ZCoeff = N::c_zero(); l.CCoeff = N::c_zero();
+            l.LAThreshold.e = MIN_BIG; l.LAThresholdC.e = MIN_BIG; l.MinMag.e = MIN_BIG; }
+        return l; }
+    LA la_new(Cplx z) const { // LAInfoDeep(la_parameters, z)  LAInfoDeep.h:109-133
+        LA l = la_blank();
+        l.Ref = z;
+        l.ZCoeff = N::c_one();
+        l.CCoeff = N::c_one();
+        l.LAThreshold = N::r_int(1);
+        l.LAThresholdC = N::r_int(1);
+        l.MinMag = N::r_int(4);
+        return l;
+    }
+    // Step  LAInfoDeep.h:185-259 ; returns "period detected"
+    bool la_step(const LA &a, LA &out, Cplx z) const {
+        const Real mz = N::c_cheb(z), mZ = N::c_cheb(a.ZCoeff), mC = N::c_cheb(a.CCoeff);
+        out.MinMag = N::r_min(mz, a.MinMag);
+        Real t1 = N::r_scale(N::r_div(mz, mZ), P.la_scale);
+        N::r_reduce(t1);
+        Real t2 = N::r_scale(N::r_div(mz, mC), P.lac_scale);
+        N::r_reduce(t2);
+        out.LAThreshold = N::r_min(a.LAThreshold, t1);
+        out.LAThresholdC = N::r_min(a.LAThresholdC, t2);
+        const Cplx z2 = N::c_mul2(z);
+        Cplx oz = N::c_mul(z2, a.ZCoeff);
+        N::c_reduce(oz);
+        Cplx oc = N::c_add_one(N::c_mul(z2, a.CCoeff));
+        N::c_reduce(oc);
+        out.ZCoeff = oz;
+        out.CCoeff = oc;
+        out.Ref = a.Ref;
+        return N::r_cmp(out.MinMag, N::r_scale(a.MinMag, P.stage0_thr2)) < 0;
+    }
+    LA la_step(const LA &a, Cplx z) const { LA r = la_blank(); la_step(a, r, z); return r; }
+    bool la_detect(const LA &a, Cplx z) const { // DetectPeriod  LAInfoDeep.h:135-157 (method 1)
+        return N::r_cmp(N::c_cheb(z), N::r_scale(a.MinMag, P.thr2)) < 0;
+    }
+    // Composite  LAInfoDeep.h:294-381
+    bool la_comp(const LA &a, LA &out, const LA &b) const {
+        const Cplx z = b.Ref;
+        const Real mz = N::c_cheb(z);
+        Real mZ = N::c_cheb(a.ZCoeff), mC = N::c_cheb(a.CCoeff);
+        Real t1 = N::r_scale(N::r_div(mz, mZ), P.la_scale);
+        N::r_reduce(t1);
+        Real t2 = N::r_scale(N::r_div(mz, mC), P.lac_scale);
+        N::r_reduce(t2);
+        Real oT = N::r_min(a.LAThreshold, t1), oTC = N::r_min(a.LAThresholdC, t2);
+        const Cplx z2 = N::c_mul2(z);
+        Cplx oz = N::c_mul(z2, a.ZCoeff);
+        N::c_reduce(oz);
+        Cplx oc = N::c_mul(z2, a.CCoeff);
+        N::c_reduce(oc);
+        mZ = N::c_cheb(oz);
+        mC = N::c_cheb(oc);
+        t1 = N::r_div(b.LAThreshold, mZ);
+        N::r_reduce(t1);
+        t2 = N::r_div(b.LAThreshold, mC);
+        N::r_reduce(t2);
+        oT = N::r_min(oT, t1);
+        oTC = N::r_min(oTC, t2);
+        oz = N::c_mul(oz, b.ZCoeff);
+        N::c_reduce(oz);
+        oc = N::c_add(N::c_mul(oc, b.ZCoeff), b.CCoeff);
+        N::c_reduce(oc);
+        out.LAThreshold = oT;
+        out.LAThresholdC = oTC;
+        out.ZCoeff = oz;
+        out.CCoeff = oc;
+        out.Ref = a.Ref;
+        const Real temp = N::r_min(mz, a.MinMag);
+        out.MinMag = N::r_min(temp, b.MinMag);
+        return N::r_cmp(temp, N::r_scale(a.MinMag, P.thr2)) < 0;
+    }
+    LA la_comp(const LA &a, const LA &b) const { LA r = la_blank(); la_comp(a, r, b); return r; }
+
+    IterT nth_root_period(double maxRef, double ratio) const {
+        const double nth = round(log2(maxRef) / periodDivisor);
+        return (IterT)round(pow(ratio, 1.0 / nth));
+    }
+
+    // CreateLAFromOrbit  LAReference.cpp:28-207
+    bool stage0(IterT maxRef) {
+        is_valid = false;
+        stages.assign(MaxLAStages, WireStage<IterT>{0, 0});
+        use_at = false;
+        stage_count = 0;
+        stages[0].LAIndex = 0;
+        IterT Period = 0;
+        LA la = la_step(la_new(N::c_zero()), orbit_at(1));
+        IterT nextIdx = 0;
+        if (N::c_is_zero(la.ZCoeff)) return false;
+        IterT i;
+        for (i = 2; i < maxRef; i++) {
+            LA nl = la_blank();
+            if (!la_step(la, nl, orbit_at(i))) { la = nl; continue; }
+            Period = i;
+            la.StepLength = Period; la.NextStageLAIndex = nextIdx;
+            las.push_back(la);
+            nextIdx = i;
+            if (i + 1 < maxRef) { la = la_step(la_new(orbit_at(i)), orbit_at(i + 1)); i += 2; }
+            else { la = la_new(orbit_at(i)); i += 1; }
+            break;
+        }
+        stage_count = 1;
+        IterT PeriodBegin = Period, PeriodEnd = PeriodBegin + Period;
+        if (Period == 0) {
+            if (maxRef > (IterT)lowBound) {
+                la = la_step(la_new(orbit_at(0)), orbit_at(1));
+                nextIdx = 0;
+                i = 2;
+                Period = nth_root_period((double)maxRef, (double)maxRef);
+                PeriodBegin = 0;
+                PeriodEnd = Period;
+            } else {
+                la.StepLength = maxRef; la.NextStageLAIndex = nextIdx;
+                las.push_back(la);
+                las.push_back(la_new(orbit_at(maxRef)));
+                stages[0].MacroItCount = 1;
+                return false;
+            }
+        } else if (Period > (IterT)lowBound) {
+            las.pop_back();
+            la = la_step(la_new(orbit_at(0)), orbit_at(1));
+            nextIdx = 0;
+            i = 2;
+            Period = nth_root_period((double)maxRef, (double)maxRef);
+            PeriodBegin = 0;
+            PeriodEnd = Period;
+        }
+        for (; i < maxRef; i++) {
+            LA nl = la_blank();
+            const bool det = la_step(la, nl, orbit_at(i));
+            if (!det && i < PeriodEnd) { la = nl; continue; }
+            la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
+            las.push_back(la);
+            nextIdx = i;
+            PeriodBegin = i;
+            PeriodEnd = PeriodBegin + Period;
+            const IterT ip1 = i + 1;
+            const bool detected = la_detect(nl, orbit_at(ip1));
+            if (detected || ip1 >= maxRef) {
+                la = la_new(orbit_at(i));
+            } else {
+                la = la_step(la_new(orbit_at(i)), orbit_at(ip1));
+                i++;
+            }
+        }
+        la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
+        las.push_back(la);
+        stages[0].MacroItCount = (IterT)las.size();
+        LA la2 = la_new(orbit_at(maxRef));
+        la2.StepLength = 0; la2.NextStageLAIndex = 0;
+        las.push_back(la2);
+        return true;
+    }
+
+    // CreateNewLAStage  LAReference.cpp:774-968
+    bool next_stage(IterT maxRef) {
+        const IterT PrevStage = stage_count - 1, CurrentStage = stage_count;
+        if (CurrentStage >= (IterT)MaxLAStages) return false;
+        const IterT PrevIdx = stages[PrevStage].LAIndex;
+        const IterT PrevCount = stages[PrevStage].MacroItCount;
+        const LA PrevLA = las[PrevIdx];
+        const LA PrevLAp1 = las[PrevIdx + 1];
+        IterT Period = 0;
+        stages[CurrentStage].LAIndex = (IterT)las.size();
+        LA la = la_comp(PrevLA, PrevLAp1);
+        IterT nextIdx = 0;
+        IterT i = PrevLA.StepLength + PrevLAp1.StepLength;
+        IterT j;
+        for (j = 2; j < PrevCount; j++) {
+            LA nl = la_blank();
+            const LA Pj = las[PrevIdx + j];
+            const bool det = la_comp(la, nl, Pj);
+            if (det) {
+                if (N::r_is_zero(Pj.LAThreshold)) break;
+                Period = i;
+                la.StepLength = Period; la.NextStageLAIndex = nextIdx;
+                las.push_back(la);
+                nextIdx = j;
+                const LA Pjp1 = las[PrevIdx + j + 1];
+                if (la_detect(nl, Pjp1.Ref) || j + 1 >= PrevCount) {
+                    la = Pj;
+                    i += Pj.StepLength;
+                    j++;
+                } else {
+                    la = la_comp(Pj, Pjp1);
+                    i += Pj.StepLength + Pjp1.StepLength;
+                    j += 2;
+                }
+                break;
+            }
+            la = nl;
+            i += las[PrevIdx + j].StepLength;
+        }
+        stage_count++;
+        IterT PeriodBegin = Period, PeriodEnd = PeriodBegin + Period;
+        if (Period == 0) {
+            if (maxRef > PrevLA.StepLength * (IterT)lowBound) {
+                la = la_comp(PrevLA, PrevLAp1);
+                i = PrevLA.StepLength + PrevLAp1.StepLength;
+                nextIdx = 0;
+                j = 2;
+                const double Ratio = (double)maxRef / (double)PrevLA.StepLength;
+                Period = PrevLA.StepLength * nth_root_period((double)maxRef, Ratio);
+                PeriodBegin = 0;
+                PeriodEnd = Period;
+            } else {
+                la.StepLength = maxRef; la.NextStageLAIndex = nextIdx;
+                las.push_back(la);
+                LA la2 = la_new(orbit_at(maxRef));
+                la2.StepLength = 0; la2.NextStageLAIndex = 0;
+                las.push_back(la2);
+                stages[CurrentStage].MacroItCount = 1;
+                return false;
+            }
+        } else if (Period > PrevLA.StepLength * (IterT)lowBound) {
+            las.pop_back();
+            la = la_comp(PrevLA, PrevLAp1);
+            i = PrevLA.StepLength + PrevLAp1.StepLength;
+            nextIdx = 0;
+            j = 2;
+            const double Ratio = (double)Period / (double)PrevLA.StepLength;
+            Period = PrevLA.StepLength * nth_root_period((double)maxRef, Ratio);
+            PeriodBegin = 0;
+            PeriodEnd = Period;
+        }
+        for (; j < PrevCount; j++) {
+            LA nl = la_blank();
+            const LA Pj = las[PrevIdx + j];
+            const bool det = la_comp(la, nl, Pj);
+            if (det || i >= PeriodEnd) {
+                la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
+                las.push_back(la);
+                nextIdx = j;
+                PeriodBegin = i;
+                PeriodEnd = PeriodBegin + Period;
+                const LA Pjp1 = las[PrevIdx + j + 1];
+                if (la_detect(nl, Pjp1.Ref) || j + 1 >= PrevCount) {
+                    la = Pj;
+                } else {
+                    la = la_comp(Pj, Pjp1);
+                    i += las[PrevIdx + j].StepLength;
+                    j++;
+                }
+            } else {
+                la = nl;
+            }
+            i += las[PrevIdx + j].StepLength;
+        }
+        la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
+        las.push_back(la);
+        stages[CurrentStage].MacroItCount = (IterT)las.size() - stages[CurrentStage].LAIndex;
+        LA la2 = la_new(orbit_at(maxRef));
+        la2.StepLength = 0; la2.NextStageLAIndex = 0;
+        las.push_back(la2);
+        return true;
+    }
+
+    // LAInfoDeep::CreateAT  LAInfoDeep.h:456-502 ; ATInfo::Usable  ATInfo.h:92-106
+    void create_at(const LA &a, const LA &next, bool small_exp) {
+        at.ZCoeff = a.ZCoeff;
+        at.CCoeff = N::c_mul(a.ZCoeff, a.CCoeff);
+        N::c_reduce(at.CCoeff);
+        at.InvZCoeff = N::c_recip(a.ZCoeff);
+        N::c_reduce(at.InvZCoeff);
+        at.CCoeffSqrInvZCoeff = N::c_mul(N::c_mul(at.CCoeff, at.CCoeff), at.InvZCoeff);
+        N::c_reduce(at.CCoeffSqrInvZCoeff);
+        at.CCoeffInvZCoeff = N::c_mul(at.CCoeff, at.InvZCoeff);
+        N::c_reduce(at.CCoeffInvZCoeff);
+        at.RefC = N::c_mul(next.Ref, a.ZCoeff);
+        N::c_reduce(at.RefC);
+        at.CCoeffNormSqr = N::c_norm2(at.CCoeff);
+        N::r_reduce(at.CCoeffNormSqr);
+        at.RefCNormSqr = N::c_norm2(at.RefC);
+        N::r_reduce(at.RefCNormSqr);
+        const Real lim = N::at_lim(small_exp);
+        at.SqrEscapeRadius = N::r_min(N::r_mul(N::c_norm2(a.ZCoeff), a.LAThreshold), lim);
+        N::r_reduce(at.SqrEscapeRadius);
+        at.ThresholdC = N::r_min(a.LAThresholdC, N::r_div(lim, N::c_cheb(at.CCoeff)));
+    }
+    bool at_usable(Real sqr_radius) const {
+        Real result = N::r_mul(N::r_mul(at.CCoeffNormSqr, sqr_radius), at.factor);
+        N::r_reduce(result);
+        return N::r_cmp(result, at.RefCNormSqr) > 0 && N::r_cmp(at.SqrEscapeRadius, N::at_four()) > 0;
+    }
+
+    // GenerateApproximationData  LAReference.cpp:971-1017 ; CreateATFromLA :1050-1074
+    void build() {
+        memset(&at, 0, sizeof(at));
+        at.factor = N::at_factor();
+        const IterT maxRef = (IterT)orbit->count - 1;
+        if (maxRef == 0) { is_valid = false; return; }
+        bool ok = stage0(maxRef);
+        if (ok) {
+            while (next_stage(maxRef)) {}
+            Real radius;
+            memcpy(&radius, orbit->max_radius, sizeof(radius));
+            const Real sqr_radius = N::r_square_reduced(radius);
+            use_at = false;
+            for (IterT s = stage_count; s > 0;) {
+                s--;
+                const IterT idx = stages[s].LAIndex;
+                create_at(las[idx], las[idx + 1], false);
+                at.StepLength = las[idx].StepLength;
+                if (at.StepLength > 0 && at_usable(sqr_radius)) { use_at = true; break; }
+            }
+            is_valid = true;
+        }
+        // Trim(): stages keep MaxLAStages entries in the reference only until trimmed to the used count
+        stages.resize(std::max<size_t>((size_t)stage_count, 1));
+    }
+};
+
+template <class N, class IterT> fsh_la *build_la(const fsh_orbit *o) {
+    LaBuilder<N, IterT> b;
+    b.orbit = o;
+    b.build();
+    fsh_la *r = new fsh_la();
+    r->las.resize(b.las.size() * sizeof(b.las[0]));
+    if (!b.las.empty()) memcpy(r->las.data(), b.las.data(), r->las.size());
+    r->stages.resize(b.stages.size() * sizeof(b.stages[0]));
+    memcpy(r->stages.data(), b.stages.data(), r->stages.size());
+    r->at.resize(sizeof(b.at));
+    memcpy(r->at.data(), &b.at, sizeof(b.at));
+    r->num_las = b.las.size();
+    r->num_stages = b.stages.size();
+    r->stage_count = b.stage_count;
+    r->use_at = b.use_at;
+    r->is_valid = b.is_valid;
+    return r;
+}
+
+unsigned long pick_precision(const char *a, const char *b) {
+    const size_t n = std::max(strlen(a), strlen(b));
+    const unsigned long bits = (unsigned long)(n * 3.3219281) + 64;
+    return bits < 256 ? 256 : bits;
+}
+
+template <class N> void fill_coord(const fs_mpf_struct *f, void *dst) {
+    if (!dst) return;
+    const typename N::Real v = FromMpf<N>::coord(f);
+    memcpy(dst, &v, sizeof(v));
+}
+
+} // namespace
+
+extern "C" {
+
+// numeric tags as in include/fs_gpu.h
+enum { NUM_F32 = 0, NUM_F64 = 1, NUM_HDR32 = 3, NUM_HDR64 = 4 };
+
+fsh_view *fsh_view_create(const char *minX, const char *minY, const char *maxX, const char *maxY, uint32_t scrn_w,
+                          uint32_t scrn_h, uint32_t antialiasing, int32_t square_aspect) {
+    const unsigned long prec = std::max(pick_precision(minX, maxX), pick_precision(minY, maxY));
+    fsh_view *v = new fsh_view(prec);
+    if (fs_mpf_set_str(v->minX.v, minX, 10) || fs_mpf_set_str(v->minY.v, minY, 10) ||
+        fs_mpf_set_str(v->maxX.v, maxX, 10) || fs_mpf_set_str(v->maxY.v, maxY, 10)) {
+        delete v;
+        return nullptr;
+    }
+    v->w = scrn_w; v->h = scrn_h; v->aa = antialiasing ? antialiasing : 1;
+    if (square_aspect && scrn_w && scrn_h) { // PointZoomBBConverter::SquareAspectRatio :271-312
+        Mpf ratio(prec), mwidth(prec), height(prec), tmp(prec), w(prec), h(prec);
+        fs_mpf_set_ui(w.v, scrn_w);
+        fs_mpf_set_ui(h.v, scrn_h);
+        fs_mpf_div(ratio.v, w.v, h.v);
+        fs_mpf_sub(mwidth.v, v->maxX.v, v->minX.v);
+        fs_mpf_div(mwidth.v, mwidth.v, ratio.v);
+        fs_mpf_sub(height.v, v->maxY.v, v->minY.v);
+        const int c = fs_mpf_cmp(height.v, mwidth.v);
+        if (c > 0) {
+            fs_mpf_sub(tmp.v, height.v, mwidth.v);
+            fs_mpf_mul(tmp.v, ratio.v, tmp.v);
+            fs_mpf_div_ui(tmp.v, tmp.v, 2);
+            fs_mpf_sub(v->minX.v, v->minX.v, tmp.v);
+            fs_mpf_add(v->maxX.v, v->maxX.v, tmp.v);
+        } else if (c < 0) {
+            fs_mpf_sub(tmp.v, mwidth.v, height.v);
+            fs_mpf_div_ui(tmp.v, tmp.v, 2);
+            fs_mpf_sub(v->minY.v, v->minY.v, tmp.v);
+            fs_mpf_add(v->maxY.v, v->maxY.v, tmp.v);
+        }
+    }
+    // reference point = view centre
+    fs_mpf_add(v->cx.v, v->minX.v, v->maxX.v);
+    fs_mpf_div_ui(v->cx.v, v->cx.v, 2);
+    fs_mpf_add(v->cy.v, v->minY.v, v->maxY.v);
+    fs_mpf_div_ui(v->cy.v, v->cy.v, 2);
+    return v;
+}
+
+void fsh_view_destroy(fsh_view *v) { delete v; }
+uint32_t fsh_view_precision_bits(const fsh_view *v) { return (uint32_t)v->prec; }
+
+// FillGpuCoords + centre deltas (Fractal.cpp:1830-1844, 2831-2840). Any output may be NULL.
+int32_t fsh_view_coords(const fsh_view *v, int32_t numeric, void *cx, void *cy, void *dx, void *dy, void *center_x,
+                        void *center_y) {
+    const unsigned long prec = v->prec;
+    Mpf ddx(prec), ddy(prec), cenx(prec), ceny(prec), div(prec);
+    fs_mpf_sub(ddx.v, v->maxX.v, v->minX.v);
+    fs_mpf_set_ui(div.v, (unsigned long)v->w * v->aa);
+    fs_mpf_div(ddx.v, ddx.v, div.v);
+    fs_mpf_sub(ddy.v, v->maxY.v, v->minY.v);
+    fs_mpf_set_ui(div.v, (unsigned long)v->h * v->aa);
+    fs_mpf_div(ddy.v, ddy.v, div.v);
+    fs_mpf_sub(cenx.v, v->cx.v, v->minX.v);
+    fs_mpf_sub(ceny.v, v->cy.v, v->maxY.v);
+#define FSH_FILL(N)                                                                                                    \
+    fill_coord<N>(v->minX.v, cx); fill_coord<N>(v->minY.v, cy); fill_coord<N>(ddx.v, dx); fill_coord<N>(ddy.v, dy);   \
+    fill_coord<N>(cenx.v, center_x); fill_coord<N>(ceny.v, center_y); return 0;
+    switch (numeric) {
+    case NUM_F32: FSH_FILL(HostPlain<float>)
+    case NUM_F64: FSH_FILL(HostPlain<double>)
+    case NUM_HDR32: FSH_FILL(HostHdr<float>)
+    case NUM_HDR64: FSH_FILL(HostHdr<double>)
+    default: return -1;
+    }
+#undef FSH_FILL
+}
+
+fsh_orbit *fsh_orbit_compute(const fsh_view *v, int32_t numeric, uint64_t max_iterations, int32_t periodicity) {
+    fsh_orbit *o = new fsh_orbit();
+    o->numeric = numeric;
+    switch (numeric) {
+    case NUM_F32: compute_orbit<HostPlain<float>>(v, o, max_iterations, periodicity != 0); break;
+    case NUM_F64: compute_orbit<HostPlain<double>>(v, o, max_iterations, periodicity != 0); break;
+    case NUM_HDR32: compute_orbit<HostHdr<float>>(v, o, max_iterations, periodicity != 0); break;
+    case NUM_HDR64: compute_orbit<HostHdr<double>>(v, o, max_iterations, periodicity != 0); break;
+    default: delete o; return nullptr;
+    }
+    return o;
+}
+void fsh_orbit_destroy(fsh_orbit *o) { delete o; }
+const void *fsh_orbit_data(const fsh_orbit *o) { return o->data.data(); }
+uint64_t fsh_orbit_count(const fsh_orbit *o) { return o->count; }
+uint64_t fsh_orbit_period(const fsh_orbit *o) { return o->period; }
+uint64_t fsh_orbit_elem_bytes(const fsh_orbit *o) { return o->elem_bytes; }
+const void *fsh_orbit_x_low(const fsh_orbit *o) { return o->x_low; }
+const void *fsh_orbit_y_low(const fsh_orbit *o) { return o->y_low; }
+const void *fsh_orbit_max_radius(const fsh_orbit *o) { return o->max_radius; }
+
+fsh_la *fsh_la_build(const fsh_orbit *o, uint32_t iter_bytes) {
+    const bool u64 = iter_bytes == 8;
+    switch (o->numeric) {
+    case NUM_F32: return u64 ? build_la<HostPlain<float>, uint64_t>(o) : build_la<HostPlain<float>, uint32_t>(o);
+    case NUM_F64: return u64 ? build_la<HostPlain<double>, uint64_t>(o) : build_la<HostPlain<double>, uint32_t>(o);
+    case NUM_HDR32: return u64 ? build_la<HostHdr<float>, uint64_t>(o) : build_la<HostHdr<float>, uint32_t>(o);
+    case NUM_HDR64: return u64 ? build_la<HostHdr<double>, uint64_t>(o) : build_la<HostHdr<double>, uint32_t>(o);
+    default: return nullptr;
+    }
+}
+void fsh_la_destroy(fsh_la *l) { delete l; }
+const void *fsh_la_las(const fsh_la *l) { return l->las.data(); }
+uint64_t fsh_la_num_las(const fsh_la *l) { return l->num_las; }
+const void *fsh_la_stages(const fsh_la *l) { return l->stages.data(); }
+uint64_t fsh_la_num_stages(const fsh_la *l) { return l->num_stages; }
+const void *fsh_la_at(const fsh_la *l) { return l->at.data(); }
+uint64_t fsh_la_at_bytes(const fsh_la *l) { return l->at.size(); }
+uint64_t fsh_la_stage_count(const fsh_la *l) { return l->stage_count; }
+int32_t fsh_la_use_at(const fsh_la *l) { return l->use_at; }
+int32_t fsh_la_is_valid(const fsh_la *l) { return l->is_valid; }
+
+} // extern "C"

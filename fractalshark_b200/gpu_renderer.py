@@ -1,0 +1,178 @@
+"""``GPURenderer`` -- host-side mirror of the reference class over the C-ABI.
+
+Method names, argument meaning and error behaviour follow FractalSharkLib/GPU_Render.h:20-227: every
+method returns the ``uint32_t`` status (0 = success, else ``cudaError_t`` or ``FractalSharkError``
+10000+); render calls only enqueue; results are pulled with ``RenderCurrent``.  Template arguments of
+the reference (``IterType``, ``T``, ``Mode``, ``PExtras``) are explicit keyword arguments here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .algorithms import LAv2Mode, Numeric, PerturbExtras, RenderAlgorithm, traits
+
+NB_THREADS_W = 16  # GPU_Render.h:116-120
+NB_THREADS_H = 8
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def _buf(b: bytes):
+    return C.cast(C.create_string_buffer(b, len(b)), C.c_void_p)
+
+
+class GPURenderer:
+    def __init__(self, device: int = 0):
+        self._lib = N.gpu_lib()
+        self._h = self._lib.fs_create(device)
+        if not self._h:
+            raise MemoryError("fs_create failed")
+        self._iter_bytes = 4
+        self._keep = []  # host buffers borrowed by in-flight async copies
+        self._cb = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # ---- statics -------------------------------------------------------------------------------
+    @staticmethod
+    def TestCudaIsWorking() -> int:
+        return int(N.gpu_lib().fs_test_cuda_is_working())
+
+    @staticmethod
+    def ConvertErrorToString(err: int) -> str:
+        return N.gpu_lib().fs_convert_error_to_string(err).decode()
+
+    # ---- lifecycle -----------------------------------------------------------------------------
+    def InitializeMemory(self, w: int, h: int, antialiasing: int = 1, palette: np.ndarray | None = None,
+                         palette_aux_depth: int = 0, palette_generation: int = 1, expected_reuse: bool = False,
+                         iter_bytes: int = 4) -> int:
+        """``w``/``h`` are the super-sampled sizes (screen size x antialiasing), GPU_Render.h:91-100."""
+        if palette is None:
+            palette = default_palette()
+        palette = np.ascontiguousarray(palette, dtype=np.uint16).reshape(-1, 4)
+        self._palette = palette
+        self._iter_bytes = iter_bytes
+        self._antialiasing = antialiasing
+        return int(self._lib.fs_initialize_memory(self._h, iter_bytes, w, h, antialiasing,
+                                                  palette.ctypes.data, palette.shape[0], palette_aux_depth,
+                                                  palette_generation, int(expected_reuse)))
+
+    def InitializePerturb(self, generation1: int, perturb1, generation2: int = 0, perturb2=None, la=None,
+                          pextras: PerturbExtras = PerturbExtras.Disable) -> int:
+        """``perturb1``/``perturb2`` are :class:`host_inputs.Orbit`, ``la`` a :class:`host_inputs.LaTable`."""
+        d1 = perturb1.descriptor()
+        d2 = perturb2.descriptor() if perturb2 is not None else None
+        dl = la.descriptor() if la is not None else None
+        return int(self._lib.fs_initialize_perturb(
+            self._h, self._iter_bytes, int(perturb1.numeric), int(pextras), generation1, C.byref(d1),
+            int(perturb2.numeric) if perturb2 is not None else 0, generation2,
+            C.byref(d2) if d2 is not None else None, C.byref(dl) if dl is not None else None))
+
+    def ClearMemory(self) -> None:
+        self._lib.fs_clear_memory(self._h)
+
+    # ---- render calls --------------------------------------------------------------------------
+    def Render(self, algorithm: RenderAlgorithm, coords: dict, n_iterations: int, iteration_precision: int = 1) -> int:
+        t = traits(algorithm)
+        return int(self._lib.fs_render(self._h, int(algorithm), int(t.numeric), _buf(coords["cx"]), _buf(coords["cy"]),
+                                       _buf(coords["dx"]), _buf(coords["dy"]), n_iterations, iteration_precision))
+
+    def RenderPerturbLAv2(self, algorithm: RenderAlgorithm, coords: dict, n_iterations: int) -> int:
+        t = traits(algorithm)
+        return int(self._lib.fs_render_perturb_lav2(
+            self._h, int(algorithm), int(t.numeric), int(t.mode), int(t.pextras), _buf(coords["cx"]), _buf(coords["cy"]),
+            _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]), _buf(coords["center_y"]), n_iterations))
+
+    # ---- results -------------------------------------------------------------------------------
+    def buffer_shape(self) -> tuple[int, int]:
+        w, h = self.GetWidth(), self.GetHeight()
+        return _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)
+
+    def RenderCurrent(self, n_iterations: int, want_iters: bool = True, want_colors: bool = False,
+                      progressive: bool = False):
+        """Returns ``(status, iters, colors, reduction)``; arrays are padded like the reference's buffers."""
+        hp, wp = self.buffer_shape()
+        dt = np.uint32 if self._iter_bytes == 4 else np.uint64
+        iters = np.empty((hp, wp), dtype=dt) if want_iters else None
+        colors = None
+        if want_colors:
+            aa = self._aa()
+            colors = np.empty((_round_up(self.GetHeight() // aa, NB_THREADS_H),
+                               _round_up(self.GetWidth() // aa, NB_THREADS_W), 4), dtype=np.uint16)
+        red = N.FsReduction()
+        rc = int(self._lib.fs_render_current(self._h, n_iterations, iters.ctypes.data if want_iters else None,
+                                             colors.ctypes.data if want_colors else None, C.byref(red),
+                                             int(progressive)))
+        if rc == 0:
+            rc = self.SyncDisplayStream() if progressive else self.SyncComputeStream()
+        return rc, iters, colors, {"Min": int(red.Min), "Max": int(red.Max), "Sum": int(red.Sum)}
+
+    def _aa(self) -> int:
+        return getattr(self, "_antialiasing", 1)
+
+    def SyncComputeStream(self) -> int:
+        return int(self._lib.fs_sync_compute_stream(self._h))
+
+    def SyncDisplayStream(self) -> int:
+        return int(self._lib.fs_sync_display_stream(self._h))
+
+    def QueryComputeStream(self) -> int:
+        return int(self._lib.fs_query_compute_stream(self._h))
+
+    def EnqueueComputeDoneCallback(self, fn) -> int:
+        self._cb = N.DONE_CALLBACK(lambda _user: fn())
+        return int(self._lib.fs_enqueue_compute_done_callback(self._h, self._cb, None))
+
+    def GetWidth(self) -> int:
+        return int(self._lib.fs_get_width(self._h))
+
+    def GetHeight(self) -> int:
+        return int(self._lib.fs_get_height(self._h))
+
+    # ---- additions (measurement / sharding) ----------------------------------------------------
+    def SetRowRange(self, row_begin: int, row_end: int) -> int:
+        return int(self._lib.fs_set_row_range(self._h, row_begin, row_end))
+
+    def LastRenderMs(self) -> float:
+        ms = C.c_float(0)
+        rc = self._lib.fs_last_render_ms(self._h, C.byref(ms))
+        if rc:
+            raise RuntimeError(self.ConvertErrorToString(rc))
+        return float(ms.value)
+
+    def EnableStepCounter(self, enable: bool = True) -> int:
+        return int(self._lib.fs_enable_step_counter(self._h, int(enable)))
+
+    def ReadStepCounter(self) -> int:
+        v = C.c_uint64(0)
+        rc = self._lib.fs_read_step_counter(self._h, C.byref(v))
+        if rc:
+            raise RuntimeError(self.ConvertErrorToString(rc))
+        return int(v.value)
+
+    def DeviceIterBuffer(self) -> int:
+        return int(self._lib.fs_device_iter_buffer(self._h) or 0)
+
+    def KernelLaunchCount(self) -> int:
+        return int(self._lib.fs_kernel_launch_count(self._h))
+
+
+def default_palette(n: int = 4096) -> np.ndarray:
+    """A deterministic RGBA16 palette (the reference's palettes are UI data, FractalPalette.cpp)."""
+    i = np.arange(n, dtype=np.float64)
+    pal = np.empty((n, 4), dtype=np.uint16)
+    pal[:, 0] = (32767.5 * (1 + np.sin(i * 0.0123))).astype(np.uint16)
+    pal[:, 1] = (32767.5 * (1 + np.sin(i * 0.0211 + 2.0))).astype(np.uint16)
+    pal[:, 2] = (32767.5 * (1 + np.sin(i * 0.0337 + 4.0))).astype(np.uint16)
+    pal[:, 3] = 65535
+    return pal

@@ -1,0 +1,131 @@
+"""Inputs of the render path: view coordinates, reference orbit, LA table (libfshost.so).
+
+These are what the reference's host code hands to ``GPURenderer`` (coordinates: Fractal.cpp:1789-1844,
+2831-2840; orbit: RefOrbitCalc.cpp:415-647; LA table: LAReference.cpp:28-1074), in the reference's
+own memory layouts.  They are inputs -- not part of the timed GPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .algorithms import Numeric
+
+# bytes of one coordinate POD per numeric tag
+POD_BYTES = {Numeric.F32: 4, Numeric.F64: 8, Numeric.X2_32: 8, Numeric.HDR32: 8, Numeric.HDR64: 16,
+             Numeric.HDR2X32: 12}
+
+
+class View:
+    """A view rectangle at a given super-sampled size (PointZoomBBConverter + SquareAspectRatio)."""
+
+    def __init__(self, min_x: str, min_y: str, max_x: str, max_y: str, width: int, height: int,
+                 antialiasing: int = 1, square_aspect: bool = True):
+        self._lib = N.host_lib()
+        self.width, self.height, self.antialiasing = width, height, antialiasing
+        self._h = self._lib.fsh_view_create(min_x.encode(), min_y.encode(), max_x.encode(), max_y.encode(),
+                                            width, height, antialiasing, int(square_aspect))
+        if not self._h:
+            raise ValueError("could not parse view coordinates")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.fsh_view_destroy(self._h)
+            self._h = None
+
+    @property
+    def precision_bits(self) -> int:
+        return int(self._lib.fsh_view_precision_bits(self._h))
+
+    def coords(self, numeric: Numeric) -> dict:
+        """cx, cy, dx, dy, centerX, centerY as raw PODs of ``numeric`` (FillGpuCoords / FillCoord)."""
+        nb = POD_BYTES[Numeric(numeric)]
+        bufs = {k: C.create_string_buffer(nb) for k in ("cx", "cy", "dx", "dy", "center_x", "center_y")}
+        rc = self._lib.fsh_view_coords(self._h, int(numeric), *[C.cast(b, C.c_void_p) for b in bufs.values()])
+        if rc != 0:
+            raise ValueError(f"numeric {numeric!r} not supported by the input generator")
+        return {k: bytes(b.raw) for k, b in bufs.items()}
+
+
+class Orbit:
+    """High-precision reference orbit stored as GPUReferenceIter<T, Disable>[count]."""
+
+    def __init__(self, view: View, numeric: Numeric, max_iterations: int, periodicity: bool = True):
+        self._lib = N.host_lib()
+        self.numeric = Numeric(numeric)
+        self._view = view
+        self._h = self._lib.fsh_orbit_compute(view._h, int(numeric), int(max_iterations), int(periodicity))
+        if not self._h:
+            raise ValueError(f"numeric {numeric!r} not supported by the input generator")
+        self.count = int(self._lib.fsh_orbit_count(self._h))
+        self.period = int(self._lib.fsh_orbit_period(self._h))
+        self.elem_bytes = int(self._lib.fsh_orbit_elem_bytes(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.fsh_orbit_destroy(self._h)
+            self._h = None
+
+    @property
+    def data_ptr(self) -> int:
+        return int(self._lib.fsh_orbit_data(self._h))
+
+    def as_numpy(self) -> np.ndarray:
+        buf = (C.c_ubyte * (self.count * self.elem_bytes)).from_address(self.data_ptr)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.count, self.elem_bytes)
+
+    def descriptor(self) -> N.FsOrbit:
+        return N.FsOrbit(self.data_ptr, self.count, self.count, self.period,
+                         int(self._lib.fsh_orbit_x_low(self._h)), int(self._lib.fsh_orbit_y_low(self._h)))
+
+
+class LaTable:
+    """LAv2 table (LAInfoDeep[], LAStageInfo[], ATInfo) built from an orbit."""
+
+    def __init__(self, orbit: Orbit, iter_bytes: int):
+        self._lib = N.host_lib()
+        self._orbit = orbit
+        self.iter_bytes = iter_bytes
+        self._h = self._lib.fsh_la_build(orbit._h, iter_bytes)
+        if not self._h:
+            raise ValueError("LA build failed")
+        L = self._lib
+        self.num_las = int(L.fsh_la_num_las(self._h))
+        self.num_stages = int(L.fsh_la_num_stages(self._h))
+        self.stage_count = int(L.fsh_la_stage_count(self._h))
+        self.use_at = bool(L.fsh_la_use_at(self._h))
+        self.is_valid = bool(L.fsh_la_is_valid(self._h))
+        self.at_bytes = int(L.fsh_la_at_bytes(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.fsh_la_destroy(self._h)
+            self._h = None
+
+    def descriptor(self) -> N.FsLaReference:
+        L = self._lib
+        return N.FsLaReference(int(L.fsh_la_las(self._h) or 0), self.num_las, int(L.fsh_la_stages(self._h) or 0),
+                               self.num_stages, int(L.fsh_la_at(self._h) or 0), self.stage_count,
+                               int(self.use_at), int(self.is_valid))
+
+    def las_numpy(self) -> np.ndarray:
+        if self.num_las == 0:
+            return np.zeros((0, 0), np.uint8)
+        ptr = int(self._lib.fsh_la_las(self._h))
+        eb = self.las_elem_bytes
+        buf = (C.c_ubyte * (self.num_las * eb)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.num_las, eb)
+
+    @property
+    def las_elem_bytes(self) -> int:
+        table = {(Numeric.HDR32, 4): 68, (Numeric.HDR32, 8): 80, (Numeric.F32, 4): 44, (Numeric.F32, 8): 56,
+                 (Numeric.F64, 4): 80, (Numeric.F64, 8): 88, (Numeric.HDR64, 4): 128, (Numeric.HDR64, 8): 136}
+        return table[(self._orbit.numeric, self.iter_bytes)]
+
+    def stages_numpy(self) -> np.ndarray:
+        ptr = int(self._lib.fsh_la_stages(self._h))
+        dt = np.uint32 if self.iter_bytes == 4 else np.uint64
+        buf = (C.c_ubyte * (self.num_stages * 2 * self.iter_bytes)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dt).reshape(self.num_stages, 2)

@@ -1,0 +1,167 @@
+/* fs_gpu.h -- C-ABI of the B200-native per-pixel render path (libfsgpu.so).
+ *
+ * Drop-in boundary for the reference class `GPURenderer`
+ * (FractalSharkLib/GPU_Render.h:20-227, implemented in FractalSharkGpuLib/GPU_Render.cu:92-1823).
+ * Every C++ template of that class collapses to a runtime tag here; all numeric arguments cross as the
+ * raw bytes of the reference PODs:
+ *     float | double | {float head,tail} | {float m; int32 e} | {double m; int32 e; pad} | {float h,t; int32 e}
+ * Orbit elements, LA records, LA stages, ATInfo and BLA records cross in the reference's own memory
+ * layout (GPU_ReferenceIter.h:119-125, LAInfoDeep.h:33-39, LAInfoI.h:5-35, ATInfo.h:80-89, BLA.h:7-14),
+ * so the reference host code can hand over `GetOrbitData()`, `GetLAs().GetData()` ... unchanged.
+ *
+ * Conventions (GPU_Render.cu:33-43, 626-628, 1007-1022): every call returns uint32_t, 0 = success,
+ * else a cudaError_t value or a FractalSharkError (10000..10008).  Host pointers are borrowed for the
+ * duration of the call; device copies are owned by the renderer and cached by generation number.
+ * Render calls only enqueue work on the renderer's low-priority compute stream.
+ * No C++ exceptions cross this boundary.  There is no CPU fallback: without a CUDA device every call
+ * fails with the CUDA error.
+ */
+#ifndef FS_GPU_H
+#define FS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fs_renderer fs_renderer;
+
+/* GPU_Types.h:14-16, 40-50 */
+typedef struct { uint16_t r, g, b, a; } fs_color16;
+typedef struct { uint64_t Min, Max, Sum; } fs_reduction;
+
+/* numeric tag = the template argument T of the reference entry points */
+enum fs_numeric {
+    FS_NUM_F32 = 0,      /* float                                  */
+    FS_NUM_F64 = 1,      /* double                                 */
+    FS_NUM_2X32 = 2,     /* CudaDblflt<MattDblflt>  {head,tail}    */
+    FS_NUM_HDR32 = 3,    /* HDRFloat<float>                        */
+    FS_NUM_HDR64 = 4,    /* HDRFloat<double>                       */
+    FS_NUM_HDR2X32 = 5,  /* HDRFloat<CudaDblflt<MattDblflt>>       */
+    FS_NUM_2X64 = 6,     /* MattDbldbl   (direct kernels only)     */
+    FS_NUM_4X32 = 7,     /* MattQFltflt  (direct kernels only)     */
+    FS_NUM_4X64 = 8      /* MattQDbldbl  (direct kernels only)     */
+};
+
+/* PerturbExtras (HpSharkFloatLib/HighPrecision.h) */
+enum fs_pextras { FS_PEXTRAS_DISABLE = 0, FS_PEXTRAS_BAD = 1, FS_PEXTRAS_SIMPLE_COMPRESSION = 2 };
+
+/* LAv2Mode (FractalSharkLib/RenderAlgorithm.h:12-17) */
+enum fs_lav2_mode { FS_LAV2_FULL = 1, FS_LAV2_PO = 2, FS_LAV2_LAO = 3 };
+
+/* FractalSharkError (GPU_Render.cu:33-43) */
+enum fs_error {
+    FS_ERROR_1 = 10000, FS_ERROR_2, FS_ERROR_3_BAD_ANTIALIASING, FS_ERROR_4_WIDTH_NOT_MULTIPLE_OF_AA,
+    FS_ERROR_5_HEIGHT_NOT_MULTIPLE_OF_AA, FS_ERROR_6_NO_ORBIT, FS_ERROR_7_NO_LA, FS_ERROR_8, FS_ERROR_9,
+    FS_ERROR_UNSUPPORTED = 10100 /* tag combination the reference does not instantiate either */
+};
+
+/* replaces GPUPerturbResults<IterType,T,PExtras> (GPU_Types.h:83-175) */
+typedef struct {
+    const void *elements;        /* GPUReferenceIter<T,PExtras>[compressed_count], reference layout */
+    uint64_t compressed_count;   /* GetCompressedSize()                                             */
+    uint64_t uncompressed_count; /* GetUncompressedSize() == GetCountOrbitEntries()                 */
+    uint64_t period_maybe_zero;  /* GetPeriodMaybeZero()                                            */
+    const void *orbit_x_low;     /* T, may be NULL unless PExtras == SimpleCompression              */
+    const void *orbit_y_low;
+} fs_orbit;
+
+/* replaces the accessors of LAReference<IterType,T,SubType,PExtras> read by the upload
+ * (GPU_LAReference.h:78-162) */
+typedef struct {
+    const void *las;        /* LAInfoDeep<IterType,T,SubType,PExtras>[num_las], reference layout */
+    uint64_t num_las;
+    const void *stages;     /* LAStageInfo<IterType>[num_stages]                                 */
+    uint64_t num_stages;
+    const void *at;         /* ATInfo<IterType,T,SubType>                                        */
+    uint64_t la_stage_count;/* GetLAStageCount()                                                 */
+    int32_t use_at;         /* UseAT()                                                           */
+    int32_t is_valid;       /* IsValid()                                                         */
+} fs_la_reference;
+
+/* replaces BLAS<IterType,T> as read by GPU_BLAS (BLA.cuh:123-160, GPU_BLAS.h:9-50) */
+typedef struct {
+    const void *const *levels;    /* levels[i] -> BLA<T>[level_counts[i]] (BLA.h:7-14), NULL for i < first_level */
+    const uint64_t *level_counts;
+    uint32_t num_levels;          /* LM2 + 2                                                     */
+    uint32_t first_level;         /* BLAS::m_FirstLevel (= 2)                                    */
+    int32_t lm2;                  /* compile-time LM2 of the reference instantiation (0..30)     */
+} fs_blas;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+uint32_t fs_test_cuda_is_working(void);                        /* GPURenderer::TestCudaIsWorking  GPU_Render.h:25   */
+fs_renderer *fs_create(int32_t device);                        /* GPURenderer()  (reference: always device 0)       */
+void fs_destroy(fs_renderer *r);                               /* ~GPURenderer()                                    */
+
+/* GPURenderer::InitializeMemory<IterType>  GPU_Render.h:91-100 ; iter_bytes = sizeof(IterType) (4|8) */
+uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, uint32_t h, uint32_t antialiasing,
+                              const fs_color16 *pal_interleaved, uint32_t pal_iters, uint32_t palette_aux_depth,
+                              uint64_t palette_generation, int32_t expected_reuse);
+
+/* GPURenderer::InitializePerturb<IterType,T1,SubType,PExtras,T2>  GPU_Render.h:102-108.
+ * perturb2 / la may be NULL exactly as in the reference. */
+uint32_t fs_initialize_perturb(fs_renderer *r, uint32_t iter_bytes, int32_t numeric1, int32_t pextras,
+                               uint64_t generation1, const fs_orbit *perturb1, int32_t numeric2, uint64_t generation2,
+                               const fs_orbit *perturb2, const fs_la_reference *la);
+
+/* GPURenderer::ClearMemory<IterType>  GPU_Render.h:110-111 */
+void fs_clear_memory(fs_renderer *r);
+
+/* ---- render calls (enqueue only) -------------------------------------------------------------- */
+/* GPURenderer::Render<IterType,T>  GPU_Render.h:27-35 */
+uint32_t fs_render(fs_renderer *r, uint32_t algorithm, int32_t numeric, const void *cx, const void *cy,
+                   const void *dx, const void *dy, uint64_t n_iterations, int32_t iteration_precision);
+
+/* GPURenderer::RenderPerturbLAv2<IterType,T,SubType,Mode,PExtras>  GPU_Render.h:79-88 */
+uint32_t fs_render_perturb_lav2(fs_renderer *r, uint32_t algorithm, int32_t numeric, int32_t mode, int32_t pextras,
+                                const void *cx, const void *cy, const void *dx, const void *dy, const void *center_x,
+                                const void *center_y, uint64_t n_iterations);
+
+/* GPURenderer::RenderPerturbBLA<IterType,T>  GPU_Render.h:51-77 */
+uint32_t fs_render_perturb_bla(fs_renderer *r, uint32_t algorithm, int32_t numeric, const fs_orbit *results,
+                               const fs_blas *blas, const void *cx, const void *cy, const void *dx, const void *dy,
+                               const void *center_x, const void *center_y, uint64_t n_iterations,
+                               int32_t iteration_precision);
+
+/* GPURenderer::RenderPerturbBLAScaled<IterType,T>  GPU_Render.h:37-49 (orbits carry the Bad field) */
+uint32_t fs_render_perturb_bla_scaled(fs_renderer *r, uint32_t algorithm, int32_t numeric,
+                                      const fs_orbit *double_perturb, const fs_orbit *float_perturb, const void *cx,
+                                      const void *cy, const void *dx, const void *dy, const void *center_x,
+                                      const void *center_y, uint64_t n_iterations, int32_t iteration_precision);
+
+/* ---- results ---------------------------------------------------------------------------------- */
+/* GPURenderer::RenderCurrent<IterType>  GPU_Render.h:123-129.  iter_buffer holds
+ * roundup16(w)*roundup8(h) IterType cells, color_buffer roundup16(w/aa)*roundup8(h/aa) cells; any may be NULL. */
+uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buffer, fs_color16 *color_buffer,
+                           fs_reduction *reduction_results, int32_t progressive);
+
+uint32_t fs_sync_compute_stream(fs_renderer *r);   /* GPU_Render.h:131 */
+uint32_t fs_sync_display_stream(fs_renderer *r);   /* GPU_Render.h:132 */
+uint32_t fs_query_compute_stream(fs_renderer *r);  /* GPU_Render.h:133 */
+/* GPU_Render.h:134-155: the callback replaces SignalComputeDone(); it runs on a CUDA host-func thread */
+typedef void (*fs_done_callback)(void *user);
+uint32_t fs_enqueue_compute_done_callback(fs_renderer *r, fs_done_callback fn, void *user);
+
+const char *fs_convert_error_to_string(uint32_t err); /* GPU_Render.h:113 */
+uint32_t fs_get_width(const fs_renderer *r);          /* GPU_Render.h:157 */
+uint32_t fs_get_height(const fs_renderer *r);         /* GPU_Render.h:158 */
+
+/* ---- additions with no reference counterpart (measurement + multi-GPU sharding) --------------- */
+/* Restrict subsequent render calls to super-sampled rows [row_begin,row_end) (0,0 = whole image). */
+uint32_t fs_set_row_range(fs_renderer *r, uint32_t row_begin, uint32_t row_end);
+/* Device time (CUDA events on the compute stream) of the most recent render kernel, in ms. Syncs. */
+uint32_t fs_last_render_ms(fs_renderer *r, float *ms);
+/* Count executed steps (perturbation + LA + AT) of subsequent renders into a device counter. */
+uint32_t fs_enable_step_counter(fs_renderer *r, int32_t enable);
+uint32_t fs_read_step_counter(fs_renderer *r, uint64_t *steps);
+/* Device pointer of the iteration buffer (for NCCL gather by the host plumbing). */
+void *fs_device_iter_buffer(fs_renderer *r);
+/* Number of kernels this renderer has launched so far. */
+uint64_t fs_kernel_launch_count(const fs_renderer *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS_GPU_H */
