@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the per-pixel render path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libfsgpu.so on N B200s)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU port on host cores
+
+Workload (config.workload): View #5, GpuHDRx32PerturbedLAv2, 3840x2160, AA 1, u32 iterations,
+maxIter 4,718,592 (BASELINE.json configs[2]/[3]; the largest "View 5/14 perturb+LA" case whose orbit this
+image can produce offline).  One step = ClearMemory + one full render of the frame.
+
+* value       pixel-iterations/s = ReductionResults.Sum / device time of the render kernel(s), inputs
+              (orbit, LA table) already resident in HBM; CUDA events on the launching stream, max over ranks.
+* e2e         same metric through the public C-ABI call sequence with HOST buffers inside the timed region:
+              InitializePerturb (H2D orbit + LA table), ClearMemory, RenderPerturbLAv2, RenderCurrent
+              (AA/palette/reduction + D2H of the iteration buffer and the 24-byte reduction).
+* roofline    FP32 issue: executed steps x FP32 instructions per step / kernel time,
+              against the FFMA issue peak measured live by a micro-kernel on the same GPU.
+* cpu_baseline the oracle's CPU port of the same kernel on a bounded pixel sample (all host threads).
+N > 1: 4-row tile bands are dealt round-robin to ranks (no data-path collective inside the render);
+the orbit/LA blob is replicated by an NCCL broadcast and the iteration buffer is merged on rank 0 with an
+NCCL reduce (disjoint rows, so SUM == gather).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 3840, 2160
+WORKLOAD = "view5_GpuHDRx32PerturbedLAv2_3840x2160_aa1_u32_maxiter4718592"
+METRIC = "pixel-iters/sec (device-timed) for View 5 perturb+LA"
+FP32_INSTR_PER_PERTURB_STEP = 20  # HDRx32 perturbation step, mantissa ops only
+FP32_INSTR_PER_LA_STEP = 22
+
+
+def _clock_sampler(stop, samples, gpu_index):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
+            if out:
+                samples.append([x.strip() for x in out[0].split(",")])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def _clock_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None, "reasons": reasons,
+            "samples": len(samples)}
+
+
+def build_inputs(width, height):
+    from fractalshark_b200 import Numeric
+    from fractalshark_b200.host_inputs import LaTable, Orbit, View
+    from fractalshark_b200.views import VIEW5
+    p = VIEW5
+    view = View(p.min_x, p.min_y, p.max_x, p.max_y, width, height)
+    t0 = time.time()
+    orbit = Orbit(view, Numeric.HDR32, p.num_iterations, True)
+    t1 = time.time()
+    la = LaTable(orbit, 4)
+    t2 = time.time()
+    return view, view.coords(Numeric.HDR32), orbit, la, p.num_iterations, {"orbit_s": t1 - t0, "la_s": t2 - t1}
+
+
+def cpu_port_sample(coords, orbit, la, n_iter, threads):
+    """Oracle CPU port (the checker, timed as a baseline only) on every 16th row x every 16th column."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_cpu
+    from fractalshark_b200 import RenderAlgorithm
+    row_step = col_step = 16
+    t0 = time.time()
+    iters, steps = oracle_cpu.render_lav2(RenderAlgorithm.GpuHDRx32PerturbedLAv2, WIDTH, HEIGHT, coords, orbit, la,
+                                          n_iter, rows=(0, HEIGHT), col_step=col_step, row_step=row_step,
+                                          threads=threads)
+    dt = time.time() - t0
+    total = int(iters[0:HEIGHT:row_step, 0:WIDTH:col_step].sum())
+    return total / dt, dt, f"every {row_step}th row x every {col_step}th column of the frame " \
+                           f"({(HEIGHT // row_step) * (WIDTH // col_step)} pixels, {steps} executed steps, {dt:.1f} s)"
+
+
+def run_reference_arm(args, rank, world):
+    """Reference arm of this tier: the CPU port of the path on the box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_cpu
+    _, coords, orbit, la, n_iter, _ = build_inputs(WIDTH, HEIGHT)
+    threads = oracle_cpu.hardware_threads()
+    vals, times, sample = [], [], ""
+    for i in range(args.warmup + args.steps):
+        v, dt, sample = cpu_port_sample(coords, orbit, la, n_iter, threads)
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pixel-iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32 (HDRx32)",
+            "data": "synthetic (View #5 preset coordinates, orbit + LA table generated in-process)",
+            "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": "pixel-iters/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pixel-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fractalshark_b200 import RenderAlgorithm
+    from fractalshark_b200.gpu_renderer import GPURenderer
+
+    if not torch.cuda.is_available() or not GPURenderer.TestCudaIsWorking():
+        raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    alg = RenderAlgorithm.GpuHDRx32PerturbedLAv2
+    view, coords, orbit, la, n_iter, gen_times = build_inputs(WIDTH, HEIGHT)
+
+    # ---- replicate the orbit + LA blob with an NCCL broadcast (north_star) -------------------------------
+    orbit_np = orbit.as_numpy()
+    if world > 1:
+        blob = torch.from_numpy(np.ascontiguousarray(orbit_np).reshape(-1)).cuda()
+        dist.broadcast(blob, src=0)
+        torch.cuda.synchronize()
+        assert bytes(blob[:64].cpu().numpy()) == bytes(orbit_np.reshape(-1)[:64]), "orbit replica mismatch"
+
+    r = GPURenderer(local_rank)
+    assert r.InitializeMemory(WIDTH, HEIGHT, 1, iter_bytes=4) == 0
+    assert r.SetShard(world, rank) == 0
+    gen = 1
+    assert r.InitializePerturb(gen, orbit, 0, None, la) == 0
+    assert r.SyncComputeStream() == 0
+    launches0 = r.KernelLaunchCount()
+
+    h2d = orbit.count * orbit.elem_bytes + la.num_las * la.las_elem_bytes + la.num_stages * 8 + la.at_bytes
+    hp, wp = r.buffer_shape()
+    d2h = hp * wp * 4 + 24
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step_resident():
+        flush.zero_()
+        torch.cuda.synchronize()
+        r.ClearMemory()
+        rc = r.RenderPerturbLAv2(alg, coords, n_iter)
+        assert rc == 0, GPURenderer.ConvertErrorToString(rc)
+        assert r.SyncComputeStream() == 0
+        return r.LastRenderMs()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+
+    # ---- timed region: K steps, device-timed ---------------------------------------------------------------
+    stop, samples = threading.Event(), []
+    sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
+    sampler.start()
+    r.EnableStepCounter(True)
+    barrier()
+    t_wall0 = time.time()
+    kernel_ms = [step_resident() for _ in range(args.steps)]
+    barrier()
+    wall_s = time.time() - t_wall0
+    exec_steps = r.ReadStepCounter() / args.steps
+    r.EnableStepCounter(False)
+    launches_timed = r.KernelLaunchCount() - launches0 - args.warmup
+    stop.set()
+    sampler.join()
+
+    rc, iters, _, red = r.RenderCurrent(n_iter)
+    assert rc == 0
+    local_sum = int(iters[:HEIGHT, :WIDTH].sum())  # this rank's rows (others are zero)
+
+    # ---- merge the iteration buffer on rank 0 (NCCL reduce of disjoint rows == gather) ----------------------
+    total_sum, max_ms = local_sum, sum(kernel_ms)
+    gather_ms = None
+    if world > 1:
+        dev_iters = torch.from_numpy(iters.view(np.int32)).cuda()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.reduce(dev_iters, dst=0, op=dist.ReduceOp.SUM)
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms = e0.elapsed_time(e1)
+        t = torch.tensor([float(max_ms)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_ms = float(t.item())
+        s = torch.tensor([local_sum], device="cuda", dtype=torch.int64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        total_sum = int(s.item())
+        es = torch.tensor([exec_steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(es, op=dist.ReduceOp.SUM)
+        exec_steps = float(es.item())
+        if rank == 0:
+            merged = dev_iters.cpu().numpy().view(np.uint32)
+            assert int(merged[:HEIGHT, :WIDTH].astype(np.int64).sum()) == total_sum
+
+    ms_per_step = max_ms / args.steps
+    value = total_sum / (ms_per_step * 1e-3)
+
+    # ---- e2e: public call sequence with host buffers (every step re-uploads orbit + LA, reads results) ------
+    def step_e2e(g):
+        rc = r.InitializePerturb(g, orbit, 0, None, la)
+        assert rc == 0
+        r.ClearMemory()
+        assert r.RenderPerturbLAv2(alg, coords, n_iter) == 0
+        rc, it, _, rd = r.RenderCurrent(n_iter)
+        assert rc == 0
+        return rd["Sum"]
+
+    for _ in range(2):
+        gen += 1
+        step_e2e(gen)
+    barrier()
+    t0 = time.time()
+    e2e_sum = 0
+    for _ in range(args.steps):
+        gen += 1
+        e2e_sum = step_e2e(gen)
+    barrier()
+    e2e_s = (time.time() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = total_sum / e2e_s
+
+    # ---- roofline -----------------------------------------------------------------------------------------------
+    peak = GPURenderer.MeasureFp32IssuePeak(local_rank)  # FFMA thread-instr/s, measured live
+    # executed steps are dominated by perturbation steps on this view (LA/AT steps < 1 %); credit 20 FP32 each
+    achieved = exec_steps * FP32_INSTR_PER_PERTURB_STEP / (ms_per_step * 1e-3)
+    roofline = {"bound": "fp32_issue", "achieved": achieved / 1e12, "peak": peak * world / 1e12, "unit": "T FP32 instr/s",
+                "frac": achieved / (peak * world), "traffic": None,
+                "note": "compute-bound scalar path (SURVEY.md 8d): not HBM, not tensor. achieved = executed "
+                        "steps/launch (device counter) x 20 FP32 mantissa instr per HDRx32 step / kernel time; "
+                        "peak = FFMA issue rate measured live by fs_measure_fp32_issue_peak on this GPU "
+                        "(MEASURED_PEAKS.json has only HBM/bf16 peaks).",
+                "executed_steps_per_launch": exec_steps,
+                "skip_factor": total_sum / max(exec_steps, 1.0)}
+
+    line = {"metric": METRIC, "value": value, "unit": "pixel-iters/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32+i32 (HDRx32)",
+            "data": "synthetic (View #5 preset coordinates; orbit via GMP + LA table generated in-process, untimed: "
+                    f"{gen_times['orbit_s']:.3f}s + {gen_times['la_s']:.3f}s)",
+            "config": {"workload": WORKLOAD, "l2": "flushed between timed iterations (256 MiB memset)",
+                       "sharding": f"4-row tile bands round-robin over {world} rank(s)",
+                       "orbit_entries": orbit.count, "la_records": la.num_las, "la_stages": la.stage_count},
+            "clocks": _clock_summary(samples),
+            "e2e": {"value": e2e_value, "unit": "pixel-iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches_timed),
+            "roofline": roofline,
+            "wall_ms_per_step_incl_flush": wall_s * 1e3 / args.steps,
+            "sum_pixel_iters": total_sum}
+    if gather_ms is not None:
+        line["gather_ms"] = gather_ms
+
+    if rank == 0:
+        # reference CUDA kernels (oracle/_ref, the checker) timed on the same GPU and inputs, for context
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import ref_renderer
+            if ref_renderer.available() and world == 1:
+                rr = ref_renderer.RefGPURenderer()
+                assert rr.InitializeMemory(WIDTH, HEIGHT, 1, iter_bytes=4) == 0
+                assert rr.InitializePerturb(1, orbit, 0, None, la) == 0
+                ms = []
+                for i in range(3):
+                    flush.zero_()
+                    torch.cuda.synchronize()
+                    rr.ClearMemory()
+                    assert rr.RenderPerturbLAv2(alg, coords, n_iter) == 0
+                    assert rr.SyncComputeStream() == 0
+                    ms.append(rr.LastRenderMs())
+                rc, ref_iters, _, ref_red = rr.RenderCurrent(n_iter)
+                exact = float((ref_iters[:HEIGHT, :WIDTH] == iters[:HEIGHT, :WIDTH]).mean())
+                line["reference_cuda_kernel"] = {"ms_per_step": min(ms[1:]), "value": ref_red["Sum"] / (min(ms[1:]) * 1e-3),
+                                                 "unit": "pixel-iters/s", "pixels_exact_vs_ours": exact,
+                                                 "what": "reference mandel_1xHDR_float_perturb_lav2 built for sm_100a"}
+                rr.close()
+        except Exception as e:  # the checker is optional here
+            line["reference_cuda_kernel"] = {"unavailable": repr(e)[:200]}
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_cpu
+            threads = oracle_cpu.hardware_threads()
+            v, dt, sample = cpu_port_sample(coords, orbit, la, n_iter, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "pixel-iters/s", "cores": threads, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

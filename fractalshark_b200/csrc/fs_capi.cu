@@ -85,7 +85,7 @@ struct fs_renderer {
     uint32_t width = 0, height = 0, aa = 0, iter_bytes = 0;
     uint32_t w_block = 0, h_block = 0, color_w = 0, color_h = 0;
     size_t n_cu = 0, n_color_cu = 0;
-    uint32_t row_begin = 0, row_end = 0;
+    uint32_t shard_count = 1, shard_index = 0;
     unsigned int *tile_counter = nullptr;
     unsigned long long *step_counter = nullptr;
     bool count_steps = false;
@@ -266,16 +266,6 @@ uint32_t end_render(fs_renderer *r) {
     return cudaGetLastError();
 }
 
-void rows(const fs_renderer *r, int &b, int &e) {
-    if (r->row_end > r->row_begin) {
-        b = (int)r->row_begin;
-        e = (int)(r->row_end < r->height ? r->row_end : r->height);
-    } else {
-        b = 0;
-        e = (int)r->height;
-    }
-}
-
 template <class T> T load_pod(const void *p) {
     T v;
     memcpy(&v, p, sizeof(T));
@@ -302,7 +292,8 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     A.width = (int)r->width;
     A.height = (int)r->height;
     A.pitch = (int)(r->w_block * NB_THREADS_W);
-    rows(r, A.row_begin, A.row_end);
+    A.shard_count = (int)r->shard_count;
+    A.shard_index = (int)r->shard_index;
     A.dx = load_pod<Real>(dx);
     A.dy = load_pod<Real>(dy);
     A.centerX = load_pod<Real>(cx);
@@ -345,7 +336,8 @@ uint32_t launch_direct(fs_renderer *r, const void *cx, const void *cy, const voi
     A.width = (int)r->width;
     A.height = (int)r->height;
     A.pitch = (int)(r->w_block * NB_THREADS_W);
-    rows(r, A.row_begin, A.row_end);
+    A.shard_count = (int)r->shard_count;
+    A.shard_index = (int)r->shard_index;
     A.cx = load_pod<M>(cx); A.cy = load_pod<M>(cy); A.dx = load_pod<M>(dx); A.dy = load_pod<M>(dy);
     A.n_iterations = (IterT)n_iter;
     A.tile_counter = r->tile_counter;
@@ -375,6 +367,22 @@ template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaSt
 #undef FS_POST
     r->launches += 2;
     return cudaGetLastError();
+}
+
+// FP32 issue-rate probe: 16 independent FFMA chains per thread, no memory traffic.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float *sink, int iters, float seed) {
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = seed + (float)(threadIdx.x + k);
+    const float m = 0.999f, c = 0.001f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) a[k] = __fmaf_rn(a[k], m, c);
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += a[k];
+    if (s == 12345.678f) *sink = s;
 }
 
 void CUDART_CB done_trampoline(void *p) {
@@ -474,7 +482,6 @@ uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, u
     const uint32_t wcb = r->color_w / NB_THREADS_W + (r->color_w % NB_THREADS_W != 0);
     const uint32_t hcb = r->color_h / NB_THREADS_H + (r->color_h % NB_THREADS_H != 0);
     r->n_color_cu = (size_t)wcb * NB_THREADS_W * hcb * NB_THREADS_H;
-    r->row_begin = r->row_end = 0;
 
     // geometry change drops cached orbit/LA uploads (ResetPerturb::Yes, GPU_Render.cu:358)
     reset_perturb(r);
@@ -625,9 +632,10 @@ const char *fs_convert_error_to_string(uint32_t err) {
 uint32_t fs_get_width(const fs_renderer *r) { return r->width; }
 uint32_t fs_get_height(const fs_renderer *r) { return r->height; }
 
-uint32_t fs_set_row_range(fs_renderer *r, uint32_t row_begin, uint32_t row_end) {
-    r->row_begin = row_begin;
-    r->row_end = row_end;
+uint32_t fs_set_shard(fs_renderer *r, uint32_t shard_count, uint32_t shard_index) {
+    if (!r || shard_count == 0 || shard_index >= shard_count) return FS_ERROR_UNSUPPORTED;
+    r->shard_count = shard_count;
+    r->shard_index = shard_index;
     return 0;
 }
 
@@ -654,6 +662,37 @@ uint32_t fs_read_step_counter(fs_renderer *r, uint64_t *steps) {
     if (err != cudaSuccess) return err;
     err = cudaStreamSynchronize(r->compute);
     *steps = v;
+    return err;
+}
+
+uint32_t fs_measure_fp32_issue_peak(int32_t device, double *ffma_per_second) {
+    DeviceGuard g(device);
+    int sms = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err != cudaSuccess) return err;
+    float *sink = nullptr;
+    err = cudaMalloc(&sink, sizeof(float));
+    if (err != cudaSuccess) return err;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        ffma_peak_kernel<<<blocks, threads>>>(sink, iters, 1.0f + rep);
+        cudaEventRecord(e1);
+        err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double n = (double)blocks * threads * (double)iters * 16.0;
+        if (rep > 0 && n / (ms * 1e-3) > best) best = n / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *ffma_per_second = best;
     return err;
 }
 

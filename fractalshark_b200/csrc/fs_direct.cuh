@@ -25,7 +25,7 @@ template <> struct DirectOps<double> {
 template <class M, class IterT> struct DirectArgs {
     IterT *out;
     int width, height, pitch;
-    int row_begin, row_end;
+    int shard_count, shard_index; // 4-row tile bands are dealt round-robin to shards (multi-GPU)
     M cx, cy, dx, dy;
     IterT n_iterations;
     unsigned int *tile_counter;
@@ -36,7 +36,7 @@ template <class M, class IterT, int P>
 __global__ void __launch_bounds__(256) direct_kernel(const DirectArgs<M, IterT> A) {
     const int lane = threadIdx.x & 31;
     const int tiles_x = (A.width + 7) >> 3;
-    const int tiles_y = (A.row_end - A.row_begin + 3) >> 2;
+    const int tiles_y = (((A.height + 3) >> 2) - A.shard_index + A.shard_count - 1) / A.shard_count;
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     const IterT n_iter = A.n_iterations - (IterT)(P - 1);
     unsigned long long steps = 0;
@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) direct_kernel(const DirectArgs<M, IterT> 
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
         const int X = (int)(tile % tiles_x) * 8 + (lane & 7);
-        const int Y = A.row_begin + (int)(tile / tiles_x) * 4 + (lane >> 3);
-        if (X >= A.width || Y >= A.row_end) continue;
+        const int Y = ((int)(tile / tiles_x) * A.shard_count + A.shard_index) * 4 + (lane >> 3);
+        if (X >= A.width || Y >= A.height) continue;
 
         const M x0 = fma_(DirectOps<M>::from_int(X), A.dx, A.cx);
         const M y0 = fma_(DirectOps<M>::from_int(Y), A.dy, A.cy);

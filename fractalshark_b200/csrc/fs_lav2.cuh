@@ -52,7 +52,7 @@ template <class Num, class IterT> struct Lav2Args {
     int la_valid;
     int use_at;
     int width, height, pitch;
-    int row_begin, row_end;  // rows [row_begin,row_end) rendered by this device (multi-GPU sharding)
+    int shard_count, shard_index; // 4-row tile bands are dealt round-robin to shards (multi-GPU)
     typename Num::Real dx, dy, centerX, centerY;
     IterT n_iterations;
     unsigned int *tile_counter;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
 
     const int lane = threadIdx.x & 31;
     const int tiles_x = (A.width + 7) >> 3;
-    const int tiles_y = (A.row_end - A.row_begin + 3) >> 2;
+    const int tiles_y = (((A.height + 3) >> 2) - A.shard_index + A.shard_count - 1) / A.shard_count;
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     unsigned long long steps = 0;
 
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
         if (tile >= n_tiles) break;
 
         const int X = (int)(tile % tiles_x) * 8 + (lane & 7);
-        const int Y = A.row_begin + (int)(tile / tiles_x) * 4 + (lane >> 3);
-        if (X >= A.width || Y >= A.row_end) continue;
+        const int Y = ((int)(tile / tiles_x) * A.shard_count + A.shard_index) * 4 + (lane >> 3);
+        if (X >= A.width || Y >= A.height) continue;
 
         IterT iter = 0;
         IterT RefIteration = 0;

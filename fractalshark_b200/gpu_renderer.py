@@ -140,8 +140,17 @@ class GPURenderer:
         return int(self._lib.fs_get_height(self._h))
 
     # ---- additions (measurement / sharding) ----------------------------------------------------
-    def SetRowRange(self, row_begin: int, row_end: int) -> int:
-        return int(self._lib.fs_set_row_range(self._h, row_begin, row_end))
+    def SetShard(self, shard_count: int, shard_index: int) -> int:
+        """Render only the 4-row tile bands b with b % shard_count == shard_index (multi-GPU sharding)."""
+        return int(self._lib.fs_set_shard(self._h, shard_count, shard_index))
+
+    @staticmethod
+    def MeasureFp32IssuePeak(device: int = 0) -> float:
+        v = C.c_double(0)
+        rc = N.gpu_lib().fs_measure_fp32_issue_peak(device, C.byref(v))
+        if rc:
+            raise RuntimeError(GPURenderer.ConvertErrorToString(rc))
+        return float(v.value)
 
     def LastRenderMs(self) -> float:
         ms = C.c_float(0)

@@ -149,8 +149,12 @@ uint32_t fs_get_width(const fs_renderer *r);          /* GPU_Render.h:157 */
 uint32_t fs_get_height(const fs_renderer *r);         /* GPU_Render.h:158 */
 
 /* ---- additions with no reference counterpart (measurement + multi-GPU sharding) --------------- */
-/* Restrict subsequent render calls to super-sampled rows [row_begin,row_end) (0,0 = whole image). */
-uint32_t fs_set_row_range(fs_renderer *r, uint32_t row_begin, uint32_t row_end);
+/* Multi-GPU sharding: subsequent render calls compute only the 4-row tile bands b with
+ * b % shard_count == shard_index (1,0 = whole image). Cells of other shards are left untouched. */
+uint32_t fs_set_shard(fs_renderer *r, uint32_t shard_count, uint32_t shard_index);
+/* Measured FP32 issue peak of `device` (FFMA thread-instructions per second, micro-kernel with 16
+ * independent chains per thread): the denominator of the roofline fraction reported by bench.py. */
+uint32_t fs_measure_fp32_issue_peak(int32_t device, double *ffma_per_second);
 /* Device time (CUDA events on the compute stream) of the most recent render kernel, in ms. Syncs. */
 uint32_t fs_last_render_ms(fs_renderer *r, float *ms);
 /* Count executed steps (perturbation + LA + AT) of subsequent renders into a device counter. */

@@ -1,0 +1,51 @@
+"""Shared parity cases: (name, view id, w, h, algorithm, n_iter (None = preset), iter_bytes)."""
+from fractalshark_b200 import RenderAlgorithm as A
+
+SMALL_CASES = [
+    ("v0_gpu1x64", 0, 96, 54, A.Gpu1x64, 1024, 4),
+    ("v0_gpu1x32", 0, 96, 54, A.Gpu1x32, 1024, 4),
+    ("v0_gpu1x64_u64", 0, 50, 37, A.Gpu1x64, 300, 8),          # ragged size (not a multiple of 16x8)
+    ("v5_hdr32_lav2", 5, 96, 54, A.GpuHDRx32PerturbedLAv2, None, 4),
+    ("v5_hdr32_lav2_u64", 5, 50, 37, A.GpuHDRx32PerturbedLAv2, None, 8),
+    ("v5_hdr32_lav2_po", 5, 64, 36, A.GpuHDRx32PerturbedLAv2PO, 3000, 4),
+    ("v5_hdr32_lav2_lao", 5, 96, 54, A.GpuHDRx32PerturbedLAv2LAO, None, 4),
+    ("v1_hdr32_lav2", 1, 96, 54, A.GpuHDRx32PerturbedLAv2, None, 4),
+    ("v1_hdr32_lav2_po", 1, 96, 54, A.GpuHDRx32PerturbedLAv2PO, None, 4),
+    ("v19_hdr32_lav2_capped", 19, 64, 36, A.GpuHDRx32PerturbedLAv2, 200000, 4),
+]
+
+
+def make_inputs(view_id, w, h, alg, n_iter, iter_bytes):
+    from fractalshark_b200 import traits
+    from fractalshark_b200.host_inputs import LaTable, Orbit, View
+    from fractalshark_b200.views import PRESETS
+    p = PRESETS[view_id]
+    n_iter = n_iter or p.num_iterations
+    t = traits(alg)
+    view = View(p.min_x, p.min_y, p.max_x, p.max_y, w, h)
+    coords = view.coords(t.numeric)
+    orbit = la = None
+    if t.family == "lav2":
+        orbit = Orbit(view, t.numeric, n_iter, True)
+        la = LaTable(orbit, iter_bytes)
+    return view, coords, orbit, la, n_iter
+
+
+def render(renderer_cls, w, h, alg, coords, orbit, la, n_iter, iter_bytes, want_colors=False, aa=1):
+    from fractalshark_b200 import traits
+    r = renderer_cls()
+    rc = r.InitializeMemory(w, h, aa, iter_bytes=iter_bytes)
+    assert rc == 0, rc
+    if orbit is not None:
+        rc = r.InitializePerturb(1, orbit, 0, None, la)
+        assert rc == 0, rc
+    r.ClearMemory()
+    if traits(alg).family == "lav2":
+        rc = r.RenderPerturbLAv2(alg, coords, n_iter)
+    else:
+        rc = r.Render(alg, coords, n_iter, 1)
+    assert rc == 0, rc
+    rc, iters, colors, red = r.RenderCurrent(n_iter, want_colors=want_colors)
+    assert rc == 0, rc
+    r.close()
+    return iters, colors, red

@@ -1,0 +1,50 @@
+"""Generates tests/golden/ref_gpu_small.npz: iteration buffers produced by the REFERENCE's own CUDA kernels
+(oracle/_ref/libref_gpurender.so, built from /root/reference for sm_100a by oracle/Makefile) for the
+small parity cases of tests/cases.py.  Run on a B200 box:
+
+    gpurun -- 'python tests/golden/make_golden.py gpurun_out/ref_gpu_small.npz'
+
+then copy the file to tests/golden/.  Inputs (orbit, LA table, coordinates) come from the in-tree
+generator (libfshost.so) and are deterministic; their CRC32 is stored beside each buffer so a drift of
+the generator is detected instead of silently invalidating the fixture.
+"""
+import os
+import sys
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import cases  # noqa: E402
+import ref_renderer  # noqa: E402
+
+
+def inputs_crc(coords, orbit, la):
+    crc = 0
+    for k in sorted(coords):
+        crc = zlib.crc32(coords[k], crc)
+    if orbit is not None:
+        crc = zlib.crc32(orbit.as_numpy().tobytes(), crc)
+    if la is not None and la.num_las:
+        crc = zlib.crc32(la.las_numpy().tobytes(), crc)
+        crc = zlib.crc32(la.stages_numpy().tobytes(), crc)
+    return crc
+
+
+def main(out_path):
+    out = {}
+    for name, view_id, w, h, alg, n_iter, ib in cases.SMALL_CASES:
+        _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
+        iters, _, red = cases.render(ref_renderer.RefGPURenderer, w, h, alg, coords, orbit, la, n, ib)
+        out[name] = iters[:h, :w].copy()
+        out[name + "__crc"] = np.array([inputs_crc(coords, orbit, la)], dtype=np.uint64)
+        print(name, iters[:h, :w].shape, red, flush=True)
+    np.savez_compressed(out_path, **out)
+    print("wrote", out_path)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "ref_gpu_small.npz"))

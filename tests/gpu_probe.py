@@ -63,7 +63,7 @@ if __name__ == "__main__":
     W, H = (512, 288) if small else (3840, 2160)
     run(0, W, H, A.Gpu1x64, 2048 if small else 65536)
     run(0, W, H, A.Gpu1x32, 2048 if small else 65536)
-    run(5, W, H, A.GpuHDRx32PerturbedLAv2PO, 20000 if small else None)
+    run(5, W, H, A.GpuHDRx32PerturbedLAv2PO, 20000)
     run(5, W, H, A.GpuHDRx32PerturbedLAv2)
     run(5, W, H, A.GpuHDRx32PerturbedLAv2LAO)
     run(5, W, H, A.GpuHDRx32PerturbedLAv2, iter_bytes=8)

@@ -1,0 +1,83 @@
+"""TEST INFRASTRUCTURE: ctypes wrapper of oracle/liboracle.so (CPU restatement of the reference kernels)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from fractalshark_b200.algorithms import traits
+from fractalshark_b200.gpu_renderer import NB_THREADS_H, NB_THREADS_W, _round_up
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(ORACLE_LIB)
+        V, I, U64 = C.c_void_p, C.c_int, C.c_uint64
+        L.orc_render_lav2.restype = U64
+        L.orc_render_lav2.argtypes = [I, I, I, V, U64, V, V, V, U64, I, I, I, I, V, V, V, V, U64, V, I, I, I, I, I]
+        L.orc_render_direct.restype = U64
+        L.orc_render_direct.argtypes = [I, I, I, I, V, V, V, V, U64, I, V, I, I, I]
+        L.orc_post.restype = None
+        L.orc_post.argtypes = [I, V, I, I, I, V, C.c_uint32, C.c_uint32, U64, V, V]
+        L.orc_hardware_threads.restype = I
+        _lib = L
+    return _lib
+
+
+def _buf(b: bytes):
+    return C.cast(C.create_string_buffer(b, len(b)), C.c_void_p)
+
+
+def hardware_threads() -> int:
+    return int(lib().orc_hardware_threads())
+
+
+def render_lav2(alg, w, h, coords, orbit, la, n_iter, iter_bytes=4, rows=None, col_step=1, row_step=1, threads=1, out=None):
+    """Returns (iters[hp, wp], executed_steps). Only rows in `rows` / every col_step-th column are computed."""
+    t = traits(alg)
+    hp, wp = _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)
+    dt = np.uint32 if iter_bytes == 4 else np.uint64
+    if out is None:
+        out = np.zeros((hp, wp), dtype=dt)
+    rb, re = rows if rows is not None else (0, h)
+    d = orbit.descriptor()
+    if la is not None:
+        l = la.descriptor()
+        largs = (l.las, l.stages, l.at, l.la_stage_count, l.use_at, l.is_valid)
+    else:
+        largs = (None, None, None, 0, 0, 0)
+    steps = lib().orc_render_lav2(int(t.numeric), iter_bytes, int(t.mode), d.elements, d.uncompressed_count, *largs,
+                                  w, h, _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]),
+                                  _buf(coords["center_y"]), n_iter, out.ctypes.data, rb, re, col_step, row_step, threads)
+    if steps == 2 ** 64 - 1:
+        raise NotImplementedError(f"oracle has no restatement for {alg!r}")
+    return out, int(steps)
+
+
+def render_direct(alg, w, h, coords, n_iter, prec=1, iter_bytes=4, rows=None, threads=1):
+    t = traits(alg)
+    hp, wp = _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)
+    out = np.zeros((hp, wp), dtype=np.uint32 if iter_bytes == 4 else np.uint64)
+    rb, re = rows if rows is not None else (0, h)
+    steps = lib().orc_render_direct(int(t.numeric), iter_bytes, w, h, _buf(coords["cx"]), _buf(coords["cy"]),
+                                    _buf(coords["dx"]), _buf(coords["dy"]), n_iter, prec, out.ctypes.data, rb, re,
+                                    threads)
+    if steps == 2 ** 64 - 1:
+        raise NotImplementedError(f"oracle has no restatement for {alg!r}")
+    return out, int(steps)
+
+
+def post(iters, w, h, aa, palette, aux_depth, n_iter):
+    iter_bytes = iters.dtype.itemsize
+    palette = np.ascontiguousarray(palette, dtype=np.uint16)
+    colors = np.zeros((h // aa, w // aa, 4), dtype=np.uint16)
+    red = np.zeros(3, dtype=np.uint64)
+    lib().orc_post(iter_bytes, iters.ctypes.data, w, h, aa, palette.ctypes.data, palette.shape[0], aux_depth, n_iter,
+                   colors.ctypes.data, red.ctypes.data)
+    return colors, {"Min": int(red[0]), "Max": int(red[1]), "Sum": int(red[2])}
