@@ -1,0 +1,156 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C-ABI of libfsgpu.so."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_cpu
+import ref_renderer
+from fractalshark_b200 import RenderAlgorithm as A
+from fractalshark_b200 import Numeric, traits
+from fractalshark_b200.gpu_renderer import GPURenderer, default_palette
+from fractalshark_b200.sharding import merge_shards, rows_of_shard
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_gpu_small.npz")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize("case", cases.SMALL_CASES, ids=[c[0] for c in cases.SMALL_CASES])
+def test_small_cases_bit_exact_vs_oracle_and_golden(golden, case):
+    """Bit-exact against the CPU oracle and against the committed reference-kernel fixtures."""
+    name, view_id, w, h, alg, n_iter, ib = case
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
+    got, _, red = cases.render(GPURenderer, w, h, alg, coords, orbit, la, n, ib)
+    np.testing.assert_array_equal(got[:h, :w], golden[name])
+    if traits(alg).family == "lav2":
+        want, _ = oracle_cpu.render_lav2(alg, w, h, coords, orbit, la, n, iter_bytes=ib, threads=oracle_cpu.hardware_threads())
+    else:
+        want, _ = oracle_cpu.render_direct(alg, w, h, coords, n, 1, iter_bytes=ib, threads=oracle_cpu.hardware_threads())
+    np.testing.assert_array_equal(got[:h, :w], want[:h, :w])
+    assert red["Sum"] == int(got[:h, :w].astype(np.uint64).sum())
+    assert red["Min"] == int(got[:h, :w].min()) and red["Max"] == int(got[:h, :w].max())
+    # cells outside width x height stay cleared
+    assert not got[h:, :].any() and not got[:, w:].any()
+
+
+FULL_CASES = [
+    ("v0_gpu1x64_full", 0, 3840, 2160, A.Gpu1x64, 65536, 4, 1.0),          # FP64 direct: bit-exact required
+    ("v0_gpu1x32_full", 0, 3840, 2160, A.Gpu1x32, 65536, 4, 1.0),
+    ("v5_hdr32_lav2_full", 5, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None, 4, 0.999),   # north_star tolerance
+    ("v5_hdr32_lav2_po_full", 5, 1920, 1080, A.GpuHDRx32PerturbedLAv2PO, 20000, 4, 0.999),
+    ("v5_hdr32_lav2_u64_full", 5, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None, 8, 0.999),
+    ("v1_hdr32_lav2_full", 1, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None, 4, 0.999),
+]
+
+
+@pytest.mark.skipif(not ref_renderer.available(), reason="oracle/_ref (reference CUDA kernels) not built")
+@pytest.mark.parametrize("case", FULL_CASES, ids=[c[0] for c in FULL_CASES])
+def test_full_size_vs_reference_cuda_kernels(case):
+    """BASELINE.json sizes against the reference's own kernels on the same GPU and inputs.
+    Tolerance (north_star): FP64/FP32 direct bit-exact; HDRx32/LA >= 99.9 % exact and |d iter| <= 1 elsewhere."""
+    name, view_id, w, h, alg, n_iter, ib, min_exact = case
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
+    got, _, red = cases.render(GPURenderer, w, h, alg, coords, orbit, la, n, ib)
+    ref, _, ref_red = cases.render(ref_renderer.RefGPURenderer, w, h, alg, coords, orbit, la, n, ib)
+    a, b = got[:h, :w].astype(np.int64), ref[:h, :w].astype(np.int64)
+    exact = float((a == b).mean())
+    assert exact >= min_exact, exact
+    if min_exact < 1.0:
+        assert int(np.abs(a - b).max()) <= 1
+    assert (red["Min"], red["Max"], red["Sum"]) == (ref_red["Min"], ref_red["Max"], ref_red["Sum"]) or min_exact < 1.0
+
+
+def test_full_size_properties_without_reference():
+    """Size-independent properties at 3840x2160: idempotence, sharded == unsharded, checksum of checksums,
+    u32 == u64, sampled rows == oracle."""
+    w, h, alg = 3840, 2160, A.GpuHDRx32PerturbedLAv2
+    _, coords, orbit, la, n = cases.make_inputs(5, w, h, alg, None, 4)
+    r = GPURenderer()
+    assert r.InitializeMemory(w, h, 1, iter_bytes=4) == 0
+    assert r.InitializePerturb(7, orbit, 0, None, la) == 0
+    outs = []
+    for _ in range(2):
+        r.ClearMemory()
+        assert r.RenderPerturbLAv2(alg, coords, n) == 0
+        rc, it, _, red = r.RenderCurrent(n)
+        assert rc == 0
+        outs.append(it.copy())
+        assert red["Sum"] == int(it[:h, :w].astype(np.uint64).sum())
+    np.testing.assert_array_equal(outs[0], outs[1])                       # idempotent / deterministic
+    # three shards merge to the unsharded frame; the shard Sums add up (checksum of checksums)
+    bufs, sums = [], 0
+    for s in range(3):
+        assert r.SetShard(3, s) == 0
+        r.ClearMemory()
+        assert r.RenderPerturbLAv2(alg, coords, n) == 0
+        rc, it, _, red = r.RenderCurrent(n)
+        rows = rows_of_shard(h, 3, s)
+        other = np.setdiff1d(np.arange(h), rows)
+        assert not it[other].any()                                        # other shards' cells untouched
+        bufs.append(it.copy())
+        sums += red["Sum"]
+    assert r.SetShard(1, 0) == 0
+    np.testing.assert_array_equal(merge_shards(bufs, h)[:h, :w], outs[0][:h, :w])
+    assert sums == int(outs[0][:h, :w].astype(np.uint64).sum())
+    # sampled rows against the CPU oracle
+    want, _ = oracle_cpu.render_lav2(alg, w, h, coords, orbit, la, n, rows=(0, h), row_step=270, col_step=7,
+                                     threads=oracle_cpu.hardware_threads())
+    np.testing.assert_array_equal(outs[0][0:h:270, 0:w:7], want[0:h:270, 0:w:7])
+    r.close()
+    # 64-bit iteration type gives the same counts
+    _, coords8, orbit8, la8, _ = cases.make_inputs(5, 960, 540, alg, None, 8)
+    it8, _, _ = cases.render(GPURenderer, 960, 540, alg, coords8, orbit8, la8, n, 8)
+    _, coords4, orbit4, la4, _ = cases.make_inputs(5, 960, 540, alg, None, 4)
+    it4, _, _ = cases.render(GPURenderer, 960, 540, alg, coords4, orbit4, la4, n, 4)
+    np.testing.assert_array_equal(it8.astype(np.uint64), it4.astype(np.uint64))
+
+
+@pytest.mark.parametrize("aa", [1, 2, 3, 4])
+def test_antialiasing_palette_reduction(aa):
+    """RenderCurrent: AA box filter + palette + Min/Max/Sum vs the oracle (and the reference when present)."""
+    w, h, alg, n = 96 * aa, 48 * aa, A.Gpu1x64, 300
+    _, coords, _, _, _ = cases.make_inputs(0, w, h, alg, n, 4)
+    iters, colors, red = cases.render(GPURenderer, w, h, alg, coords, None, None, n, 4, want_colors=True, aa=aa)
+    want_c, want_r = oracle_cpu.post(iters, w, h, aa, default_palette(), 0, n)
+    assert red == want_r
+    np.testing.assert_array_equal(colors.reshape(-1, 4)[: (h // aa) * (w // aa)].reshape(h // aa, w // aa, 4), want_c)
+    if ref_renderer.available():
+        _, rcol, rred = cases.render(ref_renderer.RefGPURenderer, w, h, alg, coords, None, None, n, 4, want_colors=True, aa=aa)
+        assert rred == red
+        np.testing.assert_array_equal(rcol.reshape(-1, 4)[: (h // aa) * (w // aa)], colors.reshape(-1, 4)[: (h // aa) * (w // aa)])
+
+
+def test_error_behaviour_matches_reference():
+    """Error codes and no-op-before-init behaviour (GPU_Render.cu:322-332, 626-628, 1007-1022)."""
+    r = GPURenderer()
+    _, coords, orbit, la, n = cases.make_inputs(1, 64, 32, A.GpuHDRx32PerturbedLAv2, None, 4)
+    assert r.RenderPerturbLAv2(A.GpuHDRx32PerturbedLAv2, coords, n) == 0      # not initialised: returns success, does nothing
+    assert r.InitializeMemory(64, 32, 5) == 10002                             # bad antialiasing
+    assert r.InitializeMemory(65, 32, 2) == 10003
+    assert r.InitializeMemory(64, 33, 2) == 10004
+    assert r.InitializeMemory(64, 32, 1) == 0
+    assert r.RenderPerturbLAv2(A.GpuHDRx32PerturbedLAv2, coords, n) == 10005  # no orbit uploaded
+    assert r.InitializePerturb(3, orbit, 0, None, la) == 0
+    assert r.RenderPerturbLAv2(A.GpuHDRx32PerturbedLAv2, coords, n) == 0
+    assert r.InitializeMemory(128, 32, 1) == 0                                # geometry change drops the cached orbit
+    assert r.RenderPerturbLAv2(A.GpuHDRx32PerturbedLAv2, coords, n) == 10005
+    assert "antialiasing" in GPURenderer.ConvertErrorToString(10002)
+    done = []
+    assert r.EnqueueComputeDoneCallback(lambda: done.append(1)) == 0
+    assert r.SyncComputeStream() == 0 and done == [1]
+    assert r.QueryComputeStream() == 0
+    r.close()
+
+
+def test_native_library_is_the_one_loaded():
+    """The CUDA path is the one that ran: libfsgpu.so is mapped into this process."""
+    maps = open("/proc/self/maps").read()
+    assert "libfsgpu.so" in maps

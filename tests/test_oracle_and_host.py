@@ -1,0 +1,134 @@
+"""CPU-only tests: oracle vs the golden fixtures (reference CUDA kernels on a B200), host-side logic,
+and the C-ABI library surface.  No GPU needed."""
+import ctypes
+import os
+import re
+import zlib
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_cpu
+from fractalshark_b200 import LAv2Mode, Numeric, PerturbExtras, RenderAlgorithm, traits
+from fractalshark_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_gpu_small.npz")
+
+
+@pytest.fixture(scope="module")
+def golden(built):
+    return np.load(GOLDEN)
+
+
+def _crc(coords, orbit, la):
+    crc = 0
+    for k in sorted(coords):
+        crc = zlib.crc32(coords[k], crc)
+    if orbit is not None:
+        crc = zlib.crc32(orbit.as_numpy().tobytes(), crc)
+    if la is not None and la.num_las:
+        crc = zlib.crc32(la.las_numpy().tobytes(), crc)
+        crc = zlib.crc32(la.stages_numpy().tobytes(), crc)
+    return crc
+
+
+@pytest.mark.parametrize("case", cases.SMALL_CASES, ids=[c[0] for c in cases.SMALL_CASES])
+def test_oracle_matches_reference_gpu_golden(golden, case):
+    """The CPU restatement reproduces, bit for bit, what the reference's own kernels produced on a B200."""
+    name, view_id, w, h, alg, n_iter, ib = case
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
+    assert int(golden[name + "__crc"][0]) == _crc(coords, orbit, la), "input generator drifted from the fixture"
+    t = traits(alg)
+    if t.family == "lav2":
+        got, _ = oracle_cpu.render_lav2(alg, w, h, coords, orbit, la, n, iter_bytes=ib, threads=oracle_cpu.hardware_threads())
+    else:
+        got, _ = oracle_cpu.render_direct(alg, w, h, coords, n, 1, iter_bytes=ib, threads=oracle_cpu.hardware_threads())
+    want = golden[name]
+    assert got.dtype == want.dtype
+    np.testing.assert_array_equal(got[:h, :w], want)
+
+
+def test_render_algorithm_enum_matches_reference_order():
+    # RenderAlgorithm.h:81-159
+    assert RenderAlgorithm.CpuHigh == 0 and RenderAlgorithm.Gpu1x32 == 11 and RenderAlgorithm.Gpu1x64 == 14
+    assert RenderAlgorithm.GpuHDRx32PerturbedBLA == 22 and RenderAlgorithm.GpuHDRx32PerturbedLAv2 == 42
+    assert RenderAlgorithm.GpuHDRx64PerturbedRCLAv2LAO == 59 and RenderAlgorithm.AUTO == 60 and RenderAlgorithm.MAX == 61
+    t = traits(RenderAlgorithm.GpuHDRx2x32PerturbedRCLAv2LAO)
+    assert (t.family, t.numeric, t.mode, t.pextras) == ("lav2", Numeric.HDR2X32, LAv2Mode.LAO, PerturbExtras.SimpleCompression)
+    assert traits(RenderAlgorithm.Gpu1x64PerturbedBLA).family == "bla"
+    assert traits(RenderAlgorithm.GpuHDRx32PerturbedScaled).pextras == PerturbExtras.Bad
+    for a in RenderAlgorithm:
+        traits(a)
+
+
+def test_c_abi_exports_every_declared_symbol(built):
+    """libfsgpu.so loads and exports exactly the entry points include/fs_gpu.h declares (no compute calls)."""
+    header = open(os.path.join(ROOT, "include", "fs_gpu.h")).read()
+    declared = set(re.findall(r"\b(fs_[a-z0-9_]+)\s*\(", header)) - {"fs_done_callback"}
+    lib = ctypes.CDLL(_native.GPU_LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(_native.GPU_SYMBOLS), declared ^ set(_native.GPU_SYMBOLS)
+    # error strings are usable without a device
+    s = _native.gpu_lib().fs_convert_error_to_string(10002).decode()
+    assert "antialiasing" in s
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_native, "_gpu", None)
+    monkeypatch.setattr(_native, "GPU_LIB_PATH", "/nonexistent/libfsgpu.so")
+    with pytest.raises(_native.NativeLibraryMissing):
+        _native.gpu_lib()
+
+
+def test_la_table_invariants(built):
+    """Structure of the LA table (LAReference.cpp:28-207, 774-968): every stage covers the whole orbit."""
+    _, coords, orbit, la, n = cases.make_inputs(5, 64, 36, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 4)
+    assert la.is_valid and la.stage_count >= 2 and la.num_stages == la.stage_count
+    las = la.las_numpy()
+    steps = las[:, 60:64].copy().view(np.uint32).reshape(-1)   # LAi.StepLength  (offset 60, u32 IterType)
+    nxt = las[:, 64:68].copy().view(np.uint32).reshape(-1)     # LAi.NextStageLAIndex
+    stages = la.stages_numpy()
+    max_ref = orbit.count - 1
+    for s in range(la.stage_count):
+        idx, cnt = int(stages[s, 0]), int(stages[s, 1])
+        assert int(steps[idx:idx + cnt].sum()) == max_ref, (s, int(steps[idx:idx + cnt].sum()), max_ref)
+        assert steps[idx + cnt] == 0          # terminal record of the stage
+        if s > 0:
+            prev_cnt = int(stages[s - 1, 1])
+            assert int(nxt[idx:idx + cnt].max()) < prev_cnt   # NextStageLAIndex indexes the previous stage
+    # stage 0 NextStageLAIndex are orbit indices, strictly increasing
+    idx, cnt = int(stages[0, 0]), int(stages[0, 1])
+    assert np.all(np.diff(nxt[idx:idx + cnt].astype(np.int64)) > 0) and nxt[idx] == 0
+    # u64 table carries the same numbers in wider fields
+    _, _, orbit8, la8, _ = cases.make_inputs(5, 64, 36, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 8)
+    assert la8.num_las == la.num_las and la8.las_elem_bytes == 80
+    np.testing.assert_array_equal(la8.las_numpy()[:, :60], las[:, :60])
+
+
+def test_orbit_layout_and_first_entries(built):
+    """Entry 0 is the zero element, entry 1 is c (RefOrbitCalc.cpp:447-623, PerturbationResults.cpp:861-868)."""
+    view, coords, orbit, la, n = cases.make_inputs(1, 64, 36, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 4)
+    raw = orbit.as_numpy()
+    assert raw.shape[1] == 16
+    e0 = raw[0].view(np.int32)
+    assert raw[0].view(np.float32)[0] == 0.0 and e0[1] == -(2 ** 28) and e0[2] == -(2 ** 28)
+    x_m, x_e = raw[1].view(np.float32)[0], raw[1].view(np.int32)[1]
+    assert 0.5 <= abs(x_m) <= 1.0                      # HDRFloat(mpf_t): mpf_get_d_2exp mantissa, unreduced
+    assert abs(x_m * 2.0 ** x_e - (-1.7633991770667527)) < 1e-6
+    assert orbit.period == orbit.count                 # periodic orbit: stops at the detected period
+
+
+def test_post_oracle_small():
+    """AA + palette + reduction semantics (AntialiasingKernel.cuh:3-71, ReductionKernels.cuh:73-142)."""
+    w, h, aa = 32, 16, 2
+    iters = np.zeros((16, 32), np.uint32)
+    iters[:h, :w] = np.arange(w * h, dtype=np.uint32).reshape(h, w) % 7
+    pal = np.arange(5 * 4, dtype=np.uint16).reshape(5, 4) * 100
+    colors, red = oracle_cpu.post(iters, w, h, aa, pal, 0, 6)
+    assert red == {"Min": 0, "Max": 6, "Sum": int(iters.sum())}
+    cell = iters[0:2, 0:2].reshape(-1)
+    want = sum(int(pal[c % 5, 0]) for c in cell if c < 6) // 4
+    assert colors[0, 0, 0] == want and colors[0, 0, 3] == 65535
