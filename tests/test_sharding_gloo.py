@@ -28,9 +28,9 @@ def _worker(rank, world, port, h, w, out_q):
     mine = np.zeros_like(full)
     rows = rows_of_shard(h, world, rank)
     mine[rows] = full[rows]                                        # a rank only renders its own bands
+    total = torch.tensor([int(mine.sum())])                        # this rank's checksum
     t = torch.from_numpy(mine)
     dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)                    # disjoint rows: SUM == gather
-    total = torch.tensor([int(mine.sum())])
     dist.all_reduce(total)
     if rank == 0:
         out_q.put((np.array_equal(t.numpy(), full), int(total.item()) == int(full.sum())))
