@@ -302,21 +302,17 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     A.tile_counter = r->tile_counter;
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     begin_render(r);
+    const bool count = r->count_steps;
+#define FS_LAUNCH_LAV2(MODE)                                                                                           \
+    if (count) { auto k = lav2_kernel<Num, IterT, MODE, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }     \
+    else { auto k = lav2_kernel<Num, IterT, MODE, false>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
     switch (mode) {
-    case FS_LAV2_FULL: {
-        auto k = lav2_kernel<Num, IterT, Lav2Mode::Full>;
-        k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A);
-    } break;
-    case FS_LAV2_PO: {
-        auto k = lav2_kernel<Num, IterT, Lav2Mode::PO>;
-        k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A);
-    } break;
-    case FS_LAV2_LAO: {
-        auto k = lav2_kernel<Num, IterT, Lav2Mode::LAO>;
-        k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A);
-    } break;
+    case FS_LAV2_FULL: FS_LAUNCH_LAV2(Lav2Mode::Full) break;
+    case FS_LAV2_PO: FS_LAUNCH_LAV2(Lav2Mode::PO) break;
+    case FS_LAV2_LAO: FS_LAUNCH_LAV2(Lav2Mode::LAO) break;
     default: return FS_ERROR_UNSUPPORTED;
     }
+#undef FS_LAUNCH_LAV2
     return end_render(r);
 }
 

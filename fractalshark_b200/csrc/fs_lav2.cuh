@@ -11,6 +11,7 @@
 // 16x8 CTA per screen block with 32-bit field loads and scalbnf-based alignment.
 #pragma once
 #include "fs_num.cuh"
+#include "fs_perturb_loop.cuh"
 
 namespace fs {
 
@@ -99,7 +100,7 @@ template <> struct OrbitIO<NumHdr<double>> {
 // ---- small vocabulary shims so the kernel reads the same for plain and HDR numbers ------------
 template <class Num> FS_D bool c_is_ge(typename Num::Real a, typename Num::Real b) { return ge_pr(a, b); }
 
-template <class Num, class IterT, Lav2Mode Mode>
+template <class Num, class IterT, Lav2Mode Mode, bool Count>
 __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A) {
     using Real = typename Num::Real;
     using Cplx = typename Num::Cplx;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
                     if constexpr (Num::kHdr) z2.e = imax(z.e + z.e, MIN_BIG);
                     z = add(z2, c);
                 }
-                steps += i;
+                if (Count) steps += i;
                 dz = mul(z, A.at.InvZCoeff);
                 reduce(dz);
                 iter = i * A.at.StepLength;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
                         break;
                     }
                     iter += l;
-                    steps++;
+                    if (Count) steps++;
                     // Evaluate  GPU_LAInfoDeep.h:120-123 ; getZ  LAstep.h:181-185
                     dz = add(mul(newdz, rec->ZCoeff), mul(dc, rec->CCoeff));
                     const Cplx z = add(rec[1].Ref, dz);
@@ -205,36 +206,14 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
         if constexpr (Mode == Lav2Mode::Full || Mode == Lav2Mode::PO) {
             // ---- plain perturbation with rebasing (LAKernel.cuh:130-236) ----
             Real dX = Num::c_re(dz), dY = Num::c_im(dz);
-            Real zx, zy;
-            OrbitIO<Num>::load(A.orbit, RefIteration, zx, zy);
-            const IterT last = A.orbit_count - 1;
-            for (;;) {
-                Num::perturb(dX, dY, zx, zy, dcX, dcY);
-                ++RefIteration;
-                OrbitIO<Num>::load(A.orbit, RefIteration, zx, zy);
-                const Real tX = add(zx, dX);
-                const Real tY = add(zy, dY);
-                const Real n2 = Num::norm2(tX, tY);
-                steps++;
-                if (lt_bailout(n2) && iter < A.n_iterations) {
-                    const Real d2 = Num::norm2(dX, dY);
-                    if (lt_pr(n2, d2) || RefIteration >= last) {
-                        dX = tX;
-                        dY = tY;
-                        RefIteration = 0;
-                        OrbitIO<Num>::load(A.orbit, 0, zx, zy);
-                    }
-                    ++iter;
-                } else {
-                    break;
-                }
-            }
+            PerturbLoop<Num, IterT, Count>::run(A.orbit, A.orbit_count, A.n_iterations, dcX, dcY, dX, dY, RefIteration,
+                                                iter, steps);
         }
 
         A.out[(size_t)Y * A.pitch + X] = iter;
     }
 
-    if (A.step_counter) {
+    if (Count && A.step_counter) {
         // one atomic per warp
         for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
         if (lane == 0 && steps) atomicAdd(A.step_counter, steps);
