@@ -81,11 +81,11 @@ def build_inputs(width, height):
 
 
 def cpu_port_sample(coords, orbit, la, n_iter, threads):
-    """Oracle CPU port (the checker, timed as a baseline only) on every 16th row x every 16th column."""
+    """Oracle CPU port (the checker, timed as a baseline only) on a regular sub-grid of the frame."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_cpu
     from fractalshark_b200 import RenderAlgorithm
-    row_step = col_step = 16
+    row_step = col_step = 6  # ~20 s of CPU work on 16 host threads
     t0 = time.time()
     iters, steps = oracle_cpu.render_lav2(RenderAlgorithm.GpuHDRx32PerturbedLAv2, WIDTH, HEIGHT, coords, orbit, la,
                                           n_iter, rows=(0, HEIGHT), col_step=col_step, row_step=row_step,
@@ -197,15 +197,17 @@ def main():
     stop, samples = threading.Event(), []
     sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
     sampler.start()
-    r.EnableStepCounter(True)
     barrier()
     t_wall0 = time.time()
     kernel_ms = [step_resident() for _ in range(args.steps)]
     barrier()
     wall_s = time.time() - t_wall0
-    exec_steps = r.ReadStepCounter() / args.steps
-    r.EnableStepCounter(False)
     launches_timed = r.KernelLaunchCount() - launches0 - args.warmup
+    # executed-step count for the roofline: one extra, untimed launch of the counting variant of the kernel
+    r.EnableStepCounter(True)
+    step_resident()
+    exec_steps = float(r.ReadStepCounter())
+    r.EnableStepCounter(False)
     stop.set()
     sampler.join()
 

@@ -6,14 +6,17 @@
 // 22 %.  The fast step below computes the SAME roundings with a different instruction mix:
 //   * alignment of (a.m, a.e) + (b.m, b.e) without selects: both operands are scaled, one of the two
 //     multipliers is exactly 1:  m = fma(b.m, 2^min(-d,0), a.m * 2^min(d,0)),  d = a.e - b.e.
-//     Each multiplier's exponent field clamp(127 -/+ d, 0, 127) is ONE DPX instruction (VIADDMNMX.RELU),
-//     and lands on 0.0f exactly when the reference's getMultiplierNeg returns 0 (|d| >= 127).
-//   * integer adds / shifts are issued as IMAD with opaque multipliers so they run on the FMA pipe;
-//   * Reduce() is one PRMT + one 3-input add + one LOP3;
+//     Each multiplier's exponent field is clamp(127 -/+ d, 0, 127) (one 3-input add + one min/relu), and
+//     lands on 0.0f exactly when the reference's getMultiplierNeg returns 0 (|d| >= 127);
+//   * Reduce() is one byte-permute + one 3-input add + one LOP3;
+//   * |d'|^2 is evaluated only when its exponent bound does not already decide the rebase test;
 //   * the reference's zero-mantissa special cases (add/sub reset the exponent, Reduce is a no-op) are not
 //     evaluated per operation: one product of the step's mantissas is tested, and a step that touched an exact
-//     zero is recomputed by the generic, reference-shaped code.  Results are bit-identical by construction in
-//     both branches; tests/test_gpu_parity.py checks that against the reference kernels.
+//     zero is recomputed by the generic, reference-shaped code;
+//   * the loop is unrolled by two with the state ping-ponging between two register sets, so a step writes its
+//     results straight into the next step's inputs (no register copies at the loop edge).
+// Results are bit-identical to the generic loop by construction; tests/test_gpu_parity.py checks them against
+// the reference kernels at full size.
 #pragma once
 #include "fs_num.cuh"
 
@@ -54,121 +57,132 @@ template <class Num, class IterT, bool Count> struct PerturbLoop {
 };
 
 // ---- HDRx32: select-free step ------------------------------------------------------------------------------
-struct Hdr32Fast {
-    // constants the compiler must not see through (keeps IMAD on the FMA pipe instead of IADD3/SHF on the ALU pipe)
-    int M1;  // -1
-    int K23; // 1 << 23
-    int K1;  // 1
-    FS_D void init() {
-        asm volatile("mov.s32 %0, -1;" : "=r"(M1));
-        asm volatile("mov.s32 %0, 8388608;" : "=r"(K23));
-        asm volatile("mov.s32 %0, 1;" : "=r"(K1));
-    }
-    // (a.m, a.e) + (b.m, b.e): mantissa returned, exponent max(a.e, b.e) in E
-    FS_D float align(float am, int ae, float bm, int be, int &E) const {
-        const int d = be * M1 + ae;  // a.e - b.e
-        const int nd = ae * M1 + be; // b.e - a.e
-        const int fa = __viaddmin_s32_relu(d, 127, 127);  // clamp(127 + d, 0, 127): field of 2^min(d,0)
-        const int fb = __viaddmin_s32_relu(nd, 127, 127); // clamp(127 - d, 0, 127): field of 2^min(-d,0)
-        const float ma = __int_as_float(fa * K23);
-        const float mb = __int_as_float(fb * K23);
-        E = max(ae, be);
-        return __fmaf_rn(bm, mb, am * ma);
-    }
-    // Reduce() of a non-zero mantissa (HDRFloat.h:432-448)
-    FS_D void reduce_nz(float &m, int &e) const {
-        const unsigned b = __float_as_uint(m);
-        const unsigned fe = __byte_perm(b + b, 0u, 0x4443); // exponent field: byte 3 of (bits << 1)
-        e = e + (int)fe - 127;
-        m = __uint_as_float((b & 0x807fffffu) | 0x3f800000u);
-    }
-    FS_D void reduce_pos(float &m, int &e) const { // mantissa known positive
-        const unsigned b = __float_as_uint(m);
-        e = e + (int)(b >> 23) - 127;
-        m = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
-    }
+namespace hdr32fast {
+
+// (a.m, a.e) + (b.m, b.e): mantissa returned, exponent max(a.e, b.e) in E
+FS_D float align(float am, int ae, float bm, int be, int &E) {
+    const int fa = __viaddmin_s32_relu(ae - be, 127, 127); // clamp(127 + d, 0, 127): field of 2^min(d,0)
+    const int fb = __viaddmin_s32_relu(be - ae, 127, 127); // clamp(127 - d, 0, 127): field of 2^min(-d,0)
+    const float ma = __int_as_float(fa << 23);
+    const float mb = __int_as_float(fb << 23);
+    E = max(ae, be);
+    return __fmaf_rn(bm, mb, am * ma);
+}
+// Reduce() of a non-zero mantissa (HDRFloat.h:432-448)
+FS_D void reduce_nz(float &m, int &e) {
+    const unsigned b = __float_as_uint(m);
+    const unsigned fe = __byte_perm(b + b, 0u, 0x4443); // exponent field: byte 3 of (bits << 1)
+    e = e + (int)fe - 127;
+    m = __uint_as_float((b & 0x807fffffu) | 0x3f800000u);
+}
+FS_D void reduce_pos(float &m, int &e) { // mantissa known positive
+    const unsigned b = __float_as_uint(m);
+    e = e + (int)(b >> 23) - 127;
+    m = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+}
+
+struct State {
+    float dxm, dym;
+    int dxe, dye;
+    uint4 z; // orbit element at RefIteration: {x.m, x.e, y.e, y.m}
 };
 
-template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Count> {
+// One perturbation step: reads `in`, writes `out` (the state the next step starts from).
+// Returns false when the pixel is finished (escaped or out of iterations).
+template <class IterT, bool Count>
+FS_D bool step(const State &in, State &out, const uint4 *__restrict__ orb, IterT last, IterT n_iterations,
+               Hdr<float> dcX, Hdr<float> dcY, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
     using Num = NumHdr<float>;
+    using Real = Hdr<float>;
+    ++RefIteration;
+    const uint4 zn = __ldg(orb + RefIteration);
+    const float dxm = in.dxm, dym = in.dym;
+    const int dxe = in.dxe, dye = in.dye;
+    const float zxm = __uint_as_float(in.z.x), zym = __uint_as_float(in.z.w);
+    const int zxe1 = (int)in.z.y + 1, zye1 = (int)in.z.z + 1; // 2*Z: exponent + 1 (the MIN_BIG clamp cannot trigger)
+    // tempSum2 = 2Zx + dx ; tempSum1 = 2Zy + dy
+    int s2e, s1e;
+    const float s2m = align(zxm, zxe1, dxm, dxe, s2e);
+    const float s1m = align(zym, zye1, dym, dye, s1e);
+    // custom_perturb2, X: dx*s2 - dy*s1 + cx
+    const float pXa = dxm * s2m, pXb = dym * s1m;
+    int eX, nxe;
+    const float sumX = align(pXa, dxe + s2e, -pXb, dye + s1e, eX);
+    float nxm = align(sumX, eX, dcX.m, dcX.e, nxe);
+    // Y: dx*s1 + dy*s2 + cy
+    const float pYa = dxm * s1m, pYb = dym * s2m;
+    int eY, nye;
+    const float sumY = align(pYa, dxe + s1e, pYb, dye + s2e, eY);
+    float nym = align(sumY, eY, dcY.m, dcY.e, nye);
+    const float nz_guard = nxm * nym; // raw (unreduced) results: a zero here needs the reference's special cases
+    reduce_nz(nxm, nxe);
+    reduce_nz(nym, nye);
+    // z = Z' + d'
+    const float wxm = __uint_as_float(zn.x), wym = __uint_as_float(zn.w);
+    int txe, tye;
+    float txm = align(wxm, (int)zn.y, nxm, nxe, txe);
+    float tym = align(wym, (int)zn.z, nym, nye, tye);
+    // |z|^2
+    const float sqx = txm * txm, sqy = tym * tym;
+    int n2e;
+    float n2m = align(sqx, txe + txe, sqy, tye + tye, n2e);
+    reduce_pos(n2m, n2e);
+    bool below = n2e <= 1; // reduced, non-zero: "< 256" can never fail at exponent 1 (HDRFloat.h:1169-1184)
+    // |d'|^2 only matters for the rebase test |z|^2 < |d'|^2.  d'x, d'y are reduced (mantissas in [1,2)), so
+    // |d'|^2 < 2^(2*max(e)+3) and its reduced exponent is <= 2*max(e)+2: when |z|^2 has a larger exponent the
+    // comparison is decided without evaluating |d'|^2 (the usual case, |z| >> |d'|).
+    bool rebase = false;
+    if (n2e <= 2 * max(nxe, nye) + 2) {
+        const float sdx = nxm * nxm, sdy = nym * nym;
+        int d2e;
+        float d2m = align(sdx, nxe + nxe, sdy, nye + nye, d2e);
+        reduce_pos(d2m, d2e);
+        rebase = n2e < d2e || (n2e == d2e && n2m < d2m);
+    }
+    // one test for every exact-zero special case of the reference (see file header)
+    const float guard = ((pXa * pXb) * (sqx * sqy)) * nz_guard;
+    if (guard == 0.0f) {
+        Real dX{dxm, dxe}, dY{dym, dye};
+        const Real zx{zxm, (int)in.z.y}, zy{zym, (int)in.z.z};
+        Num::perturb(dX, dY, zx, zy, dcX, dcY);
+        const Real tX = add(Real{wxm, (int)zn.y}, dX), tY = add(Real{wym, (int)zn.z}, dY);
+        const Real n2 = Num::norm2(tX, tY), d2 = Num::norm2(dX, dY);
+        nxm = dX.m; nxe = dX.e; nym = dY.m; nye = dY.e;
+        txm = tX.m; txe = tX.e; tym = tY.m; tye = tY.e;
+        below = lt_bailout(n2);
+        rebase = lt_pr(n2, d2);
+    }
+    if (Count) steps++;
+    if (!(below && iter < n_iterations)) return false;
+    ++iter;
+    if (rebase || RefIteration >= last) {
+        out.dxm = txm; out.dxe = txe; out.dym = tym; out.dye = tye;
+        RefIteration = 0;
+        out.z = __ldg(orb);
+    } else {
+        out.dxm = nxm; out.dxe = nxe; out.dym = nym; out.dye = nye;
+        out.z = zn;
+    }
+    return true;
+}
+
+} // namespace hdr32fast
+
+template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Count> {
     using Real = Hdr<float>;
     FS_D static void run(const void *orbit, IterT orbit_count, IterT n_iterations, Real dcX, Real dcY, Real &dXio,
                          Real &dYio, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
-        Hdr32Fast F;
-        F.init();
+        using namespace hdr32fast;
         const uint4 *__restrict__ orb = reinterpret_cast<const uint4 *>(orbit);
         const IterT last = orbit_count - 1;
-        float dxm = dXio.m, dym = dYio.m;
-        int dxe = dXio.e, dye = dYio.e;
-        const float cxm = dcX.m, cym = dcY.m;
-        const int cxe = dcX.e, cye = dcY.e;
-        uint4 z = __ldg(orb + RefIteration); // {x.m, x.e, y.e, y.m}
+        State a, b;
+        a.dxm = dXio.m; a.dxe = dXio.e; a.dym = dYio.m; a.dye = dYio.e;
+        a.z = __ldg(orb + RefIteration);
         for (;;) {
-            ++RefIteration;
-            const uint4 zn = __ldg(orb + RefIteration);
-            const float zxm = __uint_as_float(z.x), zym = __uint_as_float(z.w);
-            const int zxe1 = (int)z.y + 1, zye1 = (int)z.z + 1; // 2*Z: exponent + 1 (the clamp at MIN_BIG cannot trigger)
-            // tempSum2 = 2Zx + dx ; tempSum1 = 2Zy + dy
-            int s2e, s1e;
-            const float s2m = F.align(zxm, zxe1, dxm, dxe, s2e);
-            const float s1m = F.align(zym, zye1, dym, dye, s1e);
-            // custom_perturb2, X: dx*s2 - dy*s1 + cx
-            const float pXa = dxm * s2m, pXb = dym * s1m;
-            int eX, nxe;
-            const float sumX = F.align(pXa, dxe + s2e, -pXb, dye + s1e, eX);
-            float nxm = F.align(sumX, eX, cxm, cxe, nxe);
-            // Y: dx*s1 + dy*s2 + cy
-            const float pYa = dxm * s1m, pYb = dym * s2m;
-            int eY, nye;
-            const float sumY = F.align(pYa, dxe + s1e, pYb, dye + s2e, eY);
-            float nym = F.align(sumY, eY, cym, cye, nye);
-            const float nz_guard = nxm * nym; // raw (unreduced) results: zero here needs the reference's special cases
-            F.reduce_nz(nxm, nxe);
-            F.reduce_nz(nym, nye);
-            // z = Z' + d'
-            const float wxm = __uint_as_float(zn.x), wym = __uint_as_float(zn.w);
-            int txe, tye;
-            float txm = F.align(wxm, (int)zn.y, nxm, nxe, txe);
-            float tym = F.align(wym, (int)zn.z, nym, nye, tye);
-            // |z|^2 and |d'|^2
-            const float sqx = txm * txm, sqy = tym * tym, sdx = nxm * nxm, sdy = nym * nym;
-            int n2e, d2e;
-            float n2m = F.align(sqx, txe + txe, sqy, tye + tye, n2e);
-            float d2m = F.align(sdx, nxe + nxe, sdy, nye + nye, d2e);
-            F.reduce_pos(n2m, n2e);
-            F.reduce_pos(d2m, d2e);
-            bool below = n2e <= 1; // reduced, non-zero: "< 256" can never fail at exponent 1 (HDRFloat.h:1169-1184)
-            bool rebase_cmp = n2e < d2e || (n2e == d2e && n2m < d2m);
-
-            // one test for every exact-zero special case of the reference (see file header)
-            const float guard = ((pXa * pXb) * (sqx * sqy)) * nz_guard;
-            if (guard == 0.0f) {
-                Real dX{dxm, dxe}, dY{dym, dye};
-                const Real zx{zxm, (int)z.y}, zy{zym, (int)z.z};
-                Num::perturb(dX, dY, zx, zy, dcX, dcY);
-                const Real tX = add(Real{wxm, (int)zn.y}, dX), tY = add(Real{wym, (int)zn.z}, dY);
-                const Real n2 = Num::norm2(tX, tY), d2 = Num::norm2(dX, dY);
-                nxm = dX.m; nxe = dX.e; nym = dY.m; nye = dY.e;
-                txm = tX.m; txe = tX.e; tym = tY.m; tye = tY.e;
-                below = lt_bailout(n2);
-                rebase_cmp = lt_pr(n2, d2);
-            }
-            if (Count) steps++;
-            if (!(below && iter < n_iterations)) {
-                dxm = nxm; dxe = nxe; dym = nym; dye = nye;
-                break;
-            }
-            ++iter;
-            if (rebase_cmp || RefIteration >= last) {
-                dxm = txm; dxe = txe; dym = tym; dye = tye;
-                RefIteration = 0;
-                z = __ldg(orb);
-            } else {
-                dxm = nxm; dxe = nxe; dym = nym; dye = nye;
-                z = zn;
-            }
+            if (!step<IterT, Count>(a, b, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) break;
+            if (!step<IterT, Count>(b, a, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) break;
         }
-        dXio.m = dxm; dXio.e = dxe; dYio.m = dym; dYio.e = dye;
+        // the delta after the last step is not observable (only `iter` is written out)
     }
 };
 
