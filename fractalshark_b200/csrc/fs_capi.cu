@@ -54,6 +54,7 @@ struct DeviceBlob {
 
 struct OrbitDev {
     DeviceBlob data;
+    DeviceBlob fast; // HDRx32: scaled::FastElem[compressed] derived on the device after the upload
     uint64_t compressed = 0, uncompressed = 0, period = 0;
     int numeric = -1, pextras = 0;
     uint64_t generation = 0;
@@ -89,6 +90,7 @@ struct fs_renderer {
     unsigned int *tile_counter = nullptr;
     unsigned long long *step_counter = nullptr;
     bool count_steps = false;
+    bool use_scaled = true; // HDRx32: scaled plain-float chunks (fs_scaled_loop.cuh); off = pure float+exponent loop
     OrbitDev orbit1, orbit2;
     LaDev la;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -116,6 +118,8 @@ void free_blob(fs_renderer *r, DeviceBlob &b) {
 void reset_perturb(fs_renderer *r) {
     free_blob(r, r->orbit1.data);
     free_blob(r, r->orbit2.data);
+    free_blob(r, r->orbit1.fast);
+    free_blob(r, r->orbit2.fast);
     r->orbit1 = OrbitDev{};
     r->orbit2 = OrbitDev{};
     free_blob(r, r->la.las);
@@ -149,10 +153,20 @@ size_t orbit_elem_bytes(int numeric, int pextras) {
     return pextras == FS_PEXTRAS_DISABLE ? base : base + 8;
 }
 
+// Derives the plain-float step table (fs_scaled_loop.cuh) from an uploaded HDRx32 orbit.
+__global__ void __launch_bounds__(256) build_fast_table_kernel(const uint4 *__restrict__ orbit, uint64_t count,
+                                                               scaled::FastElem *__restrict__ tab) {
+    for (uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < count; n += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = orbit[n];
+        tab[n] = scaled::make_fast_elem(__uint_as_float(v.x), (int)v.y, __uint_as_float(v.w), (int)v.z, n + 1 >= count);
+    }
+}
+
 uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, uint64_t generation, const fs_orbit *src) {
     const size_t eb = orbit_elem_bytes(numeric, pextras);
     if (eb == 0) return FS_ERROR_UNSUPPORTED;
     free_blob(r, dst.data);
+    free_blob(r, dst.fast);
     dst = OrbitDev{};
     const size_t bytes = eb * src->compressed_count;
     cudaError_t err = cudaMallocAsync(&dst.data.ptr, bytes ? bytes : 16, r->compute);
@@ -160,6 +174,19 @@ uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, u
     dst.data.bytes = bytes;
     err = cudaMemcpyAsync(dst.data.ptr, src->elements, bytes, cudaMemcpyDefault, r->compute);
     if (err != cudaSuccess) return err;
+    if (numeric == FS_NUM_HDR32 && pextras == FS_PEXTRAS_DISABLE && src->compressed_count > 1 && r->use_scaled) {
+        const size_t fbytes = sizeof(scaled::FastElem) * src->compressed_count;
+        err = cudaMallocAsync(&dst.fast.ptr, fbytes, r->compute);
+        if (err != cudaSuccess) return err;
+        dst.fast.bytes = fbytes;
+        const uint64_t want = (src->compressed_count + 255) / 256;
+        const unsigned grid = (unsigned)(want < (uint64_t)r->num_sms * 8 ? want : (uint64_t)r->num_sms * 8);
+        build_fast_table_kernel<<<grid, 256, 0, r->compute>>>(static_cast<const uint4 *>(dst.data.ptr), src->compressed_count,
+                                                              static_cast<scaled::FastElem *>(dst.fast.ptr));
+        r->launches++;
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
     dst.compressed = src->compressed_count;
     dst.uncompressed = src->uncompressed_count;
     dst.period = src->period_maybe_zero;
@@ -279,6 +306,7 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     memset(&A, 0, sizeof(A));
     A.out = static_cast<IterT *>(r->iter_buf);
     A.orbit = r->orbit1.data.ptr;
+    A.orbit_fast = r->use_scaled ? r->orbit1.fast.ptr : nullptr;
     A.orbit_count = (IterT)r->orbit1.uncompressed;
     const bool have_la = r->la.present && r->la.numeric == r->orbit1.numeric && r->la.iter_bytes == sizeof(IterT);
     if (have_la) {
@@ -690,6 +718,12 @@ uint32_t fs_measure_fp32_issue_peak(int32_t device, double *ffma_per_second) {
     cudaFree(sink);
     *ffma_per_second = best;
     return err;
+}
+
+uint32_t fs_set_scaled_steps(fs_renderer *r, int32_t enable) {
+    if (!r) return FS_ERROR_UNSUPPORTED;
+    r->use_scaled = enable != 0;
+    return 0;
 }
 
 void *fs_device_iter_buffer(fs_renderer *r) { return r ? r->iter_buf : nullptr; }

@@ -45,6 +45,7 @@ template <class Num, class IterT> struct AtDev {
 template <class Num, class IterT> struct Lav2Args {
     IterT *out;              // iteration buffer, row pitch = roundup16(width)
     const void *orbit;       // reference-layout orbit elements (GPU_ReferenceIter.h:119-125)
+    const void *orbit_fast;  // HDRx32 only: per-element table of fs_scaled_loop.cuh (nullptr = not built)
     IterT orbit_count;       // uncompressed entries
     const LaRec<Num, IterT> *las;
     const StageRec<IterT> *stages;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
         if constexpr (Mode == Lav2Mode::Full || Mode == Lav2Mode::PO) {
             // ---- plain perturbation with rebasing (LAKernel.cuh:130-236) ----
             Real dX = Num::c_re(dz), dY = Num::c_im(dz);
-            PerturbLoop<Num, IterT, Count>::run(A.orbit, A.orbit_count, A.n_iterations, dcX, dcY, dX, dY, RefIteration,
+            PerturbLoop<Num, IterT, Count>::run(A.orbit, A.orbit_fast, A.orbit_count, A.n_iterations, dcX, dcY, dX, dY, RefIteration,
                                                 iter, steps);
         }
 

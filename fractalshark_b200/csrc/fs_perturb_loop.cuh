@@ -19,6 +19,7 @@
 // the reference kernels at full size.
 #pragma once
 #include "fs_num.cuh"
+#include "fs_scaled_loop.cuh"
 
 namespace fs {
 
@@ -27,8 +28,8 @@ template <class Num> struct OrbitIO; // fs_lav2.cuh
 // ---- generic loop (any numeric policy) --------------------------------------------------------------------
 template <class Num, class IterT, bool Count> struct PerturbLoop {
     using Real = typename Num::Real;
-    FS_D static void run(const void *orbit, IterT orbit_count, IterT n_iterations, Real dcX, Real dcY, Real &dX,
-                         Real &dY, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
+    FS_D static void run(const void *orbit, const void * /*orbit_fast*/, IterT orbit_count, IterT n_iterations, Real dcX,
+                         Real dcY, Real &dX, Real &dY, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
         Real zx, zy;
         OrbitIO<Num>::load(orbit, RefIteration, zx, zy);
         const IterT last = orbit_count - 1;
@@ -170,17 +171,40 @@ FS_D bool step(const State &in, State &out, const uint4 *__restrict__ orb, IterT
 
 template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Count> {
     using Real = Hdr<float>;
-    FS_D static void run(const void *orbit, IterT orbit_count, IterT n_iterations, Real dcX, Real dcY, Real &dXio,
-                         Real &dYio, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
+    // orbit_fast: the per-element table of fs_scaled_loop.cuh (built on upload); nullptr selects the pure
+    // float+exponent loop.
+    FS_D static void run(const void *orbit, const void *orbit_fast, IterT orbit_count, IterT n_iterations, Real dcX,
+                         Real dcY, Real &dXio, Real &dYio, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
         using namespace hdr32fast;
         const uint4 *__restrict__ orb = reinterpret_cast<const uint4 *>(orbit);
         const IterT last = orbit_count - 1;
         State a, b;
         a.dxm = dXio.m; a.dxe = dXio.e; a.dym = dYio.m; a.dye = dYio.e;
-        a.z = __ldg(orb + RefIteration);
+        if (orbit_fast == nullptr) {
+            a.z = __ldg(orb + RefIteration);
+            for (;;) {
+                if (!step<IterT, Count>(a, b, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) break;
+                if (!step<IterT, Count>(b, a, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) break;
+            }
+            return;
+        }
+        const scaled::FastElem *__restrict__ tab = reinterpret_cast<const scaled::FastElem *>(orbit_fast);
         for (;;) {
+            // scaled plain-float chunks for as long as they commit ...
+            scaled::Scale sc;
+            float wx, wy;
+            scaled::FastElem E0;
+            if (scaled::enter<IterT>(tab, dcX, dcY, a.dxm, a.dxe, a.dym, a.dye, RefIteration, iter, n_iterations, sc, wx, wy,
+                                     E0)) {
+                const scaled::Outcome oc = scaled::run<IterT, Count>(tab, last, n_iterations, sc, wx, wy, E0, a.dxm, a.dxe,
+                                                                     a.dym, a.dye, RefIteration, iter, steps);
+                if (oc == scaled::kFinished) break;
+                if (oc == scaled::kContinue) continue;
+            }
+            // ... and one float+exponent step whenever the scaled form refuses the state or rejects a chunk
+            a.z = __ldg(orb + RefIteration);
             if (!step<IterT, Count>(a, b, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) break;
-            if (!step<IterT, Count>(b, a, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) break;
+            a = b;
         }
         // the delta after the last step is not observable (only `iter` is written out)
     }

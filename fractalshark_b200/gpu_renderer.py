@@ -169,6 +169,10 @@ class GPURenderer:
             raise RuntimeError(self.ConvertErrorToString(rc))
         return int(v.value)
 
+    def SetScaledSteps(self, enable: bool = True) -> int:
+        """A/B switch of the HDRx32 perturbation loop (same results either way); applies to the next upload."""
+        return int(self._lib.fs_set_scaled_steps(self._h, int(enable)))
+
     def DeviceIterBuffer(self) -> int:
         return int(self._lib.fs_device_iter_buffer(self._h) or 0)
 

@@ -160,6 +160,10 @@ uint32_t fs_last_render_ms(fs_renderer *r, float *ms);
 /* Count executed steps (perturbation + LA + AT) of subsequent renders into a device counter. */
 uint32_t fs_enable_step_counter(fs_renderer *r, int32_t enable);
 uint32_t fs_read_step_counter(fs_renderer *r, uint64_t *steps);
+/* HDRx32 perturbation: 1 (default) = scaled plain-float chunks with float+exponent fallback
+ * (fs_scaled_loop.cuh), 0 = pure float+exponent loop.  Results are identical; takes effect at the next
+ * InitializePerturb upload.  A/B switch for tests and profiling. */
+uint32_t fs_set_scaled_steps(fs_renderer *r, int32_t enable);
 /* Device pointer of the iteration buffer (for NCCL gather by the host plumbing). */
 void *fs_device_iter_buffer(fs_renderer *r);
 /* Number of kernels this renderer has launched so far. */

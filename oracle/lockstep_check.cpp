@@ -1,0 +1,119 @@
+// lockstep_check.cpp -- TEST INFRASTRUCTURE ONLY (built into oracle/liblockstep.so, loaded by tests/).
+//
+// Runs the product's scaled plain-float perturbation chunks (fractalshark_b200/csrc/fs_scaled_loop.cuh, the
+// FS_HD arithmetic the CUDA kernel executes) on the CPU, in lockstep with the oracle's float+exponent
+// restatement of LAKernel.cuh:130-236 (oracle_cpu.cpp: perturb_step).  After every committed chunk the two
+// states are compared BY VALUE (reduced mantissa + exponent of both delta components, orbit index, iteration
+// count); rejected chunks and everything the scaled form refuses go through the oracle step, exactly like the
+// kernel falls back to its float+exponent step.  x86 binary32 with -ffp-contract=off and explicit fmaf is the
+// same IEEE arithmetic the GPU executes (no FTZ on either side), so a clean run here is evidence for the
+// bit-exactness argument in the header of fs_scaled_loop.cuh on every step it touched.
+#include "oracle_cpu.cpp"
+
+#include <mutex>
+
+#include "../fractalshark_b200/csrc/fs_scaled_loop.cuh"
+
+namespace {
+
+struct LockStats {
+    uint64_t fast_steps = 0, slow_steps = 0, chunks_ok = 0, chunks_rejected = 0, entries_refused = 0, mismatches = 0,
+             finished_fast = 0;
+};
+
+template <class IterT>
+IterT lockstep_pixel(const Lav2Job<IterT> &J, const fs::scaled::FastElem *tab, int X, int Y, LockStats &st) {
+    using namespace fs::scaled;
+    uint64_t steps = 0;
+    PerturbState<IterT> S;
+    lav2_prologue(J, X, Y, steps, S);
+    if (!(J.mode == 1 || J.mode == 2)) return S.iter;
+    const IterT last = J.orbit_count - 1;
+    for (;;) {
+        Scale sc;
+        float wx, wy;
+        FastElem E0;
+        const fs::Hdr<float> cX{S.cX.mantissa, S.cX.exp}, cY{S.cY.mantissa, S.cY.exp};
+        if (enter<IterT>(tab, cX, cY, S.dX.mantissa, S.dX.exp, S.dY.mantissa, S.dY.exp, S.RefIteration, S.iter,
+                         J.n_iterations, sc, wx, wy, E0)) {
+            PerturbState<IterT> F = S; // scaled path works on F, the oracle shadow on S
+            unsigned long long fsteps = 0;
+            const Outcome oc = run<IterT, true>(tab, last, J.n_iterations, sc, wx, wy, E0, F.dX.mantissa, F.dX.exp,
+                                                F.dY.mantissa, F.dY.exp, F.RefIteration, F.iter, fsteps);
+            st.fast_steps += fsteps;
+            // advance the shadow by the committed steps
+            bool alive = true;
+            for (unsigned long long i = 0; i < fsteps && alive; i++) alive = perturb_step(J, S);
+            if (oc == kFinished) {
+                st.finished_fast++;
+                if (alive || S.iter != F.iter) st.mismatches++;
+                return F.iter;
+            }
+            if (!alive) { st.mismatches++; return S.iter; }
+            st.chunks_ok += fsteps / kChunk;
+            if (fsteps) {
+                HF ax = S.dX, ay = S.dY, bx = F.dX, by = F.dY;
+                Reduce(ax); Reduce(ay); Reduce(bx); Reduce(by);
+                if (!(ax.mantissa == bx.mantissa && ax.exp == bx.exp && ay.mantissa == by.mantissa && ay.exp == by.exp &&
+                      S.RefIteration == F.RefIteration && S.iter == F.iter))
+                    st.mismatches++;
+                // continue from the scaled path's representation (what the kernel does)
+                S.dX = F.dX; S.dY = F.dY;
+            }
+            if (oc == kContinue) continue;
+            st.chunks_rejected++;
+        } else {
+            st.entries_refused++;
+        }
+        st.slow_steps++;
+        if (!perturb_step(J, S)) return S.iter;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+// Returns the number of lockstep mismatches (0 = every committed chunk matched the oracle by value).
+// stats[7]: fast steps, slow steps, chunks committed, chunks rejected, entries refused, mismatches, pixels finished in a chunk
+uint64_t lockstep_render_lav2(int mode, const void *orbit, uint64_t count, const void *las, const void *stages,
+                              const void *at, uint64_t stage_count, int use_at, int is_valid, int w, int h,
+                              const void *dx, const void *dy, const void *cenx, const void *ceny, uint64_t n_iter,
+                              void *out, int col_step, int row_step, int threads, uint64_t *stats) {
+    using IterT = uint32_t;
+    Lav2Job<IterT> J;
+    J.mode = mode;
+    J.orbit = (const OrbitElemF *)orbit;
+    J.orbit_count = (IterT)count;
+    J.las = (const LAInfoDeepF<IterT> *)las;
+    J.stages = (const LAStageInfo<IterT> *)stages;
+    J.at = (const ATInfoF<IterT> *)at;
+    J.la_stage_count = (IterT)stage_count;
+    J.use_at = use_at && at;
+    J.is_valid = is_valid && las;
+    J.width = w; J.height = h; J.pitch = (w + 15) / 16 * 16;
+    memcpy(&J.dx, dx, 8); memcpy(&J.dy, dy, 8); memcpy(&J.centerX, cenx, 8); memcpy(&J.centerY, ceny, 8);
+    J.n_iterations = (IterT)n_iter;
+    J.out = (IterT *)out;
+    std::vector<fs::scaled::FastElem> tab(count);
+    for (uint64_t n = 0; n < count; n++)
+        tab[n] = fs::scaled::make_fast_elem(J.orbit[n].xm, J.orbit[n].xe, J.orbit[n].ym, J.orbit[n].ye, n + 1 >= count);
+    std::mutex mu;
+    LockStats total;
+    if (col_step < 1) col_step = 1;
+    parallel_rows(0, h, threads, [&](int y) {
+        LockStats st;
+        for (int x = 0; x < w; x += col_step) J.out[(size_t)y * J.pitch + x] = lockstep_pixel(J, tab.data(), x, y, st);
+        std::lock_guard<std::mutex> g(mu);
+        total.fast_steps += st.fast_steps; total.slow_steps += st.slow_steps; total.chunks_ok += st.chunks_ok;
+        total.chunks_rejected += st.chunks_rejected; total.entries_refused += st.entries_refused;
+        total.mismatches += st.mismatches; total.finished_fast += st.finished_fast;
+    }, row_step);
+    if (stats) {
+        stats[0] = total.fast_steps; stats[1] = total.slow_steps; stats[2] = total.chunks_ok; stats[3] = total.chunks_rejected;
+        stats[4] = total.entries_refused; stats[5] = total.mismatches; stats[6] = total.finished_fast;
+    }
+    return total.mismatches;
+}
+
+} // extern "C"

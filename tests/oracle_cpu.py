@@ -81,3 +81,31 @@ def post(iters, w, h, aa, palette, aux_depth, n_iter):
     lib().orc_post(iter_bytes, iters.ctypes.data, w, h, aa, palette.ctypes.data, palette.shape[0], aux_depth, n_iter,
                    colors.ctypes.data, red.ctypes.data)
     return colors, {"Min": int(red[0]), "Max": int(red[1]), "Sum": int(red[2])}
+
+
+LOCKSTEP_LIB = os.path.join(ROOT, "oracle", "liblockstep.so")
+_lock = None
+
+
+def lockstep_lav2(alg, w, h, coords, orbit, la, n_iter, col_step=1, row_step=1, threads=1):
+    """Runs the product's scaled plain-float chunks (fs_scaled_loop.cuh, host build) in lockstep with the
+    float+exponent oracle.  Returns (iters, stats dict); stats["mismatches"] must be 0."""
+    global _lock
+    if _lock is None:
+        L = C.CDLL(LOCKSTEP_LIB)
+        V, I, U64 = C.c_void_p, C.c_int, C.c_uint64
+        L.lockstep_render_lav2.restype = U64
+        L.lockstep_render_lav2.argtypes = [I, V, U64, V, V, V, U64, I, I, I, I, V, V, V, V, U64, V, I, I, I, V]
+        _lock = L
+    t = traits(alg)
+    hp, wp = _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)
+    out = np.zeros((hp, wp), dtype=np.uint32)
+    d, l = orbit.descriptor(), la.descriptor()
+    stats = (C.c_uint64 * 8)()
+    _lock.lockstep_render_lav2(int(t.mode), d.elements, d.uncompressed_count, l.las, l.stages, l.at, l.la_stage_count,
+                               l.use_at, l.is_valid, w, h, _buf(coords["dx"]), _buf(coords["dy"]),
+                               _buf(coords["center_x"]), _buf(coords["center_y"]), n_iter, out.ctypes.data, col_step,
+                               row_step, threads, stats)
+    keys = ("fast_steps", "slow_steps", "chunks_committed", "chunks_rejected", "entries_refused", "mismatches",
+            "finished_in_chunk")
+    return out, dict(zip(keys, [int(x) for x in stats]))

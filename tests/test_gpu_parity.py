@@ -128,6 +128,34 @@ def test_antialiasing_palette_reduction(aa):
         np.testing.assert_array_equal(rcol.reshape(-1, 4)[: (h // aa) * (w // aa)], colors.reshape(-1, 4)[: (h // aa) * (w // aa)])
 
 
+@pytest.mark.parametrize("view_id,w,h,alg,n_iter", [
+    (5, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None),
+    (5, 960, 540, A.GpuHDRx32PerturbedLAv2PO, 20000),
+    (1, 1920, 1080, A.GpuHDRx32PerturbedLAv2PO, None),
+    (19, 960, 540, A.GpuHDRx32PerturbedLAv2, 3000000),
+])
+def test_scaled_chunks_equal_float_exponent_loop(view_id, w, h, alg, n_iter):
+    """A/B inside the library: the scaled plain-float chunks (default) and the pure float+exponent loop give
+    the same iteration buffer, and the scaled form executes the same number of algorithmic steps."""
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, 4)
+    outs, steps = [], []
+    for scaled in (True, False):
+        r = GPURenderer()
+        assert r.InitializeMemory(w, h, 1, iter_bytes=4) == 0
+        assert r.SetScaledSteps(scaled) == 0
+        assert r.InitializePerturb(1, orbit, 0, None, la) == 0
+        assert r.EnableStepCounter(True) == 0
+        r.ClearMemory()
+        assert r.RenderPerturbLAv2(alg, coords, n) == 0
+        rc, it, _, _ = r.RenderCurrent(n)
+        assert rc == 0
+        outs.append(it.copy())
+        steps.append(r.ReadStepCounter())
+        r.close()
+    np.testing.assert_array_equal(outs[0], outs[1])
+    assert steps[0] == steps[1]
+
+
 def test_error_behaviour_matches_reference():
     """Error codes and no-op-before-init behaviour (GPU_Render.cu:322-332, 626-628, 1007-1022)."""
     r = GPURenderer()

@@ -132,3 +132,29 @@ def test_post_oracle_small():
     cell = iters[0:2, 0:2].reshape(-1)
     want = sum(int(pal[c % 5, 0]) for c in cell if c < 6) // 4
     assert colors[0, 0, 0] == want and colors[0, 0, 3] == 65535
+
+
+LOCKSTEP_CASES = [
+    # (view, algorithm, n_iter (None = preset), pixel stride at 3840x2160)
+    (5, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 48),
+    (5, RenderAlgorithm.GpuHDRx32PerturbedLAv2PO, 20000, 96),
+    (1, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 24),
+    (1, RenderAlgorithm.GpuHDRx32PerturbedLAv2PO, None, 24),
+    (19, RenderAlgorithm.GpuHDRx32PerturbedLAv2, 2000000, 48),
+]
+
+
+@pytest.mark.parametrize("case", LOCKSTEP_CASES, ids=[f"v{c[0]}_{c[1].name}" for c in LOCKSTEP_CASES])
+def test_scaled_plain_float_chunks_match_float_exponent_steps_in_lockstep(built, case):
+    """fs_scaled_loop.cuh (host build of the arithmetic the kernel runs) against the float+exponent restatement:
+    identical by value after every committed chunk, identical iteration counts, and the fast form does the bulk."""
+    view_id, alg, n_iter, stride = case
+    w, h = 3840, 2160
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, 4)
+    want, _ = oracle_cpu.render_lav2(alg, w, h, coords, orbit, la, n, row_step=stride, col_step=stride,
+                                     threads=oracle_cpu.hardware_threads())
+    got, st = oracle_cpu.lockstep_lav2(alg, w, h, coords, orbit, la, n, col_step=stride, row_step=stride,
+                                       threads=oracle_cpu.hardware_threads())
+    assert st["mismatches"] == 0, st
+    np.testing.assert_array_equal(got, want)
+    assert st["fast_steps"] > 4 * st["slow_steps"], st
