@@ -101,11 +101,89 @@ template <> struct OrbitIO<NumHdr<double>> {
 // ---- small vocabulary shims so the kernel reads the same for plain and HDR numbers ------------
 template <class Num> FS_D bool c_is_ge(typename Num::Real a, typename Num::Real b) { return ge_pr(a, b); }
 
+// ---- AT shortcut + LA stages of one pixel (LAKernel.cuh:66-127) ---------------------------------------------------
+template <class Num, class IterT, bool Count>
+FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, typename Num::Cplx &dz,
+                         IterT &RefIteration, IterT &iter, unsigned long long &steps) {
+    using Real = typename Num::Real;
+    using Cplx = typename Num::Cplx;
+    using LA = LaRec<Num, IterT>;
+    // ---- AT (ATInfo.h:128-188) ----
+    if (A.la_valid && A.use_at && le_pr(cheb(dc), A.at.ThresholdC)) {
+        const IterT at_max = A.n_iterations / A.at.StepLength;
+        Cplx c = add(mul(dc, A.at.CCoeff), A.at.RefC);
+        reduce(c);
+        Cplx z = Num::c_zero();
+        IterT i = 0;
+        for (; i < at_max; i++) {
+            // nvcc shares re*re / im*im between norm_squared and z*z in the reference build:
+            //   nsq = rr + ii ; z2.re = rr - ii ; z2.im = fma(re, im, re*im)
+            const auto rr = z.re * z.re;
+            const auto ii = z.im * z.im;
+            Real nsq;
+            if constexpr (Num::kHdr) { nsq.m = rr + ii; nsq.e = z.e << 1; reduce(nsq); }
+            else { nsq = rr + ii; }
+            if (gt_pr(nsq, A.at.SqrEscapeRadius)) break;
+            Cplx z2;
+            z2.re = rr - ii;
+            z2.im = fma_(z.re, z.im, z.re * z.im);
+            if constexpr (Num::kHdr) z2.e = imax(z.e + z.e, MIN_BIG);
+            z = add(z2, c);
+        }
+        if (Count) steps += i;
+        dz = mul(z, A.at.InvZCoeff);
+        reduce(dz);
+        iter = i * A.at.StepLength;
+    }
+
+    // ---- LA stages (LAKernel.cuh:91-127) ----
+    IterT stage = A.la_valid ? A.la_stage_count : 0;
+    while (stage > 0) {
+        stage--;
+        const IterT LAIndex = A.stages[stage].LAIndex;
+        // isLAStageInvalid  GPU_LAReference.h:241-255
+        if (ge_pr(cheb(dc), A.las[LAIndex].LAThresholdC)) continue;
+        const IterT MacroItCount = A.stages[stage].MacroItCount;
+        IterT j = RefIteration;
+
+        while (iter < A.n_iterations) {
+            // getLA  GPU_LAReference.h:271-303
+            const LA *rec = A.las + (LAIndex + j);
+            const IterT l = rec->StepLength;
+            bool unusable = true;
+            Cplx newdz;
+            if (iter + l <= A.n_iterations) {
+                // Prepare  GPU_LAInfoDeep.h:90-105: newdz = dz * (2*Ref + dz), reduced
+                newdz = mul(dz, add(Num::c_mul2(rec->Ref), dz));
+                reduce(newdz);
+                unusable = ge_pr(cheb(newdz), rec->LAThreshold);
+            }
+            if (unusable) {
+                RefIteration = rec->NextStageLAIndex;
+                break;
+            }
+            iter += l;
+            if (Count) steps++;
+            // Evaluate  GPU_LAInfoDeep.h:120-123 ; getZ  LAstep.h:181-185
+            dz = add(mul(newdz, rec->ZCoeff), mul(dc, rec->CCoeff));
+            const Cplx z = add(rec[1].Ref, dz);
+            j++;
+            Real zn = cheb(z), dn = cheb(dz);
+            reduce(zn);
+            reduce(dn);
+            if (lt_pr(zn, dn) || j >= MacroItCount) {
+                dz = z;
+                j = 0;
+            }
+        }
+        if (iter >= A.n_iterations) break;
+    }
+}
+
 template <class Num, class IterT, Lav2Mode Mode, bool Count>
 __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A) {
     using Real = typename Num::Real;
     using Cplx = typename Num::Cplx;
-    using LA = LaRec<Num, IterT>;
 
     const int lane = threadIdx.x & 31;
     const int tiles_x = (A.width + 7) >> 3;
@@ -121,7 +199,8 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
 
         const int X = (int)(tile % tiles_x) * 8 + (lane & 7);
         const int Y = ((int)(tile / tiles_x) * A.shard_count + A.shard_index) * 4 + (lane >> 3);
-        if (X >= A.width || Y >= A.height) continue;
+        // lanes outside the image stay with the warp (the perturbation loop is warp-synchronous) and do nothing
+        const bool live = X < A.width && Y < A.height;
 
         IterT iter = 0;
         IterT RefIteration = 0;
@@ -132,86 +211,19 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
         Cplx dz = Num::c_zero();
 
         if constexpr (Mode == Lav2Mode::Full || Mode == Lav2Mode::LAO) {
-            // ---- AT (ATInfo.h:128-188) ----
-            if (A.la_valid && A.use_at && le_pr(cheb(dc), A.at.ThresholdC)) {
-                const IterT at_max = A.n_iterations / A.at.StepLength;
-                Cplx c = add(mul(dc, A.at.CCoeff), A.at.RefC);
-                reduce(c);
-                Cplx z = Num::c_zero();
-                IterT i = 0;
-                for (; i < at_max; i++) {
-                    // nvcc shares re*re / im*im between norm_squared and z*z in the reference build:
-                    //   nsq = rr + ii ; z2.re = rr - ii ; z2.im = fma(re, im, re*im)
-                    const auto rr = z.re * z.re;
-                    const auto ii = z.im * z.im;
-                    Real nsq;
-                    if constexpr (Num::kHdr) { nsq.m = rr + ii; nsq.e = z.e << 1; reduce(nsq); }
-                    else { nsq = rr + ii; }
-                    if (gt_pr(nsq, A.at.SqrEscapeRadius)) break;
-                    Cplx z2;
-                    z2.re = rr - ii;
-                    z2.im = fma_(z.re, z.im, z.re * z.im);
-                    if constexpr (Num::kHdr) z2.e = imax(z.e + z.e, MIN_BIG);
-                    z = add(z2, c);
-                }
-                if (Count) steps += i;
-                dz = mul(z, A.at.InvZCoeff);
-                reduce(dz);
-                iter = i * A.at.StepLength;
-            }
-
-            // ---- LA stages (LAKernel.cuh:91-127) ----
-            IterT stage = A.la_valid ? A.la_stage_count : 0;
-            while (stage > 0) {
-                stage--;
-                const IterT LAIndex = A.stages[stage].LAIndex;
-                // isLAStageInvalid  GPU_LAReference.h:241-255
-                if (ge_pr(cheb(dc), A.las[LAIndex].LAThresholdC)) continue;
-                const IterT MacroItCount = A.stages[stage].MacroItCount;
-                IterT j = RefIteration;
-
-                while (iter < A.n_iterations) {
-                    // getLA  GPU_LAReference.h:271-303
-                    const LA *rec = A.las + (LAIndex + j);
-                    const IterT l = rec->StepLength;
-                    bool unusable = true;
-                    Cplx newdz;
-                    if (iter + l <= A.n_iterations) {
-                        // Prepare  GPU_LAInfoDeep.h:90-105: newdz = dz * (2*Ref + dz), reduced
-                        newdz = mul(dz, add(Num::c_mul2(rec->Ref), dz));
-                        reduce(newdz);
-                        unusable = ge_pr(cheb(newdz), rec->LAThreshold);
-                    }
-                    if (unusable) {
-                        RefIteration = rec->NextStageLAIndex;
-                        break;
-                    }
-                    iter += l;
-                    if (Count) steps++;
-                    // Evaluate  GPU_LAInfoDeep.h:120-123 ; getZ  LAstep.h:181-185
-                    dz = add(mul(newdz, rec->ZCoeff), mul(dc, rec->CCoeff));
-                    const Cplx z = add(rec[1].Ref, dz);
-                    j++;
-                    Real zn = cheb(z), dn = cheb(dz);
-                    reduce(zn);
-                    reduce(dn);
-                    if (lt_pr(zn, dn) || j >= MacroItCount) {
-                        dz = z;
-                        j = 0;
-                    }
-                }
-                if (iter >= A.n_iterations) break;
+            if (live) {
+                lav2_la_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps);
             }
         }
 
         if constexpr (Mode == Lav2Mode::Full || Mode == Lav2Mode::PO) {
             // ---- plain perturbation with rebasing (LAKernel.cuh:130-236) ----
             Real dX = Num::c_re(dz), dY = Num::c_im(dz);
-            PerturbLoop<Num, IterT, Count>::run(A.orbit, A.orbit_fast, A.orbit_count, A.n_iterations, dcX, dcY, dX, dY, RefIteration,
-                                                iter, steps);
+            PerturbLoop<Num, IterT, Count>::run(live, A.orbit, A.orbit_fast, A.orbit_count, A.n_iterations, dcX, dcY, dX, dY,
+                                                RefIteration, iter, steps);
         }
 
-        A.out[(size_t)Y * A.pitch + X] = iter;
+        if (live) A.out[(size_t)Y * A.pitch + X] = iter;
     }
 
     if (Count && A.step_counter) {

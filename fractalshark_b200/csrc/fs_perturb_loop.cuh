@@ -28,8 +28,9 @@ template <class Num> struct OrbitIO; // fs_lav2.cuh
 // ---- generic loop (any numeric policy) --------------------------------------------------------------------
 template <class Num, class IterT, bool Count> struct PerturbLoop {
     using Real = typename Num::Real;
-    FS_D static void run(const void *orbit, const void * /*orbit_fast*/, IterT orbit_count, IterT n_iterations, Real dcX,
-                         Real dcY, Real &dX, Real &dY, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
+    FS_D static void run(bool live, const void *orbit, const void * /*orbit_fast*/, IterT orbit_count, IterT n_iterations,
+                         Real dcX, Real dcY, Real &dX, Real &dY, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
+        if (!live) return;
         Real zx, zy;
         OrbitIO<Num>::load(orbit, RefIteration, zx, zy);
         const IterT last = orbit_count - 1;
@@ -173,7 +174,10 @@ template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Coun
     using Real = Hdr<float>;
     // orbit_fast: the per-element table of fs_scaled_loop.cuh (built on upload); nullptr selects the pure
     // float+exponent loop.
-    FS_D static void run(const void *orbit, const void *orbit_fast, IterT orbit_count, IterT n_iterations, Real dcX,
+    static constexpr unsigned kRecenterEvery = 4; // rounds between warp-wide re-centrings of w
+    static constexpr int kSlowBatch = 1;          // lanes that must be waiting before a float+exponent step is issued
+    // Warp-synchronous: all 32 lanes call this converged; `live` = the lane has a pixel to iterate.
+    FS_D static void run(bool live, const void *orbit, const void *orbit_fast, IterT orbit_count, IterT n_iterations, Real dcX,
                          Real dcY, Real &dXio, Real &dYio, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
         using namespace hdr32fast;
         const uint4 *__restrict__ orb = reinterpret_cast<const uint4 *>(orbit);
@@ -181,6 +185,7 @@ template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Coun
         State a, b;
         a.dxm = dXio.m; a.dxe = dXio.e; a.dym = dYio.m; a.dye = dYio.e;
         if (orbit_fast == nullptr) {
+            if (!live) return;
             a.z = __ldg(orb + RefIteration);
             for (;;) {
                 if (!step<IterT, Count>(a, b, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) break;
@@ -189,22 +194,28 @@ template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Coun
             return;
         }
         const scaled::FastElem *__restrict__ tab = reinterpret_cast<const scaled::FastElem *>(orbit_fast);
-        for (;;) {
-            // scaled plain-float chunks for as long as they commit ...
-            scaled::Scale sc;
-            float wx, wy;
-            scaled::FastElem E0;
-            if (scaled::enter<IterT>(tab, dcX, dcY, a.dxm, a.dxe, a.dym, a.dye, RefIteration, iter, n_iterations, sc, wx, wy,
-                                     E0)) {
-                const scaled::Outcome oc = scaled::run<IterT, Count>(tab, last, n_iterations, sc, wx, wy, E0, a.dxm, a.dxe,
-                                                                     a.dym, a.dye, RefIteration, iter, steps);
-                if (oc == scaled::kFinished) break;
-                if (oc == scaled::kContinue) continue;
+        const scaled::CRed c = scaled::reduce_c(dcX, dcY);
+        const unsigned lane_bit = 1u << (threadIdx.x & 31);
+        scaled::Lane L;
+        scaled::Mode mode = live ? scaled::kTry : scaled::kDone;
+        for (unsigned round = 0;; ++round) {
+            if (mode == scaled::kTry)
+                mode = scaled::enter<IterT>(tab, c, a.dxm, a.dxe, a.dym, a.dye, RefIteration, iter, n_iterations, L.sc, L.wx,
+                                            L.wy, L.E) ? scaled::kFast : scaled::kSlow;
+            const unsigned fast_m = __ballot_sync(0xffffffffu, mode == scaled::kFast);
+            const unsigned slow_m = __ballot_sync(0xffffffffu, mode == scaled::kSlow);
+            if ((fast_m | slow_m) == 0u) break;
+            if (mode == scaled::kFast) {
+                // scaled plain-float chunk; every kRecenterEvery-th round all lanes re-centre together
+                mode = scaled::fast_iteration<IterT, Count>(tab, last, n_iterations, c, (round % kRecenterEvery) == kRecenterEvery - 1,
+                                                            L, RefIteration, iter, a.dxm, a.dxe, a.dym, a.dye, steps);
+            } else if ((slow_m & lane_bit) && (fast_m == 0u || __popc(slow_m) >= kSlowBatch)) {
+                // one float+exponent step for the lanes the scaled form refused (batched: they wait for company
+                // while other lanes still make fast progress)
+                a.z = __ldg(orb + RefIteration);
+                if (!step<IterT, Count>(a, b, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) mode = scaled::kDone;
+                else { a = b; mode = scaled::kTry; }
             }
-            // ... and one float+exponent step whenever the scaled form refuses the state or rejects a chunk
-            a.z = __ldg(orb + RefIteration);
-            if (!step<IterT, Count>(a, b, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) break;
-            a = b;
         }
         // the delta after the last step is not observable (only `iter` is written out)
     }

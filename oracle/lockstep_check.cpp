@@ -25,48 +25,52 @@ template <class IterT>
 IterT lockstep_pixel(const Lav2Job<IterT> &J, const fs::scaled::FastElem *tab, int X, int Y, LockStats &st) {
     using namespace fs::scaled;
     uint64_t steps = 0;
-    PerturbState<IterT> S;
+    PerturbState<IterT> S; // the oracle shadow (float+exponent form)
     lav2_prologue(J, X, Y, steps, S);
     if (!(J.mode == 1 || J.mode == 2)) return S.iter;
     const IterT last = J.orbit_count - 1;
-    for (;;) {
-        Scale sc;
-        float wx, wy;
-        FastElem E0;
-        const fs::Hdr<float> cX{S.cX.mantissa, S.cX.exp}, cY{S.cY.mantissa, S.cY.exp};
-        if (enter<IterT>(tab, cX, cY, S.dX.mantissa, S.dX.exp, S.dY.mantissa, S.dY.exp, S.RefIteration, S.iter,
-                         J.n_iterations, sc, wx, wy, E0)) {
-            PerturbState<IterT> F = S; // scaled path works on F, the oracle shadow on S
+    const CRed c = reduce_c(fs::Hdr<float>{S.cX.mantissa, S.cX.exp}, fs::Hdr<float>{S.cY.mantissa, S.cY.exp});
+    // same per-lane control flow as PerturbLoop<NumHdr<float>>::run in fs_perturb_loop.cuh
+    Lane L;
+    Mode mode = kTry;
+    PerturbState<IterT> F = S; // what the scaled path believes
+    for (unsigned round = 0;; ++round) {
+        if (mode == kTry) {
+            F = S;
+            const bool in = enter<IterT>(tab, c, F.dX.mantissa, F.dX.exp, F.dY.mantissa, F.dY.exp, F.RefIteration, F.iter,
+                                         J.n_iterations, L.sc, L.wx, L.wy, L.E);
+            if (!in) st.entries_refused++;
+            mode = in ? kFast : kSlow;
+        }
+        if (mode == kFast) {
             unsigned long long fsteps = 0;
-            const Outcome oc = run<IterT, true>(tab, last, J.n_iterations, sc, wx, wy, E0, F.dX.mantissa, F.dX.exp,
-                                                F.dY.mantissa, F.dY.exp, F.RefIteration, F.iter, fsteps);
+            const IterT iter_before = F.iter;
+            mode = fast_iteration<IterT, true>(tab, last, J.n_iterations, c, (round % 4) == 3, L, F.RefIteration, F.iter,
+                                               F.dX.mantissa, F.dX.exp, F.dY.mantissa, F.dY.exp, fsteps);
             st.fast_steps += fsteps;
-            // advance the shadow by the committed steps
             bool alive = true;
             for (unsigned long long i = 0; i < fsteps && alive; i++) alive = perturb_step(J, S);
-            if (oc == kFinished) {
+            if (mode == kDone) {
                 st.finished_fast++;
                 if (alive || S.iter != F.iter) st.mismatches++;
                 return F.iter;
             }
             if (!alive) { st.mismatches++; return S.iter; }
-            st.chunks_ok += fsteps / kChunk;
-            if (fsteps) {
-                HF ax = S.dX, ay = S.dY, bx = F.dX, by = F.dY;
-                Reduce(ax); Reduce(ay); Reduce(bx); Reduce(by);
-                if (!(ax.mantissa == bx.mantissa && ax.exp == bx.exp && ay.mantissa == by.mantissa && ay.exp == by.exp &&
-                      S.RefIteration == F.RefIteration && S.iter == F.iter))
-                    st.mismatches++;
-                // continue from the scaled path's representation (what the kernel does)
-                S.dX = F.dX; S.dY = F.dY;
-            }
-            if (oc == kContinue) continue;
-            st.chunks_rejected++;
+            if (fsteps) st.chunks_ok++; else if (F.iter == iter_before && mode == kSlow) st.chunks_rejected++;
+            // compare by value: the scaled state (w * 2^k) against the shadow
+            float fxm, fym; int fxe, fye;
+            leave(L.sc, L.wx, L.wy, fxm, fxe, fym, fye);
+            HF ax = S.dX, ay = S.dY;
+            Reduce(ax); Reduce(ay);
+            if (!(ax.mantissa == fxm && ax.exp == fxe && ay.mantissa == fym && ay.exp == fye &&
+                  S.RefIteration == F.RefIteration && S.iter == F.iter))
+                st.mismatches++;
+            if (mode == kSlow) { S.dX = F.dX; S.dY = F.dY; } // continue from the scaled path's representation
         } else {
-            st.entries_refused++;
+            st.slow_steps++;
+            if (!perturb_step(J, S)) return S.iter;
+            mode = kTry;
         }
-        st.slow_steps++;
-        if (!perturb_step(J, S)) return S.iter;
     }
 }
 
