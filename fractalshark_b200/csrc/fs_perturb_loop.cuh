@@ -174,7 +174,7 @@ template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Coun
     using Real = Hdr<float>;
     // orbit_fast: the per-element table of fs_scaled_loop.cuh (built on upload); nullptr selects the pure
     // float+exponent loop.
-    static constexpr unsigned kRecenterEvery = 4; // rounds between warp-wide re-centrings of w
+    static constexpr unsigned kRecenterEvery = 8; // rounds between warp-wide re-centrings of w
     static constexpr int kSlowBatch = 1;          // lanes that must be waiting before a float+exponent step is issued
     // Warp-synchronous: all 32 lanes call this converged; `live` = the lane has a pixel to iterate.
     FS_D static void run(bool live, const void *orbit, const void *orbit_fast, IterT orbit_count, IterT n_iterations, Real dcX,

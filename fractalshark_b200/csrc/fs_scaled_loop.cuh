@@ -40,16 +40,18 @@ struct alignas(16) FastElem {
     float ax, ay, th, kmin;
 };
 
-constexpr int kChunk = 8;         // speculative steps per commit
+constexpr int kChunk = 16;        // speculative steps per commit
 constexpr int kNorm = 16;         // (re)normalisation puts |w|_inf into [2^16, 2^17)
 constexpr float kLo = 0x1p-6f;    // every component of every committed w must be >= kLo ...
-constexpr float kHi = 0x1p56f;    // ... and |w|_inf < kHi at every chunk boundary (< 2^84 inside a chunk)
-constexpr float kTestScale = 0x1p-30f; // the rebase test squares w * 2^-30 (keeps 2^84 ^2 inside binary32)
+constexpr float kHi = 0x1p40f;    // ... and |w|_inf < kHi at every chunk boundary (< 2^95 inside a chunk: <= x10 per step)
+constexpr float kTestScale = 0x1p-40f; // the rebase test squares w * 2^-40 (keeps (2^95)^2 inside binary32; a square
+                                       // that underflows is > 2^20 below the other side, the decision is unaffected)
 constexpr int kCMaxExp = 30;      // c' must be below 2^31
 constexpr int kCDropExp = -110;   // c' below 2^-109 is dropped: any sum it could change is rejected by kLo anyway
-constexpr int kDeepK = -100;      // the exact escape/rebase tests need 2^-k representable with headroom
+constexpr int kDeepK = -126;      // the exact escape/rebase tests need 2^k and 2^-k representable
+constexpr int kNegligibleK = -200; // below this, d is < 2^-25 of every eligible non-zero orbit component (>= 2^-77)
 constexpr float kZeroKmin = -100.0f; // a step on Z = 0 needs d itself well inside the normal range
-constexpr float kTinyKmin = -70.0f;  // same for elements with a component below 2^-20
+constexpr float kTinyKmin = -126.0f; // elements with a component below 2^-20 need 2^k exact (or d negligible, see chunk)
 constexpr int kMinZExp = -20, kTinyZExp = -77;
 
 FS_HD float pow2i(int e) { return u2f((uint32_t)(e + 127) << 23); } // exact 2^e, e in [-126, 127]
@@ -73,7 +75,9 @@ FS_HD FastElem make_fast_elem(float xm, int xe, float ym, int ye, bool last) {
             e.ax = (xm * pow2i(xe + 1 + 60)) * pow2i(-60);
             e.ay = (ym * pow2i(ye + 1 + 60)) * pow2i(-60);
             if (vx < kMinZExp || vy < kMinZExp) {
-                e.kmin = kTinyKmin; // th stays 0
+                // th stays 0.  |Z|_inf < 1 keeps |Z|^2 < 2: with d negligible such an element cannot escape
+                if (vx >= 0 || vy >= 0) e.th = u2f(0x7fc00000u);
+                e.kmin = kTinyKmin;
             } else {
                 e.kmin = -3.0e38f;
                 const double a = 0.5 * fabs((double)e.ax), b = 0.5 * fabs((double)e.ay);
@@ -137,7 +141,9 @@ FS_HD bool set_scale(Scale &sc, int k, const CRed &c) {
     return true;
 }
 // The element a step starts from must allow the current scale.
-FS_HD bool elem_allows(const FastElem &E, int k) { return !is_nan(E.th) && (float)k >= E.kmin; }
+FS_HD bool elem_allows(const FastElem &E, int k) {
+    return !is_nan(E.th) && ((float)k >= E.kmin || (k <= kNegligibleK && E.kmin == kTinyKmin));
+}
 
 // Try to express the float+exponent state (dX, dY) at orbit index n in scaled form.
 template <class IterT>
@@ -178,11 +184,10 @@ enum ChunkResult : int { kCommitted = 0, kFinished = 1, kRejected = 2 };
 // One speculative chunk of kChunk steps from (wx, wy, E = element at n).  kCommitted: state advanced by kChunk
 // steps.  kFinished: the pixel escaped after `done_steps` further iterations.  kRejected: state untouched.
 template <class IterT>
-FS_HD ChunkResult chunk(const FastElem *tab, IterT last, const Scale &sc, float &wxio, float &wyio, FastElem &Eio,
-                        IterT &nio, int &done_steps) {
-    float wx = wxio, wy = wyio;
-    FastElem E = Eio;
-    IterT n = nio;
+FS_HD ChunkResult chunk(const FastElem *tab, IterT last, const Scale &sc, float &wx, float &wy, FastElem &E, IterT &n,
+                        int &done_steps) {
+    const float wx0 = wx, wy0 = wy;
+    const IterT n0 = n;
     float lo = 0x1p100f;
     bool ok = true, done = false;
     int s = 0;
@@ -192,37 +197,46 @@ FS_HD ChunkResult chunk(const FastElem *tab, IterT last, const Scale &sc, float 
         const float Sx = fma_(wx, sc.sk, E.ax), Sy = fma_(wy, sc.sk, E.ay); // 2Z + d
         const float pa = wx * Sx, pb = wy * Sy, pc = wx * Sy, pd = wy * Sx;
         const float sumX = pa - pb, sumY = pc + pd;
-        float nx = sumX + sc.ccx, ny = sumY + sc.ccy;
+        wx = sumX + sc.ccx;
+        wy = sumY + sc.ccy;
         ++n;
-        FastElem Ec = En;
-        const float m = fmaxf(fabsf(nx), fabsf(ny));
-        lo = fminf(fminf(fabsf(nx), fabsf(ny)), lo);
+        E = En;
+        const float m = fmaxf(fabsf(wx), fabsf(wy));
+        lo = fminf(fminf(fabsf(wx), fabsf(wy)), lo);
         const float thr = En.th * sc.ik;
         if (!(m < thr)) {
             // ---- exact escape and rebase tests (LAKernel.cuh:196-226), in scaled plain floats ----
-            if (sc.k < kDeepK || !elem_allows(En, sc.k)) { ok = false; break; }
-            const float tx = fma_(nx, sc.sk2, En.ax), ty = fma_(ny, sc.sk2, En.ay); // 2*(Z' + d')
+            if (!elem_allows(En, sc.k)) { ok = false; break; }
+            if (sc.k < kDeepK) {
+                // d is negligible against Z' (both components in [2^-77, 1)): no escape, no rebase by norm;
+                // everything else at this depth takes the float+exponent step
+                if (sc.k > kNegligibleK || En.kmin != kTinyKmin || n >= last) { ok = false; break; }
+                continue;
+            }
+            const float tx = fma_(wx, sc.sk2, En.ax), ty = fma_(wy, sc.sk2, En.ay); // 2*(Z' + d')
             const float tx2 = tx * tx, ty2 = ty * ty;
             const float n2 = tx2 + ty2;
             if (!(n2 < 16.0f)) { done = true; break; }
-            const float Tx = fma_(En.ax, 0.5f * sc.ik, nx), Ty = fma_(En.ay, 0.5f * sc.ik, ny); // (Z' + d') * 2^-k
-            const float Txs = Tx * kTestScale, Tys = Ty * kTestScale, dxs = nx * kTestScale, dys = ny * kTestScale;
+            const float Tx = fma_(En.ax, 0.5f * sc.ik, wx), Ty = fma_(En.ay, 0.5f * sc.ik, wy); // (Z' + d') * 2^-k
+            const float Txs = Tx * kTestScale, Tys = Ty * kTestScale, dxs = wx * kTestScale, dys = wy * kTestScale;
             const float Tx2 = Txs * Txs, Ty2 = Tys * Tys, dx2 = dxs * dxs, dy2 = dys * dys;
             const float N2 = Tx2 + Ty2, D2 = dx2 + dy2;
             if (N2 < D2 || n >= last) {
                 // rebase: the next step runs on Z_0
-                Ec = load_elem(tab, 0);
-                if (!elem_allows(Ec, sc.k) || !(fmaxf(fabsf(Tx), fabsf(Ty)) < kHi)) { ok = false; break; }
-                nx = Tx; ny = Ty;
+                E = load_elem(tab, 0);
+                if (!elem_allows(E, sc.k) || !(fmaxf(fabsf(Tx), fabsf(Ty)) < kHi)) { ok = false; break; }
+                wx = Tx; wy = Ty;
                 n = 0;
-                lo = fminf(fminf(fabsf(nx), fabsf(ny)), lo);
+                lo = fminf(fminf(fabsf(wx), fabsf(wy)), lo);
             }
         }
-        wx = nx; wy = ny; E = Ec;
     }
-    if (!ok || !(lo >= kLo)) return kRejected;
+    if (!ok || !(lo >= kLo)) {
+        wx = wx0; wy = wy0; n = n0;
+        E = load_elem(tab, n0);
+        return kRejected;
+    }
     if (done) { done_steps = s; return kFinished; }
-    wxio = wx; wyio = wy; Eio = E; nio = n;
     return kCommitted;
 }
 

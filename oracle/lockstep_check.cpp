@@ -45,7 +45,7 @@ IterT lockstep_pixel(const Lav2Job<IterT> &J, const fs::scaled::FastElem *tab, i
         if (mode == kFast) {
             unsigned long long fsteps = 0;
             const IterT iter_before = F.iter;
-            mode = fast_iteration<IterT, true>(tab, last, J.n_iterations, c, (round % 4) == 3, L, F.RefIteration, F.iter,
+            mode = fast_iteration<IterT, true>(tab, last, J.n_iterations, c, (round % 8) == 7, L, F.RefIteration, F.iter,
                                                F.dX.mantissa, F.dX.exp, F.dY.mantissa, F.dY.exp, fsteps);
             st.fast_steps += fsteps;
             bool alive = true;
