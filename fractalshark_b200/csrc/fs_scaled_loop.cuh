@@ -181,62 +181,82 @@ FS_HD bool renorm(Scale &sc, const CRed &c, float &wx, float &wy, const FastElem
 
 enum ChunkResult : int { kCommitted = 0, kFinished = 1, kRejected = 2 };
 
-// One speculative chunk of kChunk steps from (wx, wy, E = element at n).  kCommitted: state advanced by kChunk
-// steps.  kFinished: the pixel escaped after `done_steps` further iterations.  kRejected: state untouched.
+FS_HD FastElem load_elem_at(const FastElem *p, int off) {
+#ifdef __CUDA_ARCH__
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p) + off);
+    FastElem e;
+    e.ax = v.x; e.ay = v.y; e.th = v.z; e.kmin = v.w;
+    return e;
+#else
+    return p[off];
+#endif
+}
+
+// One speculative chunk: up to kChunk steps from (wx, wy, E = element at n), straight-line; the first step whose
+// result passes the element's threshold ends the chunk and gets the exact escape / rebase tests (one shared
+// copy of that code).  kCommitted: state advanced by `steps` iterations.  kFinished: the pixel escaped after
+// `steps` further iterations (steps + 1 executed).  kRejected: state untouched, steps = 0.
 template <class IterT>
 FS_HD ChunkResult chunk(const FastElem *tab, IterT last, const Scale &sc, float &wx, float &wy, FastElem &E, IterT &n,
-                        int &done_steps) {
+                        int &steps) {
     const float wx0 = wx, wy0 = wy;
     const IterT n0 = n;
+    const FastElem *p = tab + n0; // step u arrives at p[u + 1]
     float lo = 0x1p100f;
-    bool ok = true, done = false;
-    int s = 0;
+    int cnt = kChunk;
+    bool trig = false;
 #pragma unroll
-    for (s = 0; s < kChunk; s++) {
-        const FastElem En = load_elem(tab, (uint64_t)n + 1);
+    for (int u = 0; u < kChunk; u++) {
+        const FastElem En = load_elem_at(p, u + 1);
         const float Sx = fma_(wx, sc.sk, E.ax), Sy = fma_(wy, sc.sk, E.ay); // 2Z + d
         const float pa = wx * Sx, pb = wy * Sy, pc = wx * Sy, pd = wy * Sx;
         const float sumX = pa - pb, sumY = pc + pd;
         wx = sumX + sc.ccx;
         wy = sumY + sc.ccy;
-        ++n;
         E = En;
         const float m = fmaxf(fabsf(wx), fabsf(wy));
         lo = fminf(fminf(fabsf(wx), fabsf(wy)), lo);
-        const float thr = En.th * sc.ik;
-        if (!(m < thr)) {
-            // ---- exact escape and rebase tests (LAKernel.cuh:196-226), in scaled plain floats ----
-            if (!elem_allows(En, sc.k)) { ok = false; break; }
-            if (sc.k < kDeepK) {
-                // d is negligible against Z' (both components in [2^-77, 1)): no escape, no rebase by norm;
-                // everything else at this depth takes the float+exponent step
-                if (sc.k > kNegligibleK || En.kmin != kTinyKmin || n >= last) { ok = false; break; }
-                continue;
-            }
-            const float tx = fma_(wx, sc.sk2, En.ax), ty = fma_(wy, sc.sk2, En.ay); // 2*(Z' + d')
+        if (!(m < En.th * sc.ik)) { cnt = u + 1; trig = true; break; }
+    }
+    n = n0 + (IterT)cnt;
+    bool ok = lo >= kLo, done = false;
+    if (trig && ok) {
+        // ---- the step that arrived at E = element n: exact escape and rebase tests (LAKernel.cuh:196-226) ----
+        if (!elem_allows(E, sc.k)) {
+            ok = false;
+        } else if (sc.k < kDeepK) {
+            // d is negligible against Z' (both components in [2^-77, 1)): no escape, no rebase by norm;
+            // everything else at this depth takes the float+exponent step
+            if (sc.k > kNegligibleK || E.kmin != kTinyKmin || n >= last) ok = false;
+        } else {
+            const float tx = fma_(wx, sc.sk2, E.ax), ty = fma_(wy, sc.sk2, E.ay); // 2*(Z' + d')
             const float tx2 = tx * tx, ty2 = ty * ty;
             const float n2 = tx2 + ty2;
-            if (!(n2 < 16.0f)) { done = true; break; }
-            const float Tx = fma_(En.ax, 0.5f * sc.ik, wx), Ty = fma_(En.ay, 0.5f * sc.ik, wy); // (Z' + d') * 2^-k
-            const float Txs = Tx * kTestScale, Tys = Ty * kTestScale, dxs = wx * kTestScale, dys = wy * kTestScale;
-            const float Tx2 = Txs * Txs, Ty2 = Tys * Tys, dx2 = dxs * dxs, dy2 = dys * dys;
-            const float N2 = Tx2 + Ty2, D2 = dx2 + dy2;
-            if (N2 < D2 || n >= last) {
-                // rebase: the next step runs on Z_0
-                E = load_elem(tab, 0);
-                if (!elem_allows(E, sc.k) || !(fmaxf(fabsf(Tx), fabsf(Ty)) < kHi)) { ok = false; break; }
-                wx = Tx; wy = Ty;
-                n = 0;
-                lo = fminf(fminf(fabsf(wx), fabsf(wy)), lo);
+            if (!(n2 < 16.0f)) {
+                done = true;
+            } else {
+                const float Tx = fma_(E.ax, 0.5f * sc.ik, wx), Ty = fma_(E.ay, 0.5f * sc.ik, wy); // (Z' + d') * 2^-k
+                const float Txs = Tx * kTestScale, Tys = Ty * kTestScale, dxs = wx * kTestScale, dys = wy * kTestScale;
+                const float Tx2 = Txs * Txs, Ty2 = Tys * Tys, dx2 = dxs * dxs, dy2 = dys * dys;
+                const float N2 = Tx2 + Ty2, D2 = dx2 + dy2;
+                if (N2 < D2 || n >= last) {
+                    // rebase: the next step runs on Z_0
+                    E = load_elem(tab, 0);
+                    ok = elem_allows(E, sc.k) && fmaxf(fabsf(Tx), fabsf(Ty)) < kHi && fminf(fabsf(Tx), fabsf(Ty)) >= kLo;
+                    wx = Tx; wy = Ty;
+                    n = 0;
+                }
             }
         }
     }
-    if (!ok || !(lo >= kLo)) {
+    if (!ok) {
         wx = wx0; wy = wy0; n = n0;
         E = load_elem(tab, n0);
+        steps = 0;
         return kRejected;
     }
-    if (done) { done_steps = s; return kFinished; }
+    if (done) { steps = cnt - 1; return kFinished; }
+    steps = cnt;
     return kCommitted;
 }
 
@@ -266,16 +286,16 @@ FS_HD Mode fast_iteration(const FastElem *tab, IterT last, IterT n_iterations, c
         leave(L.sc, L.wx, L.wy, dxm, dxe, dym, dye);
         return kSlow;
     }
-    int done_steps = 0;
-    const ChunkResult r = chunk<IterT>(tab, last, L.sc, L.wx, L.wy, L.E, n, done_steps);
+    int cnt = 0;
+    const ChunkResult r = chunk<IterT>(tab, last, L.sc, L.wx, L.wy, L.E, n, cnt);
     if (r == kFinished) {
-        iter += (IterT)done_steps;
-        if (Count) steps += (unsigned long long)done_steps + 1;
+        iter += (IterT)cnt;
+        if (Count) steps += (unsigned long long)cnt + 1;
         return kDone;
     }
     if (r == kCommitted) {
-        iter += (IterT)kChunk;
-        if (Count) steps += (unsigned long long)kChunk;
+        iter += (IterT)cnt;
+        if (Count) steps += (unsigned long long)cnt;
         const bool budget = (uint64_t)(n_iterations - iter) >= (uint64_t)kChunk;
         if (budget && fmaxf(fabsf(L.wx), fabsf(L.wy)) < kHi) return kFast;
         if (budget && renorm(L.sc, c, L.wx, L.wy, L.E)) return kFast;

@@ -140,7 +140,7 @@ LOCKSTEP_CASES = [
     (5, RenderAlgorithm.GpuHDRx32PerturbedLAv2PO, 20000, 96),
     (1, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 24),
     (1, RenderAlgorithm.GpuHDRx32PerturbedLAv2PO, None, 24),
-    (19, RenderAlgorithm.GpuHDRx32PerturbedLAv2, 2000000, 48),
+    (19, RenderAlgorithm.GpuHDRx32PerturbedLAv2, 3000000, 48),
 ]
 
 
