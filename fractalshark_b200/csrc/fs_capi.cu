@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) build_fast_table_kernel(const uint4 *__re
                                                                scaled::FastElem *__restrict__ tab) {
     for (uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; n < count; n += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 v = orbit[n];
-        tab[n] = scaled::make_fast_elem(__uint_as_float(v.x), (int)v.y, __uint_as_float(v.w), (int)v.z, n + 1 >= count);
+        tab[n] = scaled::make_fast_elem(__uint_as_float(v.x), (int)v.y, __uint_as_float(v.w), (int)v.z, n, n + 1 >= count);
     }
 }
 
@@ -174,7 +174,8 @@ uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, u
     dst.data.bytes = bytes;
     err = cudaMemcpyAsync(dst.data.ptr, src->elements, bytes, cudaMemcpyDefault, r->compute);
     if (err != cudaSuccess) return err;
-    if (numeric == FS_NUM_HDR32 && pextras == FS_PEXTRAS_DISABLE && src->compressed_count > 1 && r->use_scaled) {
+    if (numeric == FS_NUM_HDR32 && pextras == FS_PEXTRAS_DISABLE && src->compressed_count > 1 &&
+        src->compressed_count <= scaled::kMaxElems && r->use_scaled) {
         const size_t fbytes = sizeof(scaled::FastElem) * src->compressed_count;
         err = cudaMallocAsync(&dst.fast.ptr, fbytes, r->compute);
         if (err != cudaSuccess) return err;

@@ -174,7 +174,6 @@ template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Coun
     using Real = Hdr<float>;
     // orbit_fast: the per-element table of fs_scaled_loop.cuh (built on upload); nullptr selects the pure
     // float+exponent loop.
-    static constexpr unsigned kRecenterEvery = 8; // rounds between warp-wide re-centrings of w
     static constexpr int kSlowBatch = 1;          // lanes that must be waiting before a float+exponent step is issued
     // Warp-synchronous: all 32 lanes call this converged; `live` = the lane has a pixel to iterate.
     FS_D static void run(bool live, const void *orbit, const void *orbit_fast, IterT orbit_count, IterT n_iterations, Real dcX,
@@ -194,24 +193,24 @@ template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Coun
             return;
         }
         const scaled::FastElem *__restrict__ tab = reinterpret_cast<const scaled::FastElem *>(orbit_fast);
-        const scaled::CRed c = scaled::reduce_c(dcX, dcY);
+        scaled::CRed c = scaled::reduce_c(dcX, dcY);
+        // keep the four words of c in registers (otherwise they are re-derived from dcX/dcY in every round)
+        asm volatile("" : "+r"(c.xb), "+r"(c.yb), "+r"(c.xe), "+r"(c.ye));
         const unsigned lane_bit = 1u << (threadIdx.x & 31);
         scaled::Lane L;
         scaled::Mode mode = live ? scaled::kTry : scaled::kDone;
-        for (unsigned round = 0;; ++round) {
+        for (;;) {
             if (mode == scaled::kTry)
-                mode = scaled::enter<IterT>(tab, c, a.dxm, a.dxe, a.dym, a.dye, RefIteration, iter, n_iterations, L.sc, L.wx,
-                                            L.wy, L.E) ? scaled::kFast : scaled::kSlow;
+                mode = scaled::enter<IterT>(tab, c, a.dxm, a.dxe, a.dym, a.dye, RefIteration, iter, n_iterations, L)
+                           ? scaled::kFast : scaled::kSlow;
             const unsigned fast_m = __ballot_sync(0xffffffffu, mode == scaled::kFast);
             const unsigned slow_m = __ballot_sync(0xffffffffu, mode == scaled::kSlow);
             if ((fast_m | slow_m) == 0u) break;
             if (mode == scaled::kFast) {
-                // scaled plain-float chunk; every kRecenterEvery-th round all lanes re-centre together
-                mode = scaled::fast_iteration<IterT, Count>(tab, last, n_iterations, c, (round % kRecenterEvery) == kRecenterEvery - 1,
-                                                            L, RefIteration, iter, a.dxm, a.dxe, a.dym, a.dye, steps);
+                mode = scaled::fast_round<IterT, Count>(tab, last, n_iterations, c, L, RefIteration, iter, a.dxm, a.dxe, a.dym,
+                                                        a.dye, steps);
             } else if ((slow_m & lane_bit) && (fast_m == 0u || __popc(slow_m) >= kSlowBatch)) {
-                // one float+exponent step for the lanes the scaled form refused (batched: they wait for company
-                // while other lanes still make fast progress)
+                // one float+exponent step for the lanes the scaled form refused
                 a.z = __ldg(orb + RefIteration);
                 if (!step<IterT, Count>(a, b, orb, last, n_iterations, dcX, dcY, RefIteration, iter, steps)) mode = scaled::kDone;
                 else { a = b; mode = scaled::kTry; }

@@ -38,15 +38,15 @@ IterT lockstep_pixel(const Lav2Job<IterT> &J, const fs::scaled::FastElem *tab, i
         if (mode == kTry) {
             F = S;
             const bool in = enter<IterT>(tab, c, F.dX.mantissa, F.dX.exp, F.dY.mantissa, F.dY.exp, F.RefIteration, F.iter,
-                                         J.n_iterations, L.sc, L.wx, L.wy, L.E);
+                                         J.n_iterations, L);
             if (!in) st.entries_refused++;
             mode = in ? kFast : kSlow;
         }
         if (mode == kFast) {
             unsigned long long fsteps = 0;
             const IterT iter_before = F.iter;
-            mode = fast_iteration<IterT, true>(tab, last, J.n_iterations, c, (round % 8) == 7, L, F.RefIteration, F.iter,
-                                               F.dX.mantissa, F.dX.exp, F.dY.mantissa, F.dY.exp, fsteps);
+            mode = fast_round<IterT, true>(tab, last, J.n_iterations, c, L, F.RefIteration, F.iter, F.dX.mantissa, F.dX.exp,
+                                           F.dY.mantissa, F.dY.exp, fsteps);
             st.fast_steps += fsteps;
             bool alive = true;
             for (unsigned long long i = 0; i < fsteps && alive; i++) alive = perturb_step(J, S);
@@ -59,7 +59,7 @@ IterT lockstep_pixel(const Lav2Job<IterT> &J, const fs::scaled::FastElem *tab, i
             if (fsteps) st.chunks_ok++; else if (F.iter == iter_before && mode == kSlow) st.chunks_rejected++;
             // compare by value: the scaled state (w * 2^k) against the shadow
             float fxm, fym; int fxe, fye;
-            leave(L.sc, L.wx, L.wy, fxm, fxe, fym, fye);
+            leave(L, fxm, fxe, fym, fye);
             HF ax = S.dX, ay = S.dY;
             Reduce(ax); Reduce(ay);
             if (!(ax.mantissa == fxm && ax.exp == fxe && ay.mantissa == fym && ay.exp == fye &&
@@ -101,7 +101,7 @@ uint64_t lockstep_render_lav2(int mode, const void *orbit, uint64_t count, const
     J.out = (IterT *)out;
     std::vector<fs::scaled::FastElem> tab(count);
     for (uint64_t n = 0; n < count; n++)
-        tab[n] = fs::scaled::make_fast_elem(J.orbit[n].xm, J.orbit[n].xe, J.orbit[n].ym, J.orbit[n].ye, n + 1 >= count);
+        tab[n] = fs::scaled::make_fast_elem(J.orbit[n].xm, J.orbit[n].xe, J.orbit[n].ym, J.orbit[n].ye, n, n + 1 >= count);
     std::mutex mu;
     LockStats total;
     if (col_step < 1) col_step = 1;
