@@ -113,7 +113,7 @@ def run_reference_arm(args, rank, world):
     value = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pixel-iters/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32 (HDRx32)",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32 (HDRx32)",
             "data": "synthetic (View #5 preset coordinates, orbit + LA table generated in-process)",
             "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": value, "unit": "pixel-iters/s", "cores": threads, "kind": "port", "sample": sample},
