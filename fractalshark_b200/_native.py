@@ -94,6 +94,13 @@ HOST_SYMBOLS = {
     "fsh_la_stage_count": (_U64, [_V]),
     "fsh_la_use_at": (_I32, [_V]),
     "fsh_la_is_valid": (_I32, [_V]),
+    "fsh_blas_build": (_V, [_V]),
+    "fsh_blas_destroy": (None, [_V]),
+    "fsh_blas_num_levels": (_U32, [_V]),
+    "fsh_blas_lm2": (_I32, [_V]),
+    "fsh_blas_elem_bytes": (_U64, [_V]),
+    "fsh_blas_levels": (C.POINTER(C.c_void_p), [_V]),
+    "fsh_blas_level_counts": (C.POINTER(C.c_uint64), [_V]),
 }
 
 

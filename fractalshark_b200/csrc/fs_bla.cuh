@@ -1,0 +1,268 @@
+// fs_bla.cuh -- perturbation + bilinear-approximation (BLA) render kernels (row a4 of SURVEY.md section 8).
+//
+// Algorithm (what): FractalSharkGpuLib/BLAKernels.cuh:193-434 (float+exponent types: one perturbation step,
+// then as many BLA skips as the table allows) and :17-168 (plain FP64: BLA skips first, then one step);
+// table lookup per FractalSharkGpuLib/BLA.cuh:202-268 (`LookupBackwards`), skip evaluation per BLA.cuh:21-38.
+//
+// Execution (how, B200-first): the same persistent warp-tile queue as the LAv2 kernel (fs_lav2.cuh).  The
+// reference's per-level arrays of 44/48/88-byte records are repacked on the device right after the upload
+// into two 16-byte-aligned arrays per table -- `BlaHead {r2, l}` (16 B: what the descending validity walk
+// reads, one LDG.128 per level probed) and `BlaCoef {A, B}` (32/64 B, read only for an accepted skip) --
+// with the level offsets in the kernel's constant bank instead of a shared-memory pointer table filled
+// behind a CTA barrier (BLAKernels.cuh:230-247).
+#pragma once
+#include "fs_lav2.cuh"
+
+namespace fs {
+
+// reference wire record BLA<T> (BLA.h:7-14); natural alignment reproduces 44 / 88 / 48 / 24 bytes
+template <class Num> struct BlaWire {
+    typename Num::Real r2, Ax, Ay, Bx, By;
+    int32_t l;
+};
+static_assert(sizeof(BlaWire<NumHdr<float>>) == 44 && sizeof(BlaWire<NumHdr<double>>) == 88, "BLA<HDRFloat>");
+static_assert(sizeof(BlaWire<NumPlain<double>>) == 48 && sizeof(BlaWire<NumPlain<float>>) == 24, "BLA<plain>");
+
+template <class Num> struct alignas(16) BlaHead {
+    typename Num::Real r2;
+    int32_t l;
+};
+template <class Num> struct alignas(16) BlaCoef {
+    typename Num::Real Ax, Ay, Bx, By;
+};
+static_assert(sizeof(BlaHead<NumHdr<float>>) == 16 && sizeof(BlaHead<NumHdr<double>>) == 32 &&
+              sizeof(BlaHead<NumPlain<double>>) == 16, "BlaHead");
+static_assert(sizeof(BlaCoef<NumHdr<float>>) == 32 && sizeof(BlaCoef<NumHdr<double>>) == 64 &&
+              sizeof(BlaCoef<NumPlain<double>>) == 32, "BlaCoef");
+
+constexpr int kBlaMaxLevels = 34; // LM2 <= 30 in the reference (BLA.cuh:288-386) => at most 32 levels
+
+template <class Num, class IterT> struct BlaArgs {
+    IterT *out;
+    const void *orbit;
+    IterT orbit_count;
+    const BlaHead<Num> *heads; // all levels concatenated
+    const BlaCoef<Num> *coefs;
+    unsigned long long level_off[kBlaMaxLevels]; // element offset of each level in heads/coefs
+    int lm2;                                     // BLAS::m_LM2
+    int width, height, pitch;
+    int shard_count, shard_index;
+    typename Num::Real dx, dy, centerX, centerY;
+    IterT n_iterations;
+    unsigned int *tile_counter;
+    unsigned long long *step_counter;
+};
+
+// 16-byte vector loads of an aligned record
+template <class T> FS_D T ldg_rec(const T *p) {
+    static_assert(sizeof(T) % 16 == 0, "record size");
+    union U {
+        T t;
+        uint4 v[sizeof(T) / 16];
+        FS_D U() {}
+    } u;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) u.v[i] = __ldg(q + i);
+    return u.t;
+}
+
+// device-side repack of one level: wire records -> heads + coefs
+template <class Num>
+__global__ void __launch_bounds__(256) bla_repack_kernel(const BlaWire<Num> *__restrict__ src, unsigned long long count,
+                                                         BlaHead<Num> *__restrict__ heads, BlaCoef<Num> *__restrict__ coefs) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const BlaWire<Num> w = src[i];
+        BlaHead<Num> h;
+        h.r2 = w.r2; h.l = w.l;
+        BlaCoef<Num> c;
+        c.Ax = w.Ax; c.Ay = w.Ay; c.Bx = w.Bx; c.By = w.By;
+        heads[i] = h;
+        coefs[i] = c;
+    }
+}
+
+// LookupBackwards  BLA.cuh:202-268.  Returns the flat record index and its skip length, or false.
+// `zeros` is computed from the low 32 bits of m - 1 for both iteration widths, as `__clz(__brev(k))` does there.
+template <class Num, class IterT>
+FS_D bool bla_lookup(const BlaArgs<Num, IterT> &A, IterT m, typename Num::Real z2, unsigned long long &rec, int &l) {
+    const IterT k = m - 1;
+    const int zeros = __clz((int)__brev((unsigned int)k));
+    IterT ix = (sizeof(IterT) == 4 && zeros >= 32) ? (IterT)0 : (IterT)(k >> zeros);
+    int level = A.lm2 == 0 ? 0 : (zeros < A.lm2 ? zeros : A.lm2);
+    for (; level >= 2; --level) {
+        const unsigned long long at = A.level_off[level] + (unsigned long long)ix;
+        const BlaHead<Num> h = ldg_rec(A.heads + at);
+        if (lt_pr(z2, h.r2)) {
+            rec = at;
+            l = h.l;
+            return true;
+        }
+        ix = ix << 1;
+    }
+    return false;
+}
+
+// BLA<T>::getValue  BLA.cuh:21-38, float+exponent operators (products rounded, sums aligned with one FMA each)
+template <class M>
+FS_D void bla_get_value(const BlaCoef<NumHdr<M>> &b, Hdr<M> &dx, Hdr<M> &dy, Hdr<M> cx, Hdr<M> cy) {
+    const Hdr<M> nx = sub(add(sub(mul(b.Ax, dx), mul(b.Ay, dy)), mul(b.Bx, cx)), mul(b.By, cy));
+    const Hdr<M> ny = add(add(add(mul(b.Ax, dy), mul(b.Ay, dx)), mul(b.Bx, cy)), mul(b.By, cx));
+    dx = nx;
+    dy = ny;
+}
+// plain FP64, contraction as nvcc emitted it for the reference (sm_100a SASS of mandel_1x_double_perturb_bla):
+//   t1 = dx*Ay ; t2 = dy*Ay ; t1 = fma(dy,Ax,t1) ; t2 = fma(dx,Ax,-t2) ; t1 = fma(cy,Bx,t1) ; t2 = fma(cx,Bx,t2)
+//   ny = fma(cx,By,t1) ; nx = fma(-cy,By,t2)
+template <class M> FS_D void bla_get_value(const BlaCoef<NumPlain<M>> &b, M &dx, M &dy, M cx, M cy) {
+    M t1 = dx * b.Ay;
+    M t2 = dy * b.Ay;
+    t1 = fma_(dy, b.Ax, t1);
+    t2 = fma_(dx, b.Ax, -t2);
+    t1 = fma_(cy, b.Bx, t1);
+    t2 = fma_(cx, b.Bx, t2);
+    dy = fma_(cx, b.By, t1);
+    dx = fma_(-cy, b.By, t2);
+}
+
+// ---- one pixel, float+exponent types: mandel_1xHDR_float_perturb_bla  BLAKernels.cuh:193-434 ----------------
+template <class Num, class IterT, bool Count>
+FS_D IterT bla_pixel_hdr(const BlaArgs<Num, IterT> &A, int X, int Y, unsigned long long &steps) {
+    using Real = typename Num::Real;
+    IterT iter = 0, Ref = 0;
+    const Real cX = Num::delta_x(A.dx, X, A.centerX);
+    const Real cY = Num::delta_y(A.dy, Y, A.centerY);
+    Real dX = Num::zero(), dY = Num::zero(), dn = Num::zero();
+    const IterT count = A.orbit_count;
+
+    while (iter < A.n_iterations) {
+        Real zx, zy;
+        OrbitIO<Num>::load(A.orbit, Ref, zx, zy);
+        ++Ref;
+        Num::perturb(dX, dY, zx, zy, cX, cY);
+        OrbitIO<Num>::load(A.orbit, Ref, zx, zy);
+        const Real tX = add(zx, dX), tY = add(zy, dY);
+        const Real n2 = reduced(add(mul(tX, tX), mul(tY, tY))); // operator*, not square(): BLAKernels.cuh:339
+        if (Count) steps++;
+        if (lt_bailout(n2) && iter < A.n_iterations) {
+            dn = reduced(add(mul(dX, dX), mul(dY, dY)));
+            if (lt_pr(n2, dn) || Ref >= count - 1) {
+                dX = tX; dY = tY; dn = n2; Ref = 0;
+            }
+            ++iter;
+        } else {
+            break;
+        }
+        for (;;) {
+            unsigned long long rec;
+            int l;
+            if (!bla_lookup<Num, IterT>(A, Ref, dn, rec, l)) break;
+            const bool res1 = Ref + (IterT)l >= count;
+            const bool res2 = iter + (IterT)l >= A.n_iterations;
+            const bool res3 = Ref + (IterT)l < count - 1;
+            if (res1 || res2) break;
+            iter += (IterT)l;
+            Ref += (IterT)l;
+            const BlaCoef<Num> b = ldg_rec(A.coefs + rec);
+            bla_get_value(b, dX, dY, cX, cY);
+            if (Count) steps++;
+            if (res3) {
+                dn = reduced(add(mul(dX, dX), mul(dY, dY)));
+                continue;
+            }
+            // landed on the last orbit element: rebase (BLAKernels.cuh:395-426); the norm kept for the next
+            // lookup is that of the ORBIT point (square_mutable: clamped exponent), as written there
+            OrbitIO<Num>::load(A.orbit, Ref, zx, zy);
+            dX = add(zx, dX);
+            dY = add(zy, dY);
+            dn = reduced(add(mul(zx, zx), mul(zy, zy)));
+            Ref = 0;
+            break;
+        }
+    }
+    return iter;
+}
+
+// ---- one pixel, plain FP64: mandel_1x_double_perturb_bla  BLAKernels.cuh:17-168 ------------------------------
+template <class Num, class IterT, bool Count>
+FS_D IterT bla_pixel_plain(const BlaArgs<Num, IterT> &A, int X, int Y, unsigned long long &steps) {
+    using Real = typename Num::Real;
+    IterT iter = 0, Ref = 0;
+    const Real cX = Num::delta_x(A.dx, X, A.centerX);
+    const Real cY = Num::delta_y(A.dy, Y, A.centerY);
+    Real dX = 0, dY = 0, dn = 0;
+    const IterT count = A.orbit_count;
+
+    while (iter < A.n_iterations) {
+        Real zx, zy;
+        bool escaped = false;
+        for (;;) {
+            unsigned long long rec;
+            int l;
+            if (!bla_lookup<Num, IterT>(A, Ref, dn, rec, l)) break;
+            if (Ref + (IterT)l >= count) break;
+            if (iter + (IterT)l >= A.n_iterations) break;
+            iter += (IterT)l;
+            Ref += (IterT)l;
+            const BlaCoef<Num> b = ldg_rec(A.coefs + rec);
+            bla_get_value(b, dX, dY, cX, cY);
+            if (Count) steps++;
+            OrbitIO<Num>::load(A.orbit, Ref, zx, zy);
+            const Real tY = dY + zy, tX = dX + zx;
+            const Real n2 = Num::norm2(tX, tY);
+            dn = Num::norm2(dX, dY);
+            if (n2 > Real(256)) { escaped = true; break; }
+            if (n2 < dn || Ref >= count - 1) {
+                dX = tX; dY = tY; dn = n2; Ref = 0;
+            }
+        }
+        (void)escaped; // the reference falls through to one more plain step either way (BLAKernels.cuh:121-166)
+        if (iter >= A.n_iterations) break;
+
+        OrbitIO<Num>::load(A.orbit, Ref, zx, zy);
+        Num::perturb(dX, dY, zx, zy, cX, cY);
+        ++Ref;
+        OrbitIO<Num>::load(A.orbit, Ref, zx, zy);
+        const Real tY = dY + zy, tX = dX + zx;
+        const Real n2 = Num::norm2(tX, tY);
+        dn = Num::norm2(dX, dY);
+        if (Count) steps++;
+        if (n2 > Real(256)) break;
+        if (n2 < dn || Ref >= count - 1) {
+            dX = tX; dY = tY; dn = n2; Ref = 0;
+        }
+        ++iter;
+    }
+    return iter;
+}
+
+template <class Num, class IterT, bool Count>
+__global__ void __launch_bounds__(256) bla_kernel(const BlaArgs<Num, IterT> A) {
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = (A.width + 7) >> 3;
+    const int tiles_y = (((A.height + 3) >> 2) - A.shard_index + A.shard_count - 1) / A.shard_count;
+    const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    unsigned long long steps = 0;
+    for (;;) {
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(A.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const int X = (int)(tile % tiles_x) * 8 + (lane & 7);
+        const int Y = ((int)(tile / tiles_x) * A.shard_count + A.shard_index) * 4 + (lane >> 3);
+        if (X < A.width && Y < A.height) {
+            IterT iter;
+            if constexpr (Num::kHdr) iter = bla_pixel_hdr<Num, IterT, Count>(A, X, Y, steps);
+            else iter = bla_pixel_plain<Num, IterT, Count>(A, X, Y, steps);
+            A.out[(size_t)Y * A.pitch + X] = iter;
+        }
+        __syncwarp();
+    }
+    if (Count && A.step_counter) {
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if (lane == 0 && steps) atomicAdd(A.step_counter, steps);
+    }
+}
+
+} // namespace fs

@@ -15,6 +15,7 @@
 #include <new>
 #include <vector>
 
+#include "fs_bla.cuh"
 #include "fs_direct.cuh"
 #include "fs_lav2.cuh"
 #include "fs_post.cuh"
@@ -92,6 +93,8 @@ struct fs_renderer {
     bool count_steps = false;
     bool use_scaled = true; // HDRx32: scaled plain-float chunks (fs_scaled_loop.cuh); off = pure float+exponent loop
     OrbitDev orbit1, orbit2;
+    OrbitDev bla_orbit;                  // RenderPerturbBLA uploads its orbit and table per call (GPU_Render.cu:1462-1483)
+    DeviceBlob bla_raw, bla_heads, bla_coefs;
     LaDev la;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
@@ -116,6 +119,12 @@ void free_blob(fs_renderer *r, DeviceBlob &b) {
 }
 
 void reset_perturb(fs_renderer *r) {
+    free_blob(r, r->bla_orbit.data);
+    free_blob(r, r->bla_orbit.fast);
+    r->bla_orbit = OrbitDev{};
+    free_blob(r, r->bla_raw);
+    free_blob(r, r->bla_heads);
+    free_blob(r, r->bla_coefs);
     free_blob(r, r->orbit1.data);
     free_blob(r, r->orbit2.data);
     free_blob(r, r->orbit1.fast);
@@ -169,9 +178,13 @@ uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, u
     free_blob(r, dst.fast);
     dst = OrbitDev{};
     const size_t bytes = eb * src->compressed_count;
-    cudaError_t err = cudaMallocAsync(&dst.data.ptr, bytes ? bytes : 16, r->compute);
+    // one zeroed element of padding: the reference's FP64 BLA kernel can read one element past the end after an
+    // escaping skip (BLAKernels.cuh:128-134, its own TODO); the value there does not reach the output
+    cudaError_t err = cudaMallocAsync(&dst.data.ptr, bytes + 64, r->compute);
     if (err != cudaSuccess) return err;
     dst.data.bytes = bytes;
+    err = cudaMemsetAsync(static_cast<char *>(dst.data.ptr) + bytes, 0, 64, r->compute);
+    if (err != cudaSuccess) return err;
     err = cudaMemcpyAsync(dst.data.ptr, src->elements, bytes, cudaMemcpyDefault, r->compute);
     if (err != cudaSuccess) return err;
     if (numeric == FS_NUM_HDR32 && pextras == FS_PEXTRAS_DISABLE && src->compressed_count > 1 &&
@@ -342,6 +355,69 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     default: return FS_ERROR_UNSUPPORTED;
     }
 #undef FS_LAUNCH_LAV2
+    return end_render(r);
+}
+
+// GPU_BLAS upload (BLA.cuh:123-160) + launch (GPU_Render.cu:1462-1570).  The wire records are copied level by
+// level into one device buffer and repacked there into the aligned head/coefficient arrays of fs_bla.cuh.
+template <class Num, class IterT>
+uint32_t launch_bla(fs_renderer *r, const fs_blas *blas, const void *dx, const void *dy, const void *cx, const void *cy,
+                    uint64_t n_iter) {
+    using Real = typename Num::Real;
+    using Wire = BlaWire<Num>;
+    if (blas->num_levels > (uint32_t)kBlaMaxLevels || blas->lm2 < 0 || blas->lm2 > 30) return FS_ERROR_UNSUPPORTED;
+    BlaArgs<Num, IterT> A;
+    memset(&A, 0, sizeof(A));
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < blas->num_levels; i++) {
+        A.level_off[i] = total;
+        if (blas->levels[i]) total += blas->level_counts[i];
+    }
+    free_blob(r, r->bla_raw);
+    free_blob(r, r->bla_heads);
+    free_blob(r, r->bla_coefs);
+    const uint64_t alloc_n = total ? total : 1;
+    cudaError_t err = cudaMallocAsync(&r->bla_raw.ptr, alloc_n * sizeof(Wire), r->compute);
+    if (err != cudaSuccess) return err;
+    err = cudaMallocAsync(&r->bla_heads.ptr, alloc_n * sizeof(BlaHead<Num>), r->compute);
+    if (err != cudaSuccess) return err;
+    err = cudaMallocAsync(&r->bla_coefs.ptr, alloc_n * sizeof(BlaCoef<Num>), r->compute);
+    if (err != cudaSuccess) return err;
+    for (uint32_t i = 0; i < blas->num_levels; i++) {
+        if (!blas->levels[i] || !blas->level_counts[i]) continue;
+        err = cudaMemcpyAsync(static_cast<Wire *>(r->bla_raw.ptr) + A.level_off[i], blas->levels[i],
+                              blas->level_counts[i] * sizeof(Wire), cudaMemcpyDefault, r->compute);
+        if (err != cudaSuccess) return err;
+    }
+    if (total) {
+        const uint64_t want = (total + 255) / 256;
+        const unsigned grid = (unsigned)(want < (uint64_t)r->num_sms * 8 ? want : (uint64_t)r->num_sms * 8);
+        bla_repack_kernel<Num><<<grid, 256, 0, r->compute>>>(static_cast<const Wire *>(r->bla_raw.ptr), total,
+                                                            static_cast<BlaHead<Num> *>(r->bla_heads.ptr),
+                                                            static_cast<BlaCoef<Num> *>(r->bla_coefs.ptr));
+        r->launches++;
+    }
+    A.out = static_cast<IterT *>(r->iter_buf);
+    A.orbit = r->bla_orbit.data.ptr;
+    A.orbit_count = (IterT)r->bla_orbit.uncompressed;
+    A.heads = static_cast<const BlaHead<Num> *>(r->bla_heads.ptr);
+    A.coefs = static_cast<const BlaCoef<Num> *>(r->bla_coefs.ptr);
+    A.lm2 = blas->lm2;
+    A.width = (int)r->width;
+    A.height = (int)r->height;
+    A.pitch = (int)(r->w_block * NB_THREADS_W);
+    A.shard_count = (int)r->shard_count;
+    A.shard_index = (int)r->shard_index;
+    A.dx = load_pod<Real>(dx);
+    A.dy = load_pod<Real>(dy);
+    A.centerX = load_pod<Real>(cx);
+    A.centerY = load_pod<Real>(cy);
+    A.n_iterations = (IterT)n_iter;
+    A.tile_counter = r->tile_counter;
+    A.step_counter = r->count_steps ? r->step_counter : nullptr;
+    begin_render(r);
+    if (r->count_steps) { auto k = bla_kernel<Num, IterT, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
+    else { auto k = bla_kernel<Num, IterT, false>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
     return end_render(r);
 }
 
@@ -591,10 +667,20 @@ uint32_t fs_render_perturb_bla(fs_renderer *r, uint32_t algorithm, int32_t numer
                                const fs_blas *blas, const void *cx, const void *cy, const void *dx, const void *dy,
                                const void *center_x, const void *center_y, uint64_t n_iterations,
                                int32_t iteration_precision) {
-    (void)algorithm; (void)numeric; (void)results; (void)blas; (void)cx; (void)cy; (void)dx; (void)dy;
-    (void)center_x; (void)center_y; (void)n_iterations; (void)iteration_precision;
-    if (!r || !memory_initialized(r)) return 0;
-    return FS_ERROR_UNSUPPORTED;
+    (void)algorithm; (void)cx; (void)cy; (void)iteration_precision;
+    if (!r || !memory_initialized(r)) return 0; // GPU_Render.cu:1454-1456
+    if (!results || !blas) return FS_ERROR_6_NO_ORBIT;
+    // the reference instantiates HDRFloat<float>, HDRFloat<double> and double (GPU_Render.cu:1610-1692)
+    if (numeric != FS_NUM_HDR32 && numeric != FS_NUM_HDR64 && numeric != FS_NUM_F64) return FS_ERROR_UNSUPPORTED;
+    DeviceGuard g(r->device);
+    const bool saved_scaled = r->use_scaled;
+    r->use_scaled = false; // no plain-float step table for this kernel
+    const uint32_t rc = upload_orbit(r, r->bla_orbit, numeric, FS_PEXTRAS_DISABLE, 0, results);
+    r->use_scaled = saved_scaled;
+    if (rc) return rc;
+    return dispatch_num_iter(numeric, r->iter_bytes, [&](auto num, auto it) -> uint32_t {
+        return launch_bla<decltype(num), decltype(it)>(r, blas, dx, dy, center_x, center_y, n_iterations);
+    });
 }
 
 uint32_t fs_render_perturb_bla_scaled(fs_renderer *r, uint32_t algorithm, int32_t numeric,

@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
         IterT iter = 0;
         IterT RefIteration = 0;
         // LAKernel.cuh:41-42 (no reduction of the deltas here)
-        const Real dcX = sub(mul(A.dx, Num::from_int(X)), A.centerX);
-        const Real dcY = sub(mul(Num::neg(A.dy), Num::from_int(Y)), A.centerY);
+        const Real dcX = Num::delta_x(A.dx, X, A.centerX);
+        const Real dcY = Num::delta_y(A.dy, Y, A.centerY);
         const Cplx dc = Num::c_make(dcX, dcY);
         Cplx dz = Num::c_zero();
 

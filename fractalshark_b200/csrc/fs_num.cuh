@@ -59,6 +59,10 @@ template <class M> struct NumPlain {
     }
     // |z|^2 = fma(x, x, y*y)
     FS_HD static Real norm2(Real x, Real y) { return fma_(x, x, y * y); }
+    // pixel deltas `dx * T(X) - centerX` / `-dy * T(Y) - centerY` (LAKernel.cuh:41-42, BLAKernels.cuh:61-62):
+    // nvcc contracts them for the plain types (reference SASS: DFMA X, dx, -centerX ; DFMA Y, -dy, -centerY)
+    FS_HD static Real delta_x(Real dx, int X, Real centerX) { return fma_((M)X, dx, -centerX); }
+    FS_HD static Real delta_y(Real dy, int Y, Real centerY) { return fma_((M)Y, -dy, -centerY); }
 };
 
 template <class M> struct NumHdr {
@@ -78,6 +82,13 @@ template <class M> struct NumHdr {
 
     // custom_perturb2  HDRFloat.h:725-794 : products aligned with exact 2^-|diff| (0 once
     // |diff| >= 127 / 1023, no 120-gap shortcut), two FMAs per component, then Reduce.
+    // The reference calls the single-precision `__fmaf_rn` for every mantissa type, so with a double mantissa
+    // its operands are rounded to binary32 first (reference SASS: DMUL products, F2F.F32.F64, FFMA): the
+    // HDRx64 perturbation step carries binary32 precision.  Reproduced, not fixed.
+    FS_HD static M fmaf_as_ref(M a, M b, M c) {
+        if constexpr (sizeof(M) == 8) return (M)fma_((float)a, (float)b, (float)c);
+        else return fma_(a, b, c);
+    }
     template <bool Minus>
     FS_HD static Real fused3(M p1, int e1, M p2, int e2, Real c) {
         const int diff = e1 - e2;
@@ -85,13 +96,13 @@ template <class M> struct NumHdr {
         const M mulv = MT<M>::pow2neg(-iabs(diff));
         const M q2 = Minus ? MT<M>::neg(p2) : p2;
         const bool ge = diff >= 0;
-        const M sum = fma_(ge ? q2 : p1, mulv, ge ? p1 : q2);
+        const M sum = fmaf_as_ref(ge ? q2 : p1, mulv, ge ? p1 : q2);
         const int diff2 = maxe - c.e;
         const M mul2v = MT<M>::pow2neg(-iabs(diff2));
         const bool ge2 = diff2 >= 0;
         Real r;
         r.e = imax(maxe, c.e);
-        r.m = fma_(ge2 ? c.m : sum, mul2v, ge2 ? sum : c.m);
+        r.m = fmaf_as_ref(ge2 ? c.m : sum, mul2v, ge2 ? sum : c.m);
         reduce(r);
         return r;
     }
@@ -105,6 +116,9 @@ template <class M> struct NumHdr {
     }
     // HdrReduce(x.square() + y.square())  LAKernel.cuh:206-208
     FS_HD static Real norm2(Real x, Real y) { return reduced(add(square(x), square(y))); }
+    // pixel deltas (LAKernel.cuh:41-42): HDR operators, not reduced
+    FS_HD static Real delta_x(Real dx, int X, Real centerX) { return sub(mul(dx, from_int(X)), centerX); }
+    FS_HD static Real delta_y(Real dy, int Y, Real centerY) { return sub(mul(neg(dy), from_int(Y)), centerY); }
 };
 
 } // namespace fs

@@ -192,6 +192,14 @@ struct fsh_orbit {
     unsigned char x_low[16] = {0}, y_low[16] = {0};
 };
 
+struct fsh_blas {
+    std::vector<std::vector<unsigned char>> levels;
+    std::vector<uint64_t> counts;
+    std::vector<const void *> ptrs;
+    size_t elem_bytes = 0;
+    int32_t lm2 = 0;
+};
+
 struct fsh_la {
     std::vector<unsigned char> las, stages, at;
     uint64_t num_las = 0, num_stages = 0, stage_count = 0;
@@ -710,6 +718,170 @@ template <class N, class IterT> fsh_la *build_la(const fsh_orbit *o) {
     return r;
 }
 
+// --------------------------------------------------------------------------------------------
+// BLA table construction (BLAS::Init  BLAS.cpp:212-254; leaves :74-92; merge :25-47 + BLA.cuh:61-88;
+// level fill :96-143; pairwise merge upwards :145-210).  Level l, entry i covers orbit steps
+// [i*2^l + 1, (i+1)*2^l]; levels 0 and 1 are never stored (m_FirstLevel = 2).
+// --------------------------------------------------------------------------------------------
+template <class N> struct WireBLA { // BLA.h:7-14
+    typename N::Real r2, Ax, Ay, Bx, By;
+    int32_t l;
+};
+static_assert(sizeof(WireBLA<HostHdr<float>>) == 44 && sizeof(WireBLA<HostHdr<double>>) == 88, "BLA<HDRFloat>");
+static_assert(sizeof(WireBLA<HostPlain<double>>) == 48 && sizeof(WireBLA<HostPlain<float>>) == 24, "BLA<plain>");
+
+template <class N> struct BlaOps;
+template <class M> struct BlaOps<HostHdr<M>> {
+    using Real = Hdr<M>;
+    static Real mul_(Real a, Real b) { return mul(a, b); }
+    static Real add_(Real a, Real b) { return add(a, b); }
+    static Real sub_(Real a, Real b) { return sub(a, b); }
+    static Real div_(Real a, Real b) { return div(a, b); }
+    static void red(Real &a) { reduce(a); }
+    static Real one() { return h_from_int<M>(1); }
+    static Real zero() { return hdr_zero<M>(); }
+    static Real eps() { return div(h_from_int<M>(1), h_from_mant<M>((M)(1L << 23))); } // T(1) / T{1L << BLA_BITS}
+    // HdrSqrt  HDRFloat.h:1358-1383 (result not reduced)
+    static Real sqrt_(Real a) {
+        const bool odd = (a.e & 1) != 0;
+        Real r;
+        r.e = odd ? (a.e - 1) / 2 : a.e / 2;
+        r.m = (M)::sqrt(odd ? M(2) * a.m : a.m);
+        return r;
+    }
+    // HDRFloat::compareTo  HDRFloat.h:1207-1247
+    static int compare_to(Real a, Real b) {
+        if (a.m == 0 && b.m == 0) return 0;
+        if (a.m > 0) {
+            if (b.m <= 0) return 1;
+            if (a.e > b.e) return 1;
+            if (a.e < b.e) return -1;
+            return a.m > b.m ? 1 : (a.m < b.m ? -1 : 0);
+        }
+        if (b.m > 0) return -1;
+        if (a.e > b.e) return -1;
+        if (a.e < b.e) return 1;
+        return a.m > b.m ? 1 : (a.m < b.m ? -1 : 0);
+    }
+    static Real max_reduced(Real a, Real b) { return compare_to(a, b) > 0 ? a : b; }       // HdrMaxReduced :1477-1494
+    static Real min_pos_reduced(Real a, Real b) { return cmp_pr(a, b) < 0 ? a : b; }       // HdrMinPositiveReduced :1518-1535
+    // 2 * orbit point as (RealA, ImagA): HDRFloatComplex{x, y}.getRe() * 2 (BLAS.cpp:76-78, HDRFloatComplex.h:158-173)
+    static void leaf_a(Real x, Real y, Real &ra, Real &ia) {
+        const HdrC<M> c = hc_from<M>(x, y);
+        ra = mul(hc_re(c), h_from_mant<M>(M(2)));
+        ia = mul(hc_im(c), h_from_mant<M>(M(2)));
+    }
+};
+template <class M> struct BlaOps<HostPlain<M>> {
+    using Real = M;
+    static Real mul_(Real a, Real b) { return a * b; }
+    static Real add_(Real a, Real b) { return a + b; }
+    static Real sub_(Real a, Real b) { return a - b; }
+    static Real div_(Real a, Real b) { return a / b; }
+    static void red(Real &) {}
+    static Real one() { return M(1); }
+    static Real zero() { return M(0); }
+    static Real eps() { return M(1) / M(1L << 23); }
+    static Real sqrt_(Real a) { return (M)::sqrt(a); }
+    static Real max_reduced(Real a, Real b) { return a > b ? a : b; }
+    static Real min_pos_reduced(Real a, Real b) { return a < b ? a : b; }
+    static void leaf_a(Real x, Real y, Real &ra, Real &ia) { ra = x * 2; ia = y * 2; }
+};
+
+template <class N> struct BlaBuilder {
+    using O = BlaOps<N>;
+    using Real = typename N::Real;
+    using Rec = WireBLA<N>;
+    const fsh_orbit *orbit = nullptr;
+    Real bla_size{};
+    std::vector<size_t> per_level;
+    std::vector<std::vector<Rec>> B;
+    int32_t lm2 = 0;
+
+    Rec one_step(size_t m) const { // CreateOneStep  BLAS.cpp:74-92
+        Real x, y, ra, ia;
+        ElemIO<N>::get(orbit->data.data() + m * orbit->elem_bytes, x, y);
+        O::leaf_a(x, y, ra, ia);
+        const Real mA = O::sqrt_(O::add_(O::mul_(ra, ra), O::mul_(ia, ia)));
+        const Real r = O::mul_(mA, O::eps());
+        Rec b;
+        memset(&b, 0, sizeof(b));
+        b.r2 = O::mul_(r, r);
+        b.Ax = ra; b.Ay = ia; b.Bx = O::one(); b.By = O::zero(); b.l = 1;
+        return b;
+    }
+    static Real hypot_(Real x, Real y) { // hypotA / hypotB  BLA.cuh:40-56
+        Real r = O::sqrt_(O::add_(O::mul_(x, x), O::mul_(y, y)));
+        O::red(r);
+        return r;
+    }
+    Rec merge(const Rec &x, const Rec &y) const { // MergeTwoBlas  BLAS.cpp:25-47
+        Rec b;
+        memset(&b, 0, sizeof(b));
+        b.l = x.l + y.l;
+        // getNewA: A = y.A * x.A   BLA.cuh:66-75
+        b.Ax = O::sub_(O::mul_(y.Ax, x.Ax), O::mul_(y.Ay, x.Ay)); O::red(b.Ax);
+        b.Ay = O::add_(O::mul_(y.Ax, x.Ay), O::mul_(y.Ay, x.Ax)); O::red(b.Ay);
+        // getNewB: B = y.A * x.B + y.B   BLA.cuh:78-88
+        b.Bx = O::add_(O::sub_(O::mul_(y.Ax, x.Bx), O::mul_(y.Ay, x.By)), y.Bx); O::red(b.Bx);
+        b.By = O::add_(O::add_(O::mul_(y.Ax, x.By), O::mul_(y.Ay, x.Bx)), y.By); O::red(b.By);
+        const Real xA = hypot_(x.Ax, x.Ay), xB = hypot_(x.Bx, x.By);
+        Real tempR = O::div_(O::sub_(O::sqrt_(y.r2), O::mul_(xB, bla_size)), xA);
+        O::red(tempR);
+        const Real r = O::min_pos_reduced(O::sqrt_(x.r2), O::max_reduced(O::zero(), tempR));
+        b.r2 = O::mul_(r, r);
+        return b;
+    }
+    Rec l_step(size_t level, size_t m) const { // CreateLStep  BLAS.cpp:49-72
+        if (level == 0) return one_step(m);
+        const size_t m2 = m << 1, mx = m2 - 1, my = m2;
+        if (my <= per_level[level - 1]) return merge(l_step(level - 1, mx), l_step(level - 1, my));
+        return l_step(level - 1, mx);
+    }
+    void build() { // Init  BLAS.cpp:212-254
+        constexpr size_t kFirst = 2;
+        size_t m = (size_t)orbit->count - 1;
+        if (orbit->count == 0 || m == 0) return;
+        for (; m > 1; m = (m + 1) >> 1) per_level.push_back(m);
+        per_level.push_back(m);
+        B.resize(per_level.size());
+        lm2 = (int32_t)per_level.size() - 2;
+        if (lm2 < 0) lm2 = 0;
+        if (kFirst >= per_level.size()) return;
+        for (size_t l = kFirst; l < B.size(); l++) B[l].resize(per_level[l]);
+        for (size_t i = 1; i < per_level[kFirst] + 1; i++) B[kFirst][i - 1] = l_step(kFirst, i);
+        // Merge  BLAS.cpp:160-210
+        size_t src = kFirst;
+        const size_t max_level = per_level.size() - 1;
+        for (size_t n_src = per_level[src]; src < max_level && n_src > 1; src++) {
+            const size_t n_dst = per_level[src + 1];
+            for (size_t i = 0; i < n_dst; i++) {
+                const size_t mx = i << 1, my = mx + 1;
+                B[src + 1][i] = my < n_src ? merge(B[src][mx], B[src][my]) : B[src][mx];
+            }
+            n_src = n_dst;
+        }
+    }
+};
+
+template <class N> fsh_blas *build_blas(const fsh_orbit *o) {
+    BlaBuilder<N> b;
+    b.orbit = o;
+    memcpy(&b.bla_size, o->max_radius, sizeof(b.bla_size));
+    b.build();
+    fsh_blas *r = new fsh_blas();
+    r->elem_bytes = sizeof(WireBLA<N>);
+    r->lm2 = b.lm2;
+    r->levels.resize(b.B.size());
+    for (size_t l = 0; l < b.B.size(); l++) {
+        r->levels[l].resize(b.B[l].size() * sizeof(WireBLA<N>));
+        if (!b.B[l].empty()) memcpy(r->levels[l].data(), b.B[l].data(), r->levels[l].size());
+        r->counts.push_back(b.B[l].size());
+        r->ptrs.push_back(b.B[l].empty() ? nullptr : r->levels[l].data());
+    }
+    return r;
+}
+
 unsigned long pick_precision(const char *a, const char *b) {
     const size_t n = std::max(strlen(a), strlen(b));
     const unsigned long bits = (unsigned long)(n * 3.3219281) + 64;
@@ -839,5 +1011,22 @@ uint64_t fsh_la_at_bytes(const fsh_la *l) { return l->at.size(); }
 uint64_t fsh_la_stage_count(const fsh_la *l) { return l->stage_count; }
 int32_t fsh_la_use_at(const fsh_la *l) { return l->use_at; }
 int32_t fsh_la_is_valid(const fsh_la *l) { return l->is_valid; }
+
+// BLAS<IterType, T>::Init(GetCountOrbitEntries(), GetMaxRadius())  Fractal.cpp:2739-2740
+fsh_blas *fsh_blas_build(const fsh_orbit *o) {
+    switch (o->numeric) {
+    case NUM_F32: return build_blas<HostPlain<float>>(o);
+    case NUM_F64: return build_blas<HostPlain<double>>(o);
+    case NUM_HDR32: return build_blas<HostHdr<float>>(o);
+    case NUM_HDR64: return build_blas<HostHdr<double>>(o);
+    default: return nullptr;
+    }
+}
+void fsh_blas_destroy(fsh_blas *b) { delete b; }
+uint32_t fsh_blas_num_levels(const fsh_blas *b) { return (uint32_t)b->levels.size(); } // m_B.size() (= m_L)
+int32_t fsh_blas_lm2(const fsh_blas *b) { return b->lm2; }
+uint64_t fsh_blas_elem_bytes(const fsh_blas *b) { return b->elem_bytes; }
+const void *const *fsh_blas_levels(const fsh_blas *b) { return b->ptrs.data(); }
+const uint64_t *fsh_blas_level_counts(const fsh_blas *b) { return b->counts.data(); }
 
 } // extern "C"

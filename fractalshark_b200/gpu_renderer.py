@@ -93,6 +93,17 @@ class GPURenderer:
             self._h, int(algorithm), int(t.numeric), int(t.mode), int(t.pextras), _buf(coords["cx"]), _buf(coords["cy"]),
             _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]), _buf(coords["center_y"]), n_iterations))
 
+    def RenderPerturbBLA(self, algorithm: RenderAlgorithm, perturb, blas, coords: dict, n_iterations: int,
+                         iteration_precision: int = 1) -> int:
+        """``perturb`` is a :class:`host_inputs.Orbit`, ``blas`` a :class:`host_inputs.BlaTable`; both are uploaded
+        by this call, as in the reference (GPU_Render.cu:1440-1570)."""
+        t = traits(algorithm)
+        d, b = perturb.descriptor(), blas.descriptor()
+        return int(self._lib.fs_render_perturb_bla(
+            self._h, int(algorithm), int(t.numeric), C.byref(d), C.byref(b), _buf(coords["cx"]), _buf(coords["cy"]),
+            _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]), _buf(coords["center_y"]), n_iterations,
+            iteration_precision))
+
     # ---- results -------------------------------------------------------------------------------
     def buffer_shape(self) -> tuple[int, int]:
         w, h = self.GetWidth(), self.GetHeight()

@@ -129,3 +129,38 @@ class LaTable:
         dt = np.uint32 if self.iter_bytes == 4 else np.uint64
         buf = (C.c_ubyte * (self.num_stages * 2 * self.iter_bytes)).from_address(ptr)
         return np.frombuffer(buf, dtype=dt).reshape(self.num_stages, 2)
+
+
+class BlaTable:
+    """BLA table (``BLAS<IterType, T>::Init(count, MaxRadius)``, BLAS.cpp:212-254) built from an orbit:
+    per-level arrays of ``BLA<T>`` records in the reference layout (BLA.h:7-14)."""
+
+    def __init__(self, orbit: Orbit):
+        self._lib = N.host_lib()
+        self._orbit = orbit
+        self._h = self._lib.fsh_blas_build(orbit._h)
+        if not self._h:
+            raise ValueError("BLA build failed")
+        L = self._lib
+        self.num_levels = int(L.fsh_blas_num_levels(self._h))
+        self.lm2 = int(L.fsh_blas_lm2(self._h))
+        self.elem_bytes = int(L.fsh_blas_elem_bytes(self._h))
+        counts = L.fsh_blas_level_counts(self._h)
+        self.level_counts = [int(counts[i]) for i in range(self.num_levels)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.fsh_blas_destroy(self._h)
+            self._h = None
+
+    def descriptor(self) -> N.FsBlas:
+        L = self._lib
+        return N.FsBlas(L.fsh_blas_levels(self._h), L.fsh_blas_level_counts(self._h), self.num_levels, 2, self.lm2)
+
+    def level_numpy(self, level: int) -> np.ndarray:
+        n = self.level_counts[level]
+        if n == 0:
+            return np.zeros((0, self.elem_bytes), np.uint8)
+        ptr = self._lib.fsh_blas_levels(self._h)[level]
+        buf = (C.c_ubyte * (n * self.elem_bytes)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(n, self.elem_bytes)

@@ -145,6 +145,37 @@ uint32_t render_lav2_t(Harness *h, uint32_t alg, int mode, const void *cx, const
     }
 }
 
+// RenderPerturbBLA reads only BLAS::m_B and BLAS::m_LM2 (GPU_Render.cu:1478-1483, BLA.cuh:288-386): a BLAS object is
+// synthesised from the flat per-level tables without running its constructor (which needs PerturbationResults).
+template <typename IterType, class T>
+uint32_t render_bla_t(Harness *h, uint32_t alg, const void *orbit, uint64_t count, uint64_t period,
+                      const void *const *levels, const uint64_t *counts, uint32_t num_levels, int lm2, const void *cx,
+                      const void *cy, const void *dx, const void *dy, const void *cenx, const void *ceny, uint64_t n) {
+    RenderAlgorithm a; *const_cast<RenderAlgorithmEnum *>(&a.Algorithm) = (RenderAlgorithmEnum)alg;
+    GPUPerturbResults<IterType, T, PerturbExtras::Disable> res{
+        (IterType)count, (IterType)count, T{}, T{}, (const GPUReferenceIter<T, PerturbExtras::Disable> *)orbit, (IterType)period};
+    using BL = BLAS<IterType, T>;
+    std::vector<unsigned char> storage(sizeof(BL) + 64, 0);
+    unsigned char *p = storage.data();
+    p += (64 - (reinterpret_cast<uintptr_t>(p) & 63)) & 63;
+    BL *b = reinterpret_cast<BL *>(p);
+    new (&b->m_B) std::vector<std::vector<BLA<T>>>(num_levels);
+    for (uint32_t i = 0; i < num_levels; i++) {
+        if (!levels[i] || !counts[i]) continue;
+        b->m_B[i].resize(counts[i]);
+        memcpy((void *)b->m_B[i].data(), levels[i], counts[i] * sizeof(BLA<T>));
+    }
+    b->m_LM2 = lm2;
+    const T vcx = pod<T>(cx), vcy = pod<T>(cy), vdx = pod<T>(dx), vdy = pod<T>(dy), vx = pod<T>(cenx), vy = pod<T>(ceny);
+    cudaEventRecord(h->ev0, h->renderer.m_ComputeStream);
+    const uint32_t rc = h->renderer.RenderPerturbBLA<IterType, T>(a, &res, b, vcx, vcy, vdx, vdy, vx, vy, (IterType)n, 1);
+    cudaEventRecord(h->ev1, h->renderer.m_ComputeStream);
+    h->renderer.SyncComputeStream();
+    using VV = std::vector<std::vector<BLA<T>>>;
+    b->m_B.~VV();
+    return rc;
+}
+
 template <class F> uint32_t by_type(int numeric, uint32_t iter_bytes, F &&f) {
     const bool u64 = iter_bytes == 8;
     switch (numeric) {
@@ -209,6 +240,26 @@ uint32_t refh_render_lav2(void *p, uint32_t iter_bytes, uint32_t alg, int numeri
     });
     cudaEventRecord(h->ev1, h->renderer.m_ComputeStream);
     return rc;
+}
+
+// GPURenderer::RenderPerturbBLA<IterType,T>; ev0/ev1 bracket the per-call orbit + table upload and the kernel,
+// exactly what the reference's own per-pixel timer sees (Fractal.cpp:2742)
+uint32_t refh_render_bla(void *p, uint32_t iter_bytes, uint32_t alg, int numeric, const void *orbit, uint64_t count,
+                         uint64_t period, const void *const *levels, const uint64_t *counts, uint32_t num_levels, int lm2,
+                         const void *cx, const void *cy, const void *dx, const void *dy, const void *cenx,
+                         const void *ceny, uint64_t n) {
+    Harness *h = (Harness *)p;
+    const bool u64 = iter_bytes == 8;
+#define REFH_BLA(T)                                                                                                    \
+    (u64 ? render_bla_t<uint64_t, T>(h, alg, orbit, count, period, levels, counts, num_levels, lm2, cx, cy, dx, dy, cenx, ceny, n) \
+         : render_bla_t<uint32_t, T>(h, alg, orbit, count, period, levels, counts, num_levels, lm2, cx, cy, dx, dy, cenx, ceny, n))
+    switch (numeric) {
+    case 1: return REFH_BLA(double);
+    case 3: return REFH_BLA(HDRFloat<float>);
+    case 4: return REFH_BLA(HDRFloat<double>);
+    default: return 10100;
+    }
+#undef REFH_BLA
 }
 
 uint32_t refh_render_direct(void *p, uint32_t iter_bytes, uint32_t alg, int numeric, const void *cx, const void *cy,

@@ -28,6 +28,10 @@ def make_inputs(view_id, w, h, alg, n_iter, iter_bytes):
     if t.family == "lav2":
         orbit = Orbit(view, t.numeric, n_iter, True)
         la = LaTable(orbit, iter_bytes)
+    elif t.family == "bla":
+        from fractalshark_b200.host_inputs import BlaTable
+        orbit = Orbit(view, t.numeric, n_iter, True)
+        la = BlaTable(orbit)   # rides in the `la` slot of the case tuple
     return view, coords, orbit, la, n_iter
 
 
@@ -36,12 +40,15 @@ def render(renderer_cls, w, h, alg, coords, orbit, la, n_iter, iter_bytes, want_
     r = renderer_cls()
     rc = r.InitializeMemory(w, h, aa, iter_bytes=iter_bytes)
     assert rc == 0, rc
-    if orbit is not None:
+    fam = traits(alg).family
+    if orbit is not None and fam == "lav2":
         rc = r.InitializePerturb(1, orbit, 0, None, la)
         assert rc == 0, rc
     r.ClearMemory()
-    if traits(alg).family == "lav2":
+    if fam == "lav2":
         rc = r.RenderPerturbLAv2(alg, coords, n_iter)
+    elif fam == "bla":
+        rc = r.RenderPerturbBLA(alg, orbit, la, coords, n_iter)
     else:
         rc = r.Render(alg, coords, n_iter, 1)
     assert rc == 0, rc

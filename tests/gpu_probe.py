@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 from fractalshark_b200 import RenderAlgorithm, Numeric, traits
 from fractalshark_b200.gpu_renderer import GPURenderer
-from fractalshark_b200.host_inputs import View, Orbit, LaTable
+from fractalshark_b200.host_inputs import View, Orbit, LaTable, BlaTable
 from fractalshark_b200.views import PRESETS
 import ref_renderer
 
@@ -30,18 +30,24 @@ def run(view_id, w, h, alg, n_iter=None, iter_bytes=4, with_ref=True):
         t0 = time.time(); orbit = Orbit(v, t.numeric, n_iter, True); t1 = time.time()
         la = LaTable(orbit, iter_bytes) if t.mode != 2 else LaTable(orbit, iter_bytes)
         print(f"  orbit count={orbit.count} period={orbit.period} ({t1-t0:.2f}s) la: n={la.num_las} stages={la.stage_count} at={la.use_at} valid={la.is_valid} ({time.time()-t1:.2f}s)", flush=True)
+    if t.family == "bla":
+        t0 = time.time(); orbit = Orbit(v, t.numeric, n_iter, True); t1 = time.time()
+        la = BlaTable(orbit)
+        print(f"  orbit count={orbit.count} period={orbit.period} ({t1-t0:.2f}s) bla: levels={la.num_levels} lm2={la.lm2} ({time.time()-t1:.2f}s)", flush=True)
     outs = {}
     for name, R in (("new", GPURenderer), ("ref", ref_renderer.RefGPURenderer)):
         if name == "ref" and not with_ref:
             continue
         r = R()
         rc = r.InitializeMemory(w, h, 1, iter_bytes=iter_bytes); assert rc == 0, rc
-        if orbit is not None:
+        if orbit is not None and t.family == "lav2":
             rc = r.InitializePerturb(1, orbit, 0, None, la); assert rc == 0, rc
         for rep in range(2):
             r.ClearMemory()
             if t.family == "lav2":
                 rc = r.RenderPerturbLAv2(alg, coords, n_iter)
+            elif t.family == "bla":
+                rc = r.RenderPerturbBLA(alg, orbit, la, coords, n_iter)
             else:
                 rc = r.Render(alg, coords, n_iter, 1)
             assert rc == 0, rc

@@ -23,6 +23,8 @@ def lib():
         L.orc_render_lav2.argtypes = [I, I, I, V, U64, V, V, V, U64, I, I, I, I, V, V, V, V, U64, V, I, I, I, I, I]
         L.orc_render_direct.restype = U64
         L.orc_render_direct.argtypes = [I, I, I, I, V, V, V, V, U64, I, V, I, I, I]
+        L.orc_render_bla.restype = U64
+        L.orc_render_bla.argtypes = [I, I, V, U64, V, I, I, I, V, V, V, V, U64, V, I, I, I, I, I]
         L.orc_post.restype = None
         L.orc_post.argtypes = [I, V, I, I, I, V, C.c_uint32, C.c_uint32, U64, V, V]
         L.orc_hardware_threads.restype = I
@@ -55,6 +57,22 @@ def render_lav2(alg, w, h, coords, orbit, la, n_iter, iter_bytes=4, rows=None, c
     steps = lib().orc_render_lav2(int(t.numeric), iter_bytes, int(t.mode), d.elements, d.uncompressed_count, *largs,
                                   w, h, _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]),
                                   _buf(coords["center_y"]), n_iter, out.ctypes.data, rb, re, col_step, row_step, threads)
+    if steps == 2 ** 64 - 1:
+        raise NotImplementedError(f"oracle has no restatement for {alg!r}")
+    return out, int(steps)
+
+
+def render_bla(alg, w, h, coords, orbit, blas, n_iter, iter_bytes=4, rows=None, col_step=1, row_step=1, threads=1):
+    """mandel_1xHDR_float_perturb_bla / mandel_1x_double_perturb_bla restated on the CPU."""
+    t = traits(alg)
+    hp, wp = _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)
+    out = np.zeros((hp, wp), dtype=np.uint32 if iter_bytes == 4 else np.uint64)
+    rb, re = rows if rows is not None else (0, h)
+    d, b = orbit.descriptor(), blas.descriptor()
+    steps = lib().orc_render_bla(int(t.numeric), iter_bytes, d.elements, d.uncompressed_count,
+                                 C.cast(b.levels, C.c_void_p), b.lm2, w, h, _buf(coords["dx"]), _buf(coords["dy"]),
+                                 _buf(coords["center_x"]), _buf(coords["center_y"]), n_iter, out.ctypes.data, rb, re,
+                                 col_step, row_step, threads)
     if steps == 2 ** 64 - 1:
         raise NotImplementedError(f"oracle has no restatement for {alg!r}")
     return out, int(steps)
