@@ -14,6 +14,65 @@ SMALL_CASES = [
     ("v19_hdr32_lav2_capped", 19, 64, 36, A.GpuHDRx32PerturbedLAv2, 200000, 4),
 ]
 
+# second fixture file (tests/golden/ref_gpu_small2.npz): BLA kernels and the other numeric variants of LAv2
+SMALL_CASES_2 = [
+    ("v5_hdr32_bla", 5, 96, 54, A.GpuHDRx32PerturbedBLA, None, 4),
+    ("v5_hdr32_bla_u64", 5, 50, 37, A.GpuHDRx32PerturbedBLA, None, 8),
+    ("v1_hdr32_bla", 1, 96, 54, A.GpuHDRx32PerturbedBLA, None, 4),
+    ("v100_hdr32_bla", 100, 96, 54, A.GpuHDRx32PerturbedBLA, None, 4),
+    ("v100_f64_bla", 100, 96, 54, A.Gpu1x64PerturbedBLA, None, 4),
+    ("v1_f64_bla_u64", 1, 50, 37, A.Gpu1x64PerturbedBLA, None, 8),
+    ("v5_hdr64_bla", 5, 64, 36, A.GpuHDRx64PerturbedBLA, None, 4),
+    ("v5_hdr64_lav2", 5, 64, 36, A.GpuHDRx64PerturbedLAv2, None, 4),
+    ("v5_hdr64_lav2_po", 5, 64, 36, A.GpuHDRx64PerturbedLAv2PO, 3000, 4),
+    ("v100_f64_lav2", 100, 96, 54, A.Gpu1x64PerturbedLAv2, None, 4),
+    ("v100_f64_lav2_po", 100, 96, 54, A.Gpu1x64PerturbedLAv2PO, None, 4),
+    ("v1_f64_lav2", 1, 96, 54, A.Gpu1x64PerturbedLAv2, None, 4),
+    ("v101_f32_lav2", 101, 96, 54, A.Gpu1x32PerturbedLAv2, None, 4),
+    ("v100_hdr32_lav2", 100, 96, 54, A.GpuHDRx32PerturbedLAv2, None, 4),
+]
+ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2
+
+
+def golden_file_of(name):
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    which = "ref_gpu_small2.npz" if any(c[0] == name for c in SMALL_CASES_2) else "ref_gpu_small.npz"
+    return os.path.join(here, "golden", which)
+
+
+def inputs_crc(coords, orbit, table):
+    """CRC32 of everything fed to the kernels, stored beside each golden buffer."""
+    import zlib
+    crc = 0
+    for k in sorted(coords):
+        crc = zlib.crc32(coords[k], crc)
+    if orbit is not None:
+        crc = zlib.crc32(orbit.as_numpy().tobytes(), crc)
+    if table is not None and hasattr(table, "num_las") and table.num_las:
+        crc = zlib.crc32(table.las_numpy().tobytes(), crc)
+        crc = zlib.crc32(table.stages_numpy().tobytes(), crc)
+    if table is not None and hasattr(table, "level_counts"):
+        for lv in range(table.num_levels):
+            crc = zlib.crc32(table.level_numpy(lv).tobytes(), crc)
+    return crc
+
+
+def oracle_render(alg, w, h, coords, orbit, table, n, ib, **kw):
+    """CPU oracle for a case, or None when the oracle has no restatement of that variant."""
+    import oracle_cpu
+    from fractalshark_b200 import traits
+    fam = traits(alg).family
+    kw.setdefault("threads", oracle_cpu.hardware_threads())
+    try:
+        if fam == "lav2":
+            return oracle_cpu.render_lav2(alg, w, h, coords, orbit, table, n, iter_bytes=ib, **kw)[0]
+        if fam == "bla":
+            return oracle_cpu.render_bla(alg, w, h, coords, orbit, table, n, iter_bytes=ib, **kw)[0]
+        return oracle_cpu.render_direct(alg, w, h, coords, n, 1, iter_bytes=ib, threads=kw["threads"])[0]
+    except NotImplementedError:
+        return None
+
 
 def make_inputs(view_id, w, h, alg, n_iter, iter_bytes):
     from fractalshark_b200 import traits

@@ -20,21 +20,19 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_gpu_small.npz")
 
 @pytest.fixture(scope="module")
 def golden():
-    return np.load(GOLDEN)
+    return {**np.load(GOLDEN), **np.load(cases.golden_file_of(cases.SMALL_CASES_2[0][0]))}
 
 
-@pytest.mark.parametrize("case", cases.SMALL_CASES, ids=[c[0] for c in cases.SMALL_CASES])
+@pytest.mark.parametrize("case", cases.ALL_SMALL_CASES, ids=[c[0] for c in cases.ALL_SMALL_CASES])
 def test_small_cases_bit_exact_vs_oracle_and_golden(golden, case):
-    """Bit-exact against the CPU oracle and against the committed reference-kernel fixtures."""
+    """Bit-exact against the committed reference-kernel fixtures and (where restated) the CPU oracle."""
     name, view_id, w, h, alg, n_iter, ib = case
     _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
     got, _, red = cases.render(GPURenderer, w, h, alg, coords, orbit, la, n, ib)
     np.testing.assert_array_equal(got[:h, :w], golden[name])
-    if traits(alg).family == "lav2":
-        want, _ = oracle_cpu.render_lav2(alg, w, h, coords, orbit, la, n, iter_bytes=ib, threads=oracle_cpu.hardware_threads())
-    else:
-        want, _ = oracle_cpu.render_direct(alg, w, h, coords, n, 1, iter_bytes=ib, threads=oracle_cpu.hardware_threads())
-    np.testing.assert_array_equal(got[:h, :w], want[:h, :w])
+    want = cases.oracle_render(alg, w, h, coords, orbit, la, n, ib)
+    if want is not None:
+        np.testing.assert_array_equal(got[:h, :w], want[:h, :w])
     assert red["Sum"] == int(got[:h, :w].astype(np.uint64).sum())
     assert red["Min"] == int(got[:h, :w].min()) and red["Max"] == int(got[:h, :w].max())
     # cells outside width x height stay cleared
@@ -48,6 +46,13 @@ FULL_CASES = [
     ("v5_hdr32_lav2_po_full", 5, 1920, 1080, A.GpuHDRx32PerturbedLAv2PO, 20000, 4, 0.999),
     ("v5_hdr32_lav2_u64_full", 5, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None, 8, 0.999),
     ("v1_hdr32_lav2_full", 1, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None, 4, 0.999),
+    ("v5_hdr32_bla_full", 5, 3840, 2160, A.GpuHDRx32PerturbedBLA, None, 4, 0.999),       # BASELINE configs[2]
+    ("v5_hdr64_bla_full", 5, 1920, 1080, A.GpuHDRx64PerturbedBLA, None, 4, 0.999),
+    ("v100_f64_bla_full", 100, 3840, 2160, A.Gpu1x64PerturbedBLA, None, 4, 1.0),          # FP64 perturbation: bit-exact
+    ("v100_f64_lav2_full", 100, 3840, 2160, A.Gpu1x64PerturbedLAv2, None, 4, 1.0),
+    ("v100_f64_lav2_po_full", 100, 1920, 1080, A.Gpu1x64PerturbedLAv2PO, None, 8, 1.0),
+    ("v5_hdr64_lav2_full", 5, 1920, 1080, A.GpuHDRx64PerturbedLAv2, None, 4, 0.999),
+    ("v101_f32_lav2_full", 101, 3840, 2160, A.Gpu1x32PerturbedLAv2, None, 4, 0.999),
 ]
 
 

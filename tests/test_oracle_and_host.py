@@ -19,32 +19,20 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_gpu_small.npz")
 
 @pytest.fixture(scope="module")
 def golden(built):
-    return np.load(GOLDEN)
+    return {**np.load(GOLDEN), **np.load(cases.golden_file_of(cases.SMALL_CASES_2[0][0]))}
 
 
-def _crc(coords, orbit, la):
-    crc = 0
-    for k in sorted(coords):
-        crc = zlib.crc32(coords[k], crc)
-    if orbit is not None:
-        crc = zlib.crc32(orbit.as_numpy().tobytes(), crc)
-    if la is not None and la.num_las:
-        crc = zlib.crc32(la.las_numpy().tobytes(), crc)
-        crc = zlib.crc32(la.stages_numpy().tobytes(), crc)
-    return crc
-
-
-@pytest.mark.parametrize("case", cases.SMALL_CASES, ids=[c[0] for c in cases.SMALL_CASES])
+@pytest.mark.parametrize("case", cases.ALL_SMALL_CASES, ids=[c[0] for c in cases.ALL_SMALL_CASES])
 def test_oracle_matches_reference_gpu_golden(golden, case):
-    """The CPU restatement reproduces, bit for bit, what the reference's own kernels produced on a B200."""
+    """The CPU restatement reproduces, bit for bit, what the reference's own kernels produced on a B200.
+    Variants without a CPU restatement (HDRx64, plain-type LAv2) still check that the input generator has
+    not drifted from the fixture's inputs."""
     name, view_id, w, h, alg, n_iter, ib = case
     _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
-    assert int(golden[name + "__crc"][0]) == _crc(coords, orbit, la), "input generator drifted from the fixture"
-    t = traits(alg)
-    if t.family == "lav2":
-        got, _ = oracle_cpu.render_lav2(alg, w, h, coords, orbit, la, n, iter_bytes=ib, threads=oracle_cpu.hardware_threads())
-    else:
-        got, _ = oracle_cpu.render_direct(alg, w, h, coords, n, 1, iter_bytes=ib, threads=oracle_cpu.hardware_threads())
+    assert int(golden[name + "__crc"][0]) == cases.inputs_crc(coords, orbit, la), "input generator drifted from the fixture"
+    got = cases.oracle_render(alg, w, h, coords, orbit, la, n, ib)
+    if got is None:
+        pytest.skip("no CPU restatement of this variant: pinned by the fixture against the CUDA path only (-m gpu)")
     want = golden[name]
     assert got.dtype == want.dtype
     np.testing.assert_array_equal(got[:h, :w], want)
@@ -106,6 +94,35 @@ def test_la_table_invariants(built):
     _, _, orbit8, la8, _ = cases.make_inputs(5, 64, 36, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 8)
     assert la8.num_las == la.num_las and la8.las_elem_bytes == 80
     np.testing.assert_array_equal(la8.las_numpy()[:, :60], las[:, :60])
+
+
+def test_bla_table_invariants(built):
+    """Structure of the BLA table (BLAS.cpp:212-254): levels 0/1 absent, level l entry i skips min(2^l, rest) steps,
+    the validity radius never grows when two entries merge, the top level has one entry."""
+    from fractalshark_b200.host_inputs import BlaTable
+    _, coords, orbit, bl, n = cases.make_inputs(5, 64, 36, RenderAlgorithm.GpuHDRx32PerturbedBLA, None, 4)
+    m = orbit.count - 1
+    assert bl.elem_bytes == 44 and bl.level_counts[0] == 0 and bl.level_counts[1] == 0 and bl.level_counts[-1] == 1
+    assert bl.num_levels == bl.lm2 + 2
+    want = m
+    for lv in range(bl.num_levels):
+        if lv >= 2:
+            assert bl.level_counts[lv] == want
+            rec = bl.level_numpy(lv)
+            l = rec[:, 40:44].copy().view(np.int32).reshape(-1)
+            assert int(l.sum()) == m and int(l.max()) == min(2 ** lv, m) and np.all(l[:-1] == 2 ** lv)
+        want = (want + 1) >> 1 if want > 1 else want
+    # r2 of a merged entry <= r2 of its first half (value = mantissa * 2^exp; compare in float64)
+    def r2(lv):
+        rec = bl.level_numpy(lv)
+        return rec[:, 0:4].copy().view(np.float32).reshape(-1).astype(np.float64) * \
+            np.exp2(rec[:, 4:8].copy().view(np.int32).reshape(-1).astype(np.float64))
+    for lv in range(3, bl.num_levels):
+        up, lo = r2(lv), r2(lv - 1)
+        assert np.all(up <= lo[0::2][: len(up)] * (1 + 1e-6))
+    # plain-double table of a shallow view: same shape rules, 48-byte records
+    _, _, orbit64, bl64, _ = cases.make_inputs(100, 64, 36, RenderAlgorithm.Gpu1x64PerturbedBLA, None, 4)
+    assert bl64.elem_bytes == 48 and bl64.level_counts[2] == ((orbit64.count - 1 + 1) // 2 + 1) // 2
 
 
 def test_orbit_layout_and_first_entries(built):
