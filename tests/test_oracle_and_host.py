@@ -112,14 +112,16 @@ def test_bla_table_invariants(built):
             l = rec[:, 40:44].copy().view(np.int32).reshape(-1)
             assert int(l.sum()) == m and int(l.max()) == min(2 ** lv, m) and np.all(l[:-1] == 2 ** lv)
         want = (want + 1) >> 1 if want > 1 else want
-    # r2 of a merged entry <= r2 of its first half (value = mantissa * 2^exp; compare in float64)
+    # r2 of a merged entry is min(r(first half), ...)^2, but the reference takes that min with a lexicographic
+    # (exponent, mantissa) compare on UNREDUCED operands (BLAS.cpp:43, HDRFloat.h:1518-1535), so by value it can
+    # exceed the first half's r2 by less than the mantissa range (reproduced, not fixed): bound it by 4x
     def r2(lv):
         rec = bl.level_numpy(lv)
         return rec[:, 0:4].copy().view(np.float32).reshape(-1).astype(np.float64) * \
             np.exp2(rec[:, 4:8].copy().view(np.int32).reshape(-1).astype(np.float64))
     for lv in range(3, bl.num_levels):
         up, lo = r2(lv), r2(lv - 1)
-        assert np.all(up <= lo[0::2][: len(up)] * (1 + 1e-6))
+        assert np.all(up <= lo[0::2][: len(up)] * 4.0)
     # plain-double table of a shallow view: same shape rules, 48-byte records
     _, _, orbit64, bl64, _ = cases.make_inputs(100, 64, 36, RenderAlgorithm.Gpu1x64PerturbedBLA, None, 4)
     assert bl64.elem_bytes == 48 and bl64.level_counts[2] == ((orbit64.count - 1 + 1) // 2 + 1) // 2
