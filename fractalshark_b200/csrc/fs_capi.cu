@@ -47,6 +47,11 @@ static_assert(sizeof(WireLA<NumHdr<double>, uint32_t>) == 128 && sizeof(WireLA<N
 static_assert(sizeof(WireAT<NumHdr<float>, uint32_t>) == 116 && sizeof(WireAT<NumHdr<float>, uint64_t>) == 120, "ATInfo");
 static_assert(sizeof(WireAT<NumPlain<float>, uint32_t>) == 72 && sizeof(WireAT<NumPlain<float>, uint64_t>) == 80, "ATInfo");
 static_assert(sizeof(WireAT<NumPlain<double>, uint32_t>) == 144 && sizeof(WireAT<NumHdr<double>, uint32_t>) == 232, "ATInfo");
+// 2x32 types (sizes from the reference headers, nvcc 12.9)
+static_assert(sizeof(WireLA<Num2x32, uint32_t>) == 80 && sizeof(WireLA<Num2x32, uint64_t>) == 88, "LAInfoDeep 2x32");
+static_assert(sizeof(WireLA<NumHdr2x32, uint32_t>) == 104 && sizeof(WireLA<NumHdr2x32, uint64_t>) == 112, "LAInfoDeep HDRx2x32");
+static_assert(sizeof(WireAT<Num2x32, uint32_t>) == 140 && sizeof(WireAT<Num2x32, uint64_t>) == 144, "ATInfo 2x32");
+static_assert(sizeof(WireAT<NumHdr2x32, uint32_t>) == 184 && sizeof(WireAT<NumHdr2x32, uint64_t>) == 192, "ATInfo HDRx2x32");
 
 struct DeviceBlob {
     void *ptr = nullptr;
@@ -264,13 +269,16 @@ template <class Num, class IterT> uint32_t upload_la_typed(fs_renderer *r, const
     return 0;
 }
 
-template <class F> uint32_t dispatch_num_iter(int numeric, uint32_t iter_bytes, F &&f) {
+template <class F> uint32_t dispatch_num_iter(int numeric, uint32_t iter_bytes, F &&f, bool allow_2x32 = true) {
     const bool u64 = iter_bytes == 8;
+    if (!allow_2x32 && (numeric == FS_NUM_2X32 || numeric == FS_NUM_HDR2X32)) return FS_ERROR_UNSUPPORTED;
     switch (numeric) {
     case FS_NUM_F32: return u64 ? f(NumPlain<float>{}, uint64_t{}) : f(NumPlain<float>{}, uint32_t{});
     case FS_NUM_F64: return u64 ? f(NumPlain<double>{}, uint64_t{}) : f(NumPlain<double>{}, uint32_t{});
     case FS_NUM_HDR32: return u64 ? f(NumHdr<float>{}, uint64_t{}) : f(NumHdr<float>{}, uint32_t{});
     case FS_NUM_HDR64: return u64 ? f(NumHdr<double>{}, uint64_t{}) : f(NumHdr<double>{}, uint32_t{});
+    case FS_NUM_2X32: return u64 ? f(Num2x32{}, uint64_t{}) : f(Num2x32{}, uint32_t{});
+    case FS_NUM_HDR2X32: return u64 ? f(NumHdr2x32{}, uint64_t{}) : f(NumHdr2x32{}, uint32_t{});
     default: return FS_ERROR_UNSUPPORTED;
     }
 }
@@ -678,9 +686,18 @@ uint32_t fs_render_perturb_bla(fs_renderer *r, uint32_t algorithm, int32_t numer
     const uint32_t rc = upload_orbit(r, r->bla_orbit, numeric, FS_PEXTRAS_DISABLE, 0, results);
     r->use_scaled = saved_scaled;
     if (rc) return rc;
-    return dispatch_num_iter(numeric, r->iter_bytes, [&](auto num, auto it) -> uint32_t {
-        return launch_bla<decltype(num), decltype(it)>(r, blas, dx, dy, center_x, center_y, n_iterations);
-    });
+    const bool u64 = r->iter_bytes == 8;
+    switch (numeric) {
+    case FS_NUM_HDR32:
+        return u64 ? launch_bla<NumHdr<float>, uint64_t>(r, blas, dx, dy, center_x, center_y, n_iterations)
+                   : launch_bla<NumHdr<float>, uint32_t>(r, blas, dx, dy, center_x, center_y, n_iterations);
+    case FS_NUM_HDR64:
+        return u64 ? launch_bla<NumHdr<double>, uint64_t>(r, blas, dx, dy, center_x, center_y, n_iterations)
+                   : launch_bla<NumHdr<double>, uint32_t>(r, blas, dx, dy, center_x, center_y, n_iterations);
+    default:
+        return u64 ? launch_bla<NumPlain<double>, uint64_t>(r, blas, dx, dy, center_x, center_y, n_iterations)
+                   : launch_bla<NumPlain<double>, uint32_t>(r, blas, dx, dy, center_x, center_y, n_iterations);
+    }
 }
 
 uint32_t fs_render_perturb_bla_scaled(fs_renderer *r, uint32_t algorithm, int32_t numeric,

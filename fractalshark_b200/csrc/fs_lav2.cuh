@@ -11,6 +11,7 @@
 // 16x8 CTA per screen block with 32-bit field loads and scalbnf-based alignment.
 #pragma once
 #include "fs_num.cuh"
+#include "fs_df32.cuh"
 #include "fs_perturb_loop.cuh"
 
 namespace fs {
@@ -98,6 +99,25 @@ template <> struct OrbitIO<NumHdr<double>> {
     }
 };
 
+// 2x32 element (16 B) = {x.head, x.tail, y.head, y.tail}. One LDG.128.
+template <> struct OrbitIO<Num2x32> {
+    static constexpr int kBytes = 16;
+    FS_D static void load(const void *base, uint64_t i, df32 &x, df32 &y) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(base) + i);
+        x.head = v.x; x.tail = v.y; y.head = v.z; y.tail = v.w;
+    }
+};
+// HDRx2x32 element (24 B) = {x.head, x.tail, x.exp | y.exp, y.head, y.tail}: x Left-order, y Right-order. Three LDG.64.
+template <> struct OrbitIO<NumHdr2x32> {
+    static constexpr int kBytes = 24;
+    FS_D static void load(const void *base, uint64_t i, Hdr<df32> &x, Hdr<df32> &y) {
+        const uint2 *p = reinterpret_cast<const uint2 *>(base) + 3 * i;
+        const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        x.m.head = __uint_as_float(a.x); x.m.tail = __uint_as_float(a.y); x.e = (int)b.x;
+        y.e = (int)b.y; y.m.head = __uint_as_float(c.x); y.m.tail = __uint_as_float(c.y);
+    }
+};
+
 // ---- small vocabulary shims so the kernel reads the same for plain and HDR numbers ------------
 template <class Num> FS_D bool c_is_ge(typename Num::Real a, typename Num::Real b) { return ge_pr(a, b); }
 
@@ -116,6 +136,13 @@ FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx
         Cplx z = Num::c_zero();
         IterT i = 0;
         for (; i < at_max; i++) {
+            if constexpr (Num::kDf) {
+                // 2x32: every operation is an explicit rounded sequence, evaluated as written (ATInfo.h:166-183)
+                Real nsq = norm2(z);
+                reduce(nsq);
+                if (gt_pr(nsq, A.at.SqrEscapeRadius)) break;
+                z = add(mul(z, z), c);
+            } else {
             // nvcc shares re*re / im*im between norm_squared and z*z in the reference build:
             //   nsq = rr + ii ; z2.re = rr - ii ; z2.im = fma(re, im, re*im)
             const auto rr = z.re * z.re;
@@ -129,6 +156,7 @@ FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx
             z2.im = fma_(z.re, z.im, z.re * z.im);
             if constexpr (Num::kHdr) z2.e = imax(z.e + z.e, MIN_BIG);
             z = add(z2, c);
+            }
         }
         if (Count) steps += i;
         dz = mul(z, A.at.InvZCoeff);

@@ -2,7 +2,7 @@
 // arithmetic variants of the render path so each kernel is written once.
 //   NumPlain<float>, NumPlain<double>           <- T = float / double         (LAKernel.cuh:46-55)
 //   NumHdr<float>,  NumHdr<double>              <- T = HDRFloat<float|double>
-// (2x32 variants live in fs_df32.cuh and plug into the same vocabulary.)
+// The 2x32 variants (Num2x32, NumHdr2x32) live in fs_df32.cuh and plug into the same vocabulary.
 #pragma once
 #include "fs_types.cuh"
 
@@ -34,6 +34,7 @@ template <class M> struct NumPlain {
     using Real = M;
     using Cplx = Cx<M>;
     static constexpr bool kHdr = false;
+    static constexpr bool kDf = false;
     FS_HD static Real zero() { return M(0); }
     FS_HD static Real from_int(int x) { return (M)x; }
     FS_HD static Real neg(Real a) { return -a; }
@@ -70,6 +71,7 @@ template <class M> struct NumHdr {
     using Real = Hdr<M>;
     using Cplx = HdrC<M>;
     static constexpr bool kHdr = true;
+    static constexpr bool kDf = false;
     FS_HD static Real zero() { return hdr_zero<M>(); }
     // T(X): HDRFloat(int) converts through the mantissa type (HDRFloat.h:295-325)
     FS_HD static Real from_int(int x) { return hdr_from<M>((M)x); }

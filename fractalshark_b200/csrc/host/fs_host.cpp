@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <memory>
+
 #include "../fs_types.cuh"
 #include "fs_gmp_min.h"
 
@@ -185,6 +187,7 @@ struct fsh_view {
 
 struct fsh_orbit {
     int numeric = 0;
+    std::shared_ptr<fsh_orbit> base; // 2x32 types: the double / HDR-double orbit they were converted from
     std::vector<unsigned char> data;
     uint64_t count = 0, period = 0;
     size_t elem_bytes = 0;
@@ -370,6 +373,7 @@ template <class N, class IterT> struct LaBuilder {
     static constexpr int MaxLAStages = 1024;
 
     const fsh_orbit *orbit;
+    bool small_exp = false; // UseSmallExponents: true when the table is destined for a 2x32 type (RefOrbitCalc.cpp:2329-2346)
     LaParams P;
     std::vector<LA> las;
     std::vector<WireStage<IterT>> stages;
@@ -688,7 +692,7 @@ template <class N, class IterT> struct LaBuilder {
             for (IterT s = stage_count; s > 0;) {
                 s--;
                 const IterT idx = stages[s].LAIndex;
-                create_at(las[idx], las[idx + 1], false);
+                create_at(las[idx], las[idx + 1], small_exp);
                 at.StepLength = las[idx].StepLength;
                 if (at.StepLength > 0 && at_usable(sqr_radius)) { use_at = true; break; }
             }
@@ -698,6 +702,107 @@ template <class N, class IterT> struct LaBuilder {
         stages.resize(std::max<size_t>((size_t)stage_count, 1));
     }
 };
+
+// --------------------------------------------------------------------------------------------
+// 2x32 types: orbit, LA table and AT are computed in double / HDR-double and converted element-wise
+// (RefOrbitCalc.cpp:2490-2516, PerturbationResults.cpp:241-348, DoubleTo2x32Converter HDRFloat.h:1739-1762).
+// --------------------------------------------------------------------------------------------
+// MattDblflt(double)  dblflt.h:38-52: split + two-sum renormalisation
+df32 h_df_from_double(double d) {
+    const float a = (float)d;
+    const float b = (float)(d - (double)a);
+    df32 z;
+    z.head = a + b;
+    float t1 = z.head - a;
+    float t2 = z.head - t1;
+    t1 = b - t1;
+    t2 = a - t2;
+    z.tail = t1 + t2;
+    return z;
+}
+df32 to_df(double v) { return h_df_from_double(v); }
+Hdr<df32> to_df(Hdr<double> v) { Hdr<df32> r; r.m = h_df_from_double(v.m); r.e = v.e; return r; }            // HDRFloat(const HDRFloat<SrcT>&)
+Cx<df32> to_df(Cx<double> v) { Cx<df32> r; r.re = h_df_from_double(v.re); r.im = h_df_from_double(v.im); return r; }
+HdrC<df32> to_df(HdrC<double> v) { HdrC<df32> r; r.re = h_df_from_double(v.re); r.im = h_df_from_double(v.im); r.e = v.e; return r; }
+
+struct HostDf { using Real = df32; using Cplx = Cx<df32>; };          // T = CudaDblflt<MattDblflt>
+struct HostHdrDf { using Real = Hdr<df32>; using Cplx = HdrC<df32>; }; // T = HDRFloat<CudaDblflt<MattDblflt>>
+static_assert(sizeof(WireLA<HostDf, uint32_t>) == 80 && sizeof(WireLA<HostDf, uint64_t>) == 88, "LAInfoDeep 2x32");
+static_assert(sizeof(WireLA<HostHdrDf, uint32_t>) == 104 && sizeof(WireLA<HostHdrDf, uint64_t>) == 112, "LAInfoDeep HDRx2x32");
+static_assert(sizeof(WireAT<HostDf, uint32_t>) == 140 && sizeof(WireAT<HostHdrDf, uint64_t>) == 192, "ATInfo 2x32");
+
+template <class ND, class NS, class IterT> WireLA<ND, IterT> convert_la_rec(const WireLA<NS, IterT> &s) {
+    WireLA<ND, IterT> d;
+    memset(&d, 0, sizeof(d));
+    d.Ref = to_df(s.Ref); d.ZCoeff = to_df(s.ZCoeff); d.CCoeff = to_df(s.CCoeff);
+    d.LAThreshold = to_df(s.LAThreshold); d.LAThresholdC = to_df(s.LAThresholdC); d.MinMag = to_df(s.MinMag);
+    d.StepLength = s.StepLength; d.NextStageLAIndex = s.NextStageLAIndex;
+    return d;
+}
+template <class ND, class NS, class IterT> WireAT<ND, IterT> convert_at(const WireAT<NS, IterT> &s) {
+    WireAT<ND, IterT> d;
+    memset(&d, 0, sizeof(d));
+    d.StepLength = s.StepLength;
+    d.ThresholdC = to_df(s.ThresholdC); d.SqrEscapeRadius = to_df(s.SqrEscapeRadius);
+    d.RefC = to_df(s.RefC); d.ZCoeff = to_df(s.ZCoeff); d.CCoeff = to_df(s.CCoeff); d.InvZCoeff = to_df(s.InvZCoeff);
+    d.CCoeffSqrInvZCoeff = to_df(s.CCoeffSqrInvZCoeff); d.CCoeffInvZCoeff = to_df(s.CCoeffInvZCoeff);
+    d.CCoeffNormSqr = to_df(s.CCoeffNormSqr); d.RefCNormSqr = to_df(s.RefCNormSqr); d.factor = to_df(s.factor);
+    return d;
+}
+
+// LA table for a 2x32 target: built on the double-typed base orbit with UseSmallExponents, then converted.
+template <class NS, class ND, class IterT> fsh_la *build_la_2x32(const fsh_orbit *base) {
+    LaBuilder<NS, IterT> b;
+    b.orbit = base;
+    b.small_exp = true;
+    b.build();
+    fsh_la *r = new fsh_la();
+    std::vector<WireLA<ND, IterT>> out(b.las.size());
+    for (size_t i = 0; i < b.las.size(); i++) out[i] = convert_la_rec<ND, NS, IterT>(b.las[i]);
+    r->las.resize(out.size() * sizeof(WireLA<ND, IterT>));
+    if (!out.empty()) memcpy(r->las.data(), out.data(), r->las.size());
+    r->stages.resize(b.stages.size() * sizeof(b.stages[0]));
+    memcpy(r->stages.data(), b.stages.data(), r->stages.size());
+    const WireAT<ND, IterT> at = convert_at<ND, NS, IterT>(b.at);
+    r->at.resize(sizeof(at));
+    memcpy(r->at.data(), &at, sizeof(at));
+    r->num_las = b.las.size();
+    r->num_stages = b.stages.size();
+    r->stage_count = b.stage_count;
+    r->use_at = b.use_at;
+    r->is_valid = b.is_valid;
+    return r;
+}
+
+// Orbit for a 2x32 target from its double-typed base (CopyFullOrbitVector, PerturbationResults.cpp:241-290)
+void convert_orbit_2x32(const std::shared_ptr<fsh_orbit> &base, fsh_orbit *o, bool hdr) {
+    o->base = base;
+    o->count = base->count;
+    o->period = base->period;
+    o->elem_bytes = hdr ? 24 : 16;
+    o->data.resize((size_t)o->count * o->elem_bytes);
+    for (uint64_t i = 0; i < o->count; i++) {
+        unsigned char *p = o->data.data() + i * o->elem_bytes;
+        if (hdr) {
+            Hdr<double> x, y;
+            ElemIO<HostHdr<double>>::get(base->data.data() + i * base->elem_bytes, x, y);
+            const Hdr<df32> cx = to_df(x), cy = to_df(y);
+            memcpy(p, &cx.m, 8); memcpy(p + 8, &cx.e, 4); memcpy(p + 12, &cy.e, 4); memcpy(p + 16, &cy.m, 8);
+        } else {
+            double x, y;
+            ElemIO<HostPlain<double>>::get(base->data.data() + i * base->elem_bytes, x, y);
+            const df32 cx = to_df(x), cy = to_df(y);
+            memcpy(p, &cx, 8); memcpy(p + 8, &cy, 8);
+        }
+    }
+    auto conv3 = [&](const unsigned char *src, unsigned char *dst) {
+        if (hdr) { Hdr<double> v; memcpy(&v, src, sizeof(v)); const Hdr<df32> c = to_df(v); memcpy(dst, &c, sizeof(c)); }
+        else { double v; memcpy(&v, src, sizeof(v)); const df32 c = to_df(v); memcpy(dst, &c, sizeof(c)); }
+    };
+    conv3(base->max_radius, o->max_radius);
+    conv3(base->x_low, o->x_low);
+    conv3(base->y_low, o->y_low);
+}
 
 template <class N, class IterT> fsh_la *build_la(const fsh_orbit *o) {
     LaBuilder<N, IterT> b;
@@ -899,7 +1004,7 @@ template <class N> void fill_coord(const fs_mpf_struct *f, void *dst) {
 extern "C" {
 
 // numeric tags as in include/fs_gpu.h
-enum { NUM_F32 = 0, NUM_F64 = 1, NUM_HDR32 = 3, NUM_HDR64 = 4 };
+enum { NUM_F32 = 0, NUM_F64 = 1, NUM_2X32 = 2, NUM_HDR32 = 3, NUM_HDR64 = 4, NUM_HDR2X32 = 5 };
 
 fsh_view *fsh_view_create(const char *minX, const char *minY, const char *maxX, const char *maxY, uint32_t scrn_w,
                           uint32_t scrn_h, uint32_t antialiasing, int32_t square_aspect) {
@@ -960,11 +1065,38 @@ int32_t fsh_view_coords(const fsh_view *v, int32_t numeric, void *cx, void *cy, 
 #define FSH_FILL(N)                                                                                                    \
     fill_coord<N>(v->minX.v, cx); fill_coord<N>(v->minY.v, cy); fill_coord<N>(ddx.v, dx); fill_coord<N>(ddy.v, dy);   \
     fill_coord<N>(cenx.v, center_x); fill_coord<N>(ceny.v, center_y); return 0;
+    // FillCoord for the 2x32 types (Fractal.cpp:1813-1826): CudaDblflt(double(src)); HDRFloat<CudaDblflt>(src)
+    // splits the mpf mantissa into head/tail without renormalising and does NOT reduce
+    auto fill_df = [&](const fs_mpf_struct *f, void *dst, bool hdr) {
+        if (!dst) return;
+        if (!hdr) {
+            const df32 v = h_df_from_double(fs_mpf_get_d(f));
+            memcpy(dst, &v, sizeof(v));
+        } else {
+            Hdr<df32> v;
+            if (fs_mpf_sgn(f) == 0) { v.m.head = 0; v.m.tail = 0; v.e = MIN_BIG; }
+            else {
+                long e = 0;
+                const double m = fs_mpf_get_d_2exp(&e, f);
+                v.m.head = (float)m;
+                v.m.tail = (float)(m - (double)v.m.head);
+                v.e = (int32_t)e;
+            }
+            memcpy(dst, &v, sizeof(v));
+        }
+    };
     switch (numeric) {
     case NUM_F32: FSH_FILL(HostPlain<float>)
     case NUM_F64: FSH_FILL(HostPlain<double>)
     case NUM_HDR32: FSH_FILL(HostHdr<float>)
     case NUM_HDR64: FSH_FILL(HostHdr<double>)
+    case NUM_2X32:
+    case NUM_HDR2X32: {
+        const bool hdr = numeric == NUM_HDR2X32;
+        fill_df(v->minX.v, cx, hdr); fill_df(v->minY.v, cy, hdr); fill_df(ddx.v, dx, hdr); fill_df(ddy.v, dy, hdr);
+        fill_df(cenx.v, center_x, hdr); fill_df(ceny.v, center_y, hdr);
+        return 0;
+    }
     default: return -1;
     }
 #undef FSH_FILL
@@ -978,6 +1110,15 @@ fsh_orbit *fsh_orbit_compute(const fsh_view *v, int32_t numeric, uint64_t max_it
     case NUM_F64: compute_orbit<HostPlain<double>>(v, o, max_iterations, periodicity != 0); break;
     case NUM_HDR32: compute_orbit<HostHdr<float>>(v, o, max_iterations, periodicity != 0); break;
     case NUM_HDR64: compute_orbit<HostHdr<double>>(v, o, max_iterations, periodicity != 0); break;
+    case NUM_2X32:
+    case NUM_HDR2X32: {
+        auto base = std::make_shared<fsh_orbit>();
+        base->numeric = numeric == NUM_2X32 ? NUM_F64 : NUM_HDR64;
+        if (numeric == NUM_2X32) compute_orbit<HostPlain<double>>(v, base.get(), max_iterations, periodicity != 0);
+        else compute_orbit<HostHdr<double>>(v, base.get(), max_iterations, periodicity != 0);
+        convert_orbit_2x32(base, o, numeric == NUM_HDR2X32);
+        break;
+    }
     default: delete o; return nullptr;
     }
     return o;
@@ -998,6 +1139,12 @@ fsh_la *fsh_la_build(const fsh_orbit *o, uint32_t iter_bytes) {
     case NUM_F64: return u64 ? build_la<HostPlain<double>, uint64_t>(o) : build_la<HostPlain<double>, uint32_t>(o);
     case NUM_HDR32: return u64 ? build_la<HostHdr<float>, uint64_t>(o) : build_la<HostHdr<float>, uint32_t>(o);
     case NUM_HDR64: return u64 ? build_la<HostHdr<double>, uint64_t>(o) : build_la<HostHdr<double>, uint32_t>(o);
+    case NUM_2X32:
+        return u64 ? build_la_2x32<HostPlain<double>, HostDf, uint64_t>(o->base.get())
+                   : build_la_2x32<HostPlain<double>, HostDf, uint32_t>(o->base.get());
+    case NUM_HDR2X32:
+        return u64 ? build_la_2x32<HostHdr<double>, HostHdrDf, uint64_t>(o->base.get())
+                   : build_la_2x32<HostHdr<double>, HostHdrDf, uint32_t>(o->base.get());
     default: return nullptr;
     }
 }

@@ -121,7 +121,8 @@ class LaTable:
     @property
     def las_elem_bytes(self) -> int:
         table = {(Numeric.HDR32, 4): 68, (Numeric.HDR32, 8): 80, (Numeric.F32, 4): 44, (Numeric.F32, 8): 56,
-                 (Numeric.F64, 4): 80, (Numeric.F64, 8): 88, (Numeric.HDR64, 4): 128, (Numeric.HDR64, 8): 136}
+                 (Numeric.F64, 4): 80, (Numeric.F64, 8): 88, (Numeric.HDR64, 4): 128, (Numeric.HDR64, 8): 136,
+                 (Numeric.X2_32, 4): 80, (Numeric.X2_32, 8): 88, (Numeric.HDR2X32, 4): 104, (Numeric.HDR2X32, 8): 112}
         return table[(self._orbit.numeric, self.iter_bytes)]
 
     def stages_numpy(self) -> np.ndarray:

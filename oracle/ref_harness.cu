@@ -181,6 +181,8 @@ template <class F> uint32_t by_type(int numeric, uint32_t iter_bytes, F &&f) {
     switch (numeric) {
     case 0: return u64 ? f(uint64_t{}, float{}, float{}) : f(uint32_t{}, float{}, float{});
     case 1: return u64 ? f(uint64_t{}, double{}, double{}) : f(uint32_t{}, double{}, double{});
+    case 2: return u64 ? f(uint64_t{}, CudaDblflt<MattDblflt>{}, CudaDblflt<MattDblflt>{}) : f(uint32_t{}, CudaDblflt<MattDblflt>{}, CudaDblflt<MattDblflt>{});
+    case 5: return u64 ? f(uint64_t{}, HDRFloat<CudaDblflt<MattDblflt>>{}, CudaDblflt<MattDblflt>{}) : f(uint32_t{}, HDRFloat<CudaDblflt<MattDblflt>>{}, CudaDblflt<MattDblflt>{});
     case 3: return u64 ? f(uint64_t{}, HDRFloat<float>{}, float{}) : f(uint32_t{}, HDRFloat<float>{}, float{});
     case 4: return u64 ? f(uint64_t{}, HDRFloat<double>{}, double{}) : f(uint32_t{}, HDRFloat<double>{}, double{});
     default: return 10100;
