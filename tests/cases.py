@@ -31,14 +31,39 @@ SMALL_CASES_2 = [
     ("v101_f32_lav2", 101, 96, 54, A.Gpu1x32PerturbedLAv2, None, 4),
     ("v100_hdr32_lav2", 100, 96, 54, A.GpuHDRx32PerturbedLAv2, None, 4),
 ]
-ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2
+# third fixture file (tests/golden/ref_gpu_small3.npz): 2x32 (CudaDblflt) and HDRx2x32 LAv2 variants
+SMALL_CASES_3 = [
+    ("v100_2x32_lav2", 100, 96, 54, A.Gpu2x32PerturbedLAv2, None, 4),
+    ("v100_2x32_lav2_po", 100, 64, 36, A.Gpu2x32PerturbedLAv2PO, None, 4),
+    ("v100_2x32_lav2_lao", 100, 96, 54, A.Gpu2x32PerturbedLAv2LAO, None, 4),
+    ("v101_2x32_lav2_u64", 101, 50, 37, A.Gpu2x32PerturbedLAv2, None, 8),
+    ("v5_hdr2x32_lav2", 5, 96, 54, A.GpuHDRx2x32PerturbedLAv2, None, 4),
+    ("v5_hdr2x32_lav2_po", 5, 64, 36, A.GpuHDRx2x32PerturbedLAv2PO, 3000, 4),
+    ("v5_hdr2x32_lav2_lao", 5, 96, 54, A.GpuHDRx2x32PerturbedLAv2LAO, None, 4),
+    ("v1_hdr2x32_lav2_u64", 1, 50, 37, A.GpuHDRx2x32PerturbedLAv2, None, 8),
+    ("v19_hdr2x32_lav2_capped", 19, 64, 36, A.GpuHDRx2x32PerturbedLAv2, 200000, 4),
+]
+ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3
+CASE_SETS = {"1": SMALL_CASES, "2": SMALL_CASES_2, "3": SMALL_CASES_3}
+GOLDEN_FILES = {"1": "ref_gpu_small.npz", "2": "ref_gpu_small2.npz", "3": "ref_gpu_small3.npz"}
 
 
 def golden_file_of(name):
     import os
     here = os.path.dirname(os.path.abspath(__file__))
-    which = "ref_gpu_small2.npz" if any(c[0] == name for c in SMALL_CASES_2) else "ref_gpu_small.npz"
-    return os.path.join(here, "golden", which)
+    which = next(k for k, cs in CASE_SETS.items() if any(c[0] == name for c in cs))
+    return os.path.join(here, "golden", GOLDEN_FILES[which])
+
+
+def load_goldens():
+    """All committed reference-kernel fixtures merged into one dict."""
+    import os
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = {}
+    for f in GOLDEN_FILES.values():
+        out.update(np.load(os.path.join(here, "golden", f)))
+    return out
 
 
 def inputs_crc(coords, orbit, table):
@@ -50,7 +75,14 @@ def inputs_crc(coords, orbit, table):
     if orbit is not None:
         crc = zlib.crc32(orbit.as_numpy().tobytes(), crc)
     if table is not None and hasattr(table, "num_las") and table.num_las:
-        crc = zlib.crc32(table.las_numpy().tobytes(), crc)
+        las = table.las_numpy()
+        if las.shape[1] in (128, 136):
+            # LAInfoDeep<HDRFloat<double>>: 4 padding bytes after every int32 exponent (3 complex {re,im,exp}
+            # of 24 B, 3 reals {m,exp} of 16 B) are indeterminate in the generator's C++ structs
+            las = las.copy()
+            for off in (20, 44, 68, 84, 100, 116):
+                las[:, off:off + 4] = 0
+        crc = zlib.crc32(las.tobytes(), crc)
         crc = zlib.crc32(table.stages_numpy().tobytes(), crc)
     if table is not None and hasattr(table, "level_counts"):
         for lv in range(table.num_levels):

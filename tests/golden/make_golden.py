@@ -2,7 +2,7 @@
 (oracle/_ref/libref_gpurender.so, built from /root/reference for sm_100a by oracle/Makefile) for the
 small parity cases of tests/cases.py.  Run on a B200 box:
 
-    gpurun -- 'python tests/golden/make_golden.py gpurun_out/ref_gpu_small.npz 1; python tests/golden/make_golden.py gpurun_out/ref_gpu_small2.npz 2'
+    gpurun -- 'python tests/golden/make_golden.py gpurun_out/ref_gpu_small.npz 1; python tests/golden/make_golden.py gpurun_out/ref_gpu_small2.npz 2; python tests/golden/make_golden.py gpurun_out/ref_gpu_small3.npz 3'
 
 then copy the file to tests/golden/.  Inputs (orbit, LA table, coordinates) come from the in-tree
 generator (libfshost.so) and are deterministic; their CRC32 is stored beside each buffer so a drift of
@@ -27,7 +27,7 @@ inputs_crc = cases.inputs_crc
 
 def main(out_path, which="1"):
     out = {}
-    for name, view_id, w, h, alg, n_iter, ib in (cases.SMALL_CASES if which == "1" else cases.SMALL_CASES_2):
+    for name, view_id, w, h, alg, n_iter, ib in cases.CASE_SETS[which]:
         _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
         iters, _, red = cases.render(ref_renderer.RefGPURenderer, w, h, alg, coords, orbit, la, n, ib)
         out[name] = iters[:h, :w].copy()
@@ -38,6 +38,6 @@ def main(out_path, which="1"):
 
 
 if __name__ == "__main__":
-    # usage: make_golden.py OUT.npz [1|2]   (1 = SMALL_CASES -> ref_gpu_small.npz, 2 = SMALL_CASES_2 -> ref_gpu_small2.npz)
+    # usage: make_golden.py OUT.npz [1|2]   (set k of cases.CASE_SETS -> cases.GOLDEN_FILES[k])
     main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "ref_gpu_small.npz"),
          sys.argv[2] if len(sys.argv) > 2 else "1")

@@ -20,7 +20,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_gpu_small.npz")
 
 @pytest.fixture(scope="module")
 def golden():
-    return {**np.load(GOLDEN), **np.load(cases.golden_file_of(cases.SMALL_CASES_2[0][0]))}
+    return cases.load_goldens()
 
 
 @pytest.mark.parametrize("case", cases.ALL_SMALL_CASES, ids=[c[0] for c in cases.ALL_SMALL_CASES])
@@ -53,6 +53,10 @@ FULL_CASES = [
     ("v100_f64_lav2_po_full", 100, 1920, 1080, A.Gpu1x64PerturbedLAv2PO, None, 8, 1.0),
     ("v5_hdr64_lav2_full", 5, 1920, 1080, A.GpuHDRx64PerturbedLAv2, None, 4, 0.999),
     ("v101_f32_lav2_full", 101, 3840, 2160, A.Gpu1x32PerturbedLAv2, None, 4, 0.999),
+    ("v100_2x32_lav2_full", 100, 1920, 1080, A.Gpu2x32PerturbedLAv2, None, 4, 0.999),
+    ("v100_2x32_lav2_po_full", 100, 1920, 1080, A.Gpu2x32PerturbedLAv2PO, None, 4, 0.999),
+    ("v5_hdr2x32_lav2_full", 5, 1920, 1080, A.GpuHDRx2x32PerturbedLAv2, None, 4, 0.999),
+    ("v1_hdr2x32_lav2_u64_full", 1, 1920, 1080, A.GpuHDRx2x32PerturbedLAv2, None, 8, 0.999),
 ]
 
 

@@ -19,7 +19,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_gpu_small.npz")
 
 @pytest.fixture(scope="module")
 def golden(built):
-    return {**np.load(GOLDEN), **np.load(cases.golden_file_of(cases.SMALL_CASES_2[0][0]))}
+    return cases.load_goldens()
 
 
 @pytest.mark.parametrize("case", cases.ALL_SMALL_CASES, ids=[c[0] for c in cases.ALL_SMALL_CASES])
