@@ -66,7 +66,7 @@ class Traits:
 
 
 _DIRECT = {"Gpu1x32": Numeric.F32, "Gpu2x32": Numeric.X2_32, "Gpu4x32": Numeric.X4_32, "Gpu1x64": Numeric.F64,
-           "Gpu2x64": Numeric.X2_64, "Gpu4x64": Numeric.X4_64, "GpuHDRx32": Numeric.HDR2X32}
+           "Gpu2x64": Numeric.X2_64, "Gpu4x64": Numeric.X4_64, "GpuHDRx32": Numeric.HDR64}  # T of Render<IterType,T> (Fractal.cpp:1228-1253)
 _PREFIX = {"Gpu1x32": Numeric.F32, "Gpu2x32": Numeric.X2_32, "Gpu1x64": Numeric.F64, "GpuHDRx32": Numeric.HDR32,
            "GpuHDRx2x32": Numeric.HDR2X32, "GpuHDRx64": Numeric.HDR64}
 
@@ -82,6 +82,11 @@ def traits(alg: "RenderAlgorithm") -> Traits:
         return Traits("direct", _DIRECT[name])
     for suffix, fam in (("PerturbedScaled", "scaled"), ("PerturbedBLA", "bla")):
         if name.endswith(suffix):
+            if fam == "scaled":
+                # T of RenderPerturbBLAScaled<IterType,T> (Fractal.cpp:1254-1261): double for Gpu1x32PerturbedScaled,
+                # HDRFloat<float> for GpuHDRx32PerturbedScaled; Gpu2x32PerturbedScaled is not wired in the reference
+                num = {"Gpu1x32": Numeric.F64, "GpuHDRx32": Numeric.HDR32}.get(name[: -len(suffix)])
+                return Traits(fam, num, pextras=PerturbExtras.Bad)
             return Traits(fam, _PREFIX[name[: -len(suffix)]],
                           pextras=PerturbExtras.Bad if fam == "scaled" else PerturbExtras.Disable)
     for tail, mode in (("LAv2PO", LAv2Mode.PO), ("LAv2LAO", LAv2Mode.LAO), ("LAv2", LAv2Mode.Full)):

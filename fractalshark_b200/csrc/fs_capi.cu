@@ -17,8 +17,10 @@
 
 #include "fs_bla.cuh"
 #include "fs_direct.cuh"
+#include "fs_direct_ext.cuh"
 #include "fs_lav2.cuh"
 #include "fs_post.cuh"
+#include "fs_scaled_kernel.cuh"
 
 using namespace fs;
 
@@ -99,6 +101,7 @@ struct fs_renderer {
     bool use_scaled = true; // HDRx32: scaled plain-float chunks (fs_scaled_loop.cuh); off = pure float+exponent loop
     OrbitDev orbit1, orbit2;
     OrbitDev bla_orbit;                  // RenderPerturbBLA uploads its orbit and table per call (GPU_Render.cu:1462-1483)
+    OrbitDev scaled_orbit_f;             // RenderPerturbBLAScaled: binary32 orbit, per call (GPU_Render.cu:1324-1350)
     DeviceBlob bla_raw, bla_heads, bla_coefs;
     LaDev la;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -127,6 +130,8 @@ void reset_perturb(fs_renderer *r) {
     free_blob(r, r->bla_orbit.data);
     free_blob(r, r->bla_orbit.fast);
     r->bla_orbit = OrbitDev{};
+    free_blob(r, r->scaled_orbit_f.data);
+    r->scaled_orbit_f = OrbitDev{};
     free_blob(r, r->bla_raw);
     free_blob(r, r->bla_heads);
     free_blob(r, r->bla_coefs);
@@ -429,6 +434,34 @@ uint32_t launch_bla(fs_renderer *r, const fs_blas *blas, const void *dx, const v
     return end_render(r);
 }
 
+// RenderPerturbBLAScaled launch (GPU_Render.cu:1352-1375); both orbits were uploaded by the caller below
+template <class Num, class IterT>
+uint32_t launch_scaled(fs_renderer *r, const void *dx, const void *dy, const void *cx, const void *cy, uint64_t n_iter) {
+    using Real = typename Num::Real;
+    ScaledArgs<Num, IterT> A;
+    memset(&A, 0, sizeof(A));
+    A.out = static_cast<IterT *>(r->iter_buf);
+    A.orbit_f = static_cast<const ScaledElemF *>(r->scaled_orbit_f.data.ptr);
+    A.orbit_t = static_cast<const unsigned char *>(r->bla_orbit.data.ptr);
+    A.orbit_count = (IterT)r->scaled_orbit_f.uncompressed;
+    A.width = (int)r->width;
+    A.height = (int)r->height;
+    A.pitch = (int)(r->w_block * NB_THREADS_W);
+    A.shard_count = (int)r->shard_count;
+    A.shard_index = (int)r->shard_index;
+    A.dx = load_pod<Real>(dx);
+    A.dy = load_pod<Real>(dy);
+    A.centerX = load_pod<Real>(cx);
+    A.centerY = load_pod<Real>(cy);
+    A.n_iterations = (IterT)n_iter;
+    A.tile_counter = r->tile_counter;
+    A.step_counter = r->count_steps ? r->step_counter : nullptr;
+    begin_render(r);
+    if (r->count_steps) { auto k = scaled_kernel<Num, IterT, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
+    else { auto k = scaled_kernel<Num, IterT, false>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
+    return end_render(r);
+}
+
 template <class M, class IterT, int P>
 void launch_direct_p(fs_renderer *r, const DirectArgs<M, IterT> &A) {
     auto k = direct_kernel<M, IterT, P>;
@@ -459,6 +492,53 @@ uint32_t launch_direct(fs_renderer *r, const void *cx, const void *cy, const voi
     default: launch_direct_p<M, IterT, 16>(r, A); break;
     }
     return end_render(r);
+}
+
+template <class Pixel, class IterT>
+uint32_t launch_direct_ext(fs_renderer *r, const typename Pixel::Coord &cx, const typename Pixel::Coord &cy,
+                           const typename Pixel::Coord &dx, const typename Pixel::Coord &dy, uint64_t n_iter) {
+    DirectExtArgs<typename Pixel::Coord, IterT> A;
+    memset(&A, 0, sizeof(A));
+    A.out = static_cast<IterT *>(r->iter_buf);
+    A.width = (int)r->width;
+    A.height = (int)r->height;
+    A.pitch = (int)(r->w_block * NB_THREADS_W);
+    A.shard_count = (int)r->shard_count;
+    A.shard_index = (int)r->shard_index;
+    A.cx = cx; A.cy = cy; A.dx = dx; A.dy = dy;
+    A.n_iterations = (IterT)n_iter;
+    A.tile_counter = r->tile_counter;
+    A.step_counter = r->count_steps ? r->step_counter : nullptr;
+    begin_render(r);
+    auto k = direct_ext_kernel<Pixel, IterT>;
+    k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A);
+    return end_render(r);
+}
+
+// HDRFloat<CudaDblflt>(const HDRFloat<double>&): mantissa through MattDblflt(double) (dblflt.h:37-52), exponent kept.
+// Host-side, as in GPURenderer::Render (GPU_Render.cu:799-803).
+Hdr<df32> hdr2x32_from_hdr64(const void *p) {
+    const Hdr<double> v = load_pod<Hdr<double>>(p);
+    const float a = (float)v.m;
+    const float b = (float)(v.m - (double)a);
+    Hdr<df32> r;
+    volatile float head = a + b;
+    volatile float t1 = head - a;
+    volatile float t2 = head - t1;
+    t1 = b - t1;
+    t2 = a - t2;
+    r.m.head = head;
+    r.m.tail = t1 + t2;
+    r.e = v.e;
+    return r;
+}
+
+template <class Pixel> uint32_t launch_direct_ext_pods(fs_renderer *r, const void *cx, const void *cy, const void *dx,
+                                                       const void *dy, uint64_t n_iter) {
+    using Cd = typename Pixel::Coord;
+    return r->iter_bytes == 8
+               ? launch_direct_ext<Pixel, uint64_t>(r, load_pod<Cd>(cx), load_pod<Cd>(cy), load_pod<Cd>(dx), load_pod<Cd>(dy), n_iter)
+               : launch_direct_ext<Pixel, uint32_t>(r, load_pod<Cd>(cx), load_pod<Cd>(cy), load_pod<Cd>(dx), load_pod<Cd>(dy), n_iter);
 }
 
 template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaStream_t stream) {
@@ -654,6 +734,31 @@ uint32_t fs_render(fs_renderer *r, uint32_t algorithm, int32_t numeric, const vo
     case FS_NUM_F64:
         return u64 ? launch_direct<double, uint64_t>(r, cx, cy, dx, dy, n_iterations, iteration_precision)
                    : launch_direct<double, uint32_t>(r, cx, cy, dx, dy, n_iterations, iteration_precision);
+    case FS_NUM_2X32: // Gpu2x32: MattDblflt {head, tail}; 1/4/8/16 steps per bailout test (GPU_Render.cu:733-771)
+        switch (iteration_precision) {
+        case 1: return launch_direct_ext_pods<Pixel2x32<1>>(r, cx, cy, dx, dy, n_iterations);
+        case 4: return launch_direct_ext_pods<Pixel2x32<4>>(r, cx, cy, dx, dy, n_iterations);
+        case 8: return launch_direct_ext_pods<Pixel2x32<8>>(r, cx, cy, dx, dy, n_iterations);
+        case 16: return launch_direct_ext_pods<Pixel2x32<16>>(r, cx, cy, dx, dy, n_iterations);
+        default: return 0;
+        }
+    case FS_NUM_2X64: return launch_direct_ext_pods<Pixel2x64>(r, cx, cy, dx, dy, n_iterations); // MattDbldbl {head, tail}
+    case FS_NUM_4X32: return launch_direct_ext_pods<Pixel4x32>(r, cx, cy, dx, dy, n_iterations); // MattQFltflt {x,y,z,w}
+    case FS_NUM_4X64: return launch_direct_ext_pods<Pixel4x64>(r, cx, cy, dx, dy, n_iterations); // MattQDbldbl {x,y,z,w}
+    case FS_NUM_HDR64: { // GpuHDRx32: HDRFloat<double> in, float+exponent over 2x32 inside (GPU_Render.cu:797-841)
+        const Hdr<df32> vcx = hdr2x32_from_hdr64(cx), vcy = hdr2x32_from_hdr64(cy), vdx = hdr2x32_from_hdr64(dx),
+                        vdy = hdr2x32_from_hdr64(dy);
+#define FS_HDRD(P) (u64 ? launch_direct_ext<PixelHdr2x32<P>, uint64_t>(r, vcx, vcy, vdx, vdy, n_iterations)             \
+                        : launch_direct_ext<PixelHdr2x32<P>, uint32_t>(r, vcx, vcy, vdx, vdy, n_iterations))
+        switch (iteration_precision) {
+        case 1: return FS_HDRD(1);
+        case 4: return FS_HDRD(4);
+        case 8: return FS_HDRD(8);
+        case 16: return FS_HDRD(16);
+        default: return 0;
+        }
+#undef FS_HDRD
+    }
     default: return FS_ERROR_UNSUPPORTED;
     }
 }
@@ -704,10 +809,23 @@ uint32_t fs_render_perturb_bla_scaled(fs_renderer *r, uint32_t algorithm, int32_
                                       const fs_orbit *double_perturb, const fs_orbit *float_perturb, const void *cx,
                                       const void *cy, const void *dx, const void *dy, const void *center_x,
                                       const void *center_y, uint64_t n_iterations, int32_t iteration_precision) {
-    (void)algorithm; (void)numeric; (void)double_perturb; (void)float_perturb; (void)cx; (void)cy; (void)dx; (void)dy;
-    (void)center_x; (void)center_y; (void)n_iterations; (void)iteration_precision;
-    if (!r || !memory_initialized(r)) return 0;
-    return FS_ERROR_UNSUPPORTED;
+    (void)algorithm; (void)cx; (void)cy; (void)iteration_precision;
+    if (!r || !memory_initialized(r)) return 0; // GPU_Render.cu:1317-1319
+    if (!double_perturb || !float_perturb) return FS_ERROR_6_NO_ORBIT;
+    // the reference instantiates T = double and T = HDRFloat<float> (GPU_Render.cu:1381-1436)
+    if (numeric != FS_NUM_F64 && numeric != FS_NUM_HDR32) return FS_ERROR_UNSUPPORTED;
+    if (double_perturb->compressed_count != float_perturb->compressed_count) return FS_ERROR_UNSUPPORTED;
+    DeviceGuard g(r->device);
+    uint32_t rc = upload_orbit(r, r->scaled_orbit_f, FS_NUM_F32, FS_PEXTRAS_BAD, 0, float_perturb);
+    if (rc) return rc;
+    rc = upload_orbit(r, r->bla_orbit, numeric, FS_PEXTRAS_BAD, 0, double_perturb);
+    if (rc) return rc;
+    const bool u64 = r->iter_bytes == 8;
+    if (numeric == FS_NUM_F64)
+        return u64 ? launch_scaled<NumPlain<double>, uint64_t>(r, dx, dy, center_x, center_y, n_iterations)
+                   : launch_scaled<NumPlain<double>, uint32_t>(r, dx, dy, center_x, center_y, n_iterations);
+    return u64 ? launch_scaled<NumHdr<float>, uint64_t>(r, dx, dy, center_x, center_y, n_iterations)
+               : launch_scaled<NumHdr<float>, uint32_t>(r, dx, dy, center_x, center_y, n_iterations);
 }
 
 uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buffer, fs_color16 *color_buffer,

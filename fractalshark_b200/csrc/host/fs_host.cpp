@@ -1004,7 +1004,8 @@ template <class N> void fill_coord(const fs_mpf_struct *f, void *dst) {
 extern "C" {
 
 // numeric tags as in include/fs_gpu.h
-enum { NUM_F32 = 0, NUM_F64 = 1, NUM_2X32 = 2, NUM_HDR32 = 3, NUM_HDR64 = 4, NUM_HDR2X32 = 5 };
+enum { NUM_F32 = 0, NUM_F64 = 1, NUM_2X32 = 2, NUM_HDR32 = 3, NUM_HDR64 = 4, NUM_HDR2X32 = 5, NUM_2X64 = 6, NUM_4X32 = 7,
+       NUM_4X64 = 8, NUM_2X32_DIRECT = 0x102 /* MattDblflt as FillCoord builds it for Gpu2x32 */ };
 
 fsh_view *fsh_view_create(const char *minX, const char *minY, const char *maxX, const char *maxY, uint32_t scrn_w,
                           uint32_t scrn_h, uint32_t antialiasing, int32_t square_aspect) {
@@ -1085,6 +1086,33 @@ int32_t fsh_view_coords(const fsh_view *v, int32_t numeric, void *cx, void *cy, 
             memcpy(dst, &v, sizeof(v));
         }
     };
+    // FillCoord for the direct kernels' split types (Fractal.cpp:1752-1779, 1805-1810): limb k is the
+    // conversion of what is left after subtracting limbs 0..k-1 in full precision
+    auto fill_split = [&](const fs_mpf_struct *f, void *dst, int limbs, bool as_float) {
+        if (!dst) return;
+        Mpf rest(prec), limb(prec);
+        fs_mpf_set(rest.v, f);
+        for (int k = 0; k < limbs; k++) {
+            double d = fs_mpf_get_d(rest.v);
+            if (as_float) {
+                const float fl = (float)d;
+                memcpy(static_cast<char *>(dst) + 4 * k, &fl, 4);
+                d = (double)fl;
+            } else {
+                memcpy(static_cast<char *>(dst) + 8 * k, &d, 8);
+            }
+            fs_mpf_set_d(limb.v, d);
+            fs_mpf_sub(rest.v, rest.v, limb.v);
+        }
+    };
+    if (numeric == NUM_2X32_DIRECT || numeric == NUM_2X64 || numeric == NUM_4X32 || numeric == NUM_4X64) {
+        const int limbs = (numeric == NUM_4X32 || numeric == NUM_4X64) ? 4 : 2;
+        const bool fl = numeric == NUM_2X32_DIRECT || numeric == NUM_4X32;
+        fill_split(v->minX.v, cx, limbs, fl); fill_split(v->minY.v, cy, limbs, fl);
+        fill_split(ddx.v, dx, limbs, fl); fill_split(ddy.v, dy, limbs, fl);
+        fill_split(cenx.v, center_x, limbs, fl); fill_split(ceny.v, center_y, limbs, fl);
+        return 0;
+    }
     switch (numeric) {
     case NUM_F32: FSH_FILL(HostPlain<float>)
     case NUM_F64: FSH_FILL(HostPlain<double>)
@@ -1120,6 +1148,50 @@ fsh_orbit *fsh_orbit_compute(const fsh_view *v, int32_t numeric, uint64_t max_it
         break;
     }
     default: delete o; return nullptr;
+    }
+    return o;
+}
+// Orbit with the `Bad` prefix (PerturbExtras::Bad, GPU_ReferenceIter.h:10-21) for the scaled kernel.
+//   to_float == 0: same T as `src` (double or HDRFloat<float>), record = {u32 bad, u32 pad, x, y}; the flag is the
+//                  underflow test of RefOrbitCalc.cpp:550-562 (|zx| <= FLT_MIN or |zy| <= FLT_MIN or
+//                  (zx^2 + zy^2) * 1e-7 <= FLT_MIN), false for entry 0 and for the last entry (:625-627)
+//   to_float == 1: the binary32 copy made by CopyUsefulPerturbationResults / CopyFullOrbitVector
+//                  (RefOrbitCalc.cpp:2585-2620, PerturbationResults.cpp:258-264): x, y cast to float, flag copied
+fsh_orbit *fsh_orbit_with_bad(const fsh_orbit *src, int32_t to_float) {
+    if (src->numeric != NUM_F64 && src->numeric != NUM_HDR32) return nullptr;
+    fsh_orbit *o = new fsh_orbit();
+    o->numeric = to_float ? NUM_F32 : src->numeric;
+    o->count = src->count;
+    o->period = src->period;
+    o->elem_bytes = to_float ? 16 : 24;
+    o->data.assign((size_t)o->count * o->elem_bytes, 0);
+    memcpy(o->max_radius, src->max_radius, sizeof(o->max_radius));
+    memcpy(o->x_low, src->x_low, sizeof(o->x_low));
+    memcpy(o->y_low, src->y_low, sizeof(o->y_low));
+    const double small = 1.1754944e-38;
+    for (uint64_t i = 0; i < src->count; i++) {
+        const unsigned char *p = src->data.data() + i * src->elem_bytes;
+        unsigned char *q = o->data.data() + i * o->elem_bytes;
+        double xv, yv;
+        float xf, yf;
+        if (src->numeric == NUM_F64) {
+            memcpy(&xv, p, 8); memcpy(&yv, p + 8, 8);
+            xf = (float)xv; yf = (float)yv;
+        } else {
+            Hdr<float> x, y;
+            ElemIO<HostHdr<float>>::get(p, x, y);
+            xv = ldexp((double)x.m, x.e < -2000 ? -2000 : x.e);
+            yv = ldexp((double)y.m, y.e < -2000 ? -2000 : y.e);
+            // (float)HDRFloat<float>: mantissa * getMultiplier(exp)  HDRFloat.h:497-557
+            auto mult = [](int e) { return e <= -127 ? 0.0f : (e >= 128 ? 3.402823466e+38f : ldexpf(1.0f, e)); };
+            xf = x.m * mult(x.e); yf = y.m * mult(y.e);
+        }
+        uint32_t bad = 0;
+        if (i != 0 && i + 1 != src->count)
+            bad = (fabs(xv) <= small || fabs(yv) <= small || (xv * xv + yv * yv) * 0.0000001 <= small) ? 1u : 0u;
+        memcpy(q, &bad, 4);
+        if (to_float) { memcpy(q + 8, &xf, 4); memcpy(q + 12, &yf, 4); }
+        else memcpy(q + 8, p, 16);
     }
     return o;
 }

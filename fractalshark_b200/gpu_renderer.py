@@ -104,6 +104,18 @@ class GPURenderer:
             _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]), _buf(coords["center_y"]), n_iterations,
             iteration_precision))
 
+    def RenderPerturbBLAScaled(self, algorithm: RenderAlgorithm, double_perturb, float_perturb, coords: dict,
+                               n_iterations: int, iteration_precision: int = 1) -> int:
+        """``double_perturb`` / ``float_perturb``: :class:`host_inputs.Orbit` objects in the ``Bad`` layout
+        (``Orbit.with_bad()`` / ``Orbit.with_bad(to_float=True)``), both uploaded by this call as in the
+        reference (GPU_Render.cu:1302-1377)."""
+        t = traits(algorithm)
+        d, f = double_perturb.descriptor(), float_perturb.descriptor()
+        return int(self._lib.fs_render_perturb_bla_scaled(
+            self._h, int(algorithm), int(t.numeric), C.byref(d), C.byref(f), _buf(coords["cx"]), _buf(coords["cy"]),
+            _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]), _buf(coords["center_y"]), n_iterations,
+            iteration_precision))
+
     # ---- results -------------------------------------------------------------------------------
     def buffer_shape(self) -> tuple[int, int]:
         w, h = self.GetWidth(), self.GetHeight()

@@ -15,7 +15,7 @@ from .algorithms import Numeric
 
 # bytes of one coordinate POD per numeric tag
 POD_BYTES = {Numeric.F32: 4, Numeric.F64: 8, Numeric.X2_32: 8, Numeric.HDR32: 8, Numeric.HDR64: 16,
-             Numeric.HDR2X32: 12}
+             Numeric.HDR2X32: 12, Numeric.X2_64: 16, Numeric.X4_32: 16, Numeric.X4_64: 32}
 
 
 class View:
@@ -39,11 +39,14 @@ class View:
     def precision_bits(self) -> int:
         return int(self._lib.fsh_view_precision_bits(self._h))
 
-    def coords(self, numeric: Numeric) -> dict:
-        """cx, cy, dx, dy, centerX, centerY as raw PODs of ``numeric`` (FillGpuCoords / FillCoord)."""
+    def coords(self, numeric: Numeric, direct: bool = False) -> dict:
+        """cx, cy, dx, dy, centerX, centerY as raw PODs of ``numeric`` (FillGpuCoords / FillCoord).
+        ``direct`` selects the MattDblflt flavour of the 2x32 POD that the direct kernel Gpu2x32 is fed
+        (Fractal.cpp:1805-1810) instead of the CudaDblflt one of the perturbation kernels (:1820-1824)."""
         nb = POD_BYTES[Numeric(numeric)]
         bufs = {k: C.create_string_buffer(nb) for k in ("cx", "cy", "dx", "dy", "center_x", "center_y")}
-        rc = self._lib.fsh_view_coords(self._h, int(numeric), *[C.cast(b, C.c_void_p) for b in bufs.values()])
+        tag = 0x102 if (direct and Numeric(numeric) == Numeric.X2_32) else int(numeric)
+        rc = self._lib.fsh_view_coords(self._h, tag, *[C.cast(b, C.c_void_p) for b in bufs.values()])
         if rc != 0:
             raise ValueError(f"numeric {numeric!r} not supported by the input generator")
         return {k: bytes(b.raw) for k, b in bufs.items()}
@@ -62,6 +65,27 @@ class Orbit:
         self.count = int(self._lib.fsh_orbit_count(self._h))
         self.period = int(self._lib.fsh_orbit_period(self._h))
         self.elem_bytes = int(self._lib.fsh_orbit_elem_bytes(self._h))
+
+    @classmethod
+    def _wrap(cls, view, numeric, handle):
+        o = cls.__new__(cls)
+        o._lib = N.host_lib()
+        o.numeric = Numeric(numeric)
+        o._view = view
+        o._h = handle
+        o.count = int(o._lib.fsh_orbit_count(handle))
+        o.period = int(o._lib.fsh_orbit_period(handle))
+        o.elem_bytes = int(o._lib.fsh_orbit_elem_bytes(handle))
+        return o
+
+    def with_bad(self, to_float: bool = False) -> "Orbit":
+        """``GPUReferenceIter<T, PerturbExtras::Bad>[count]`` for the scaled kernel: the same orbit with the
+        underflow flag of RefOrbitCalc.cpp:550-562, or (``to_float``) its binary32 copy
+        (RefOrbitCalc::CopyUsefulPerturbationResults)."""
+        h = self._lib.fsh_orbit_with_bad(self._h, int(to_float))
+        if not h:
+            raise ValueError("Bad-flagged orbits exist for double and HDRFloat<float> only")
+        return Orbit._wrap(self._view, Numeric.F32 if to_float else self.numeric, h)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -176,6 +176,24 @@ uint32_t render_bla_t(Harness *h, uint32_t alg, const void *orbit, uint64_t coun
     return rc;
 }
 
+// GPURenderer::RenderPerturbBLAScaled<IterType,T>: both orbits in the Bad layout, uploaded per call
+template <typename IterType, class T>
+uint32_t render_scaled_t(Harness *h, uint32_t alg, const void *orbit_t, const void *orbit_f, uint64_t count,
+                         uint64_t period, const void *cx, const void *cy, const void *dx, const void *dy,
+                         const void *cenx, const void *ceny, uint64_t n) {
+    RenderAlgorithm a; *const_cast<RenderAlgorithmEnum *>(&a.Algorithm) = (RenderAlgorithmEnum)alg;
+    GPUPerturbResults<IterType, T, PerturbExtras::Bad> rt{
+        (IterType)count, (IterType)count, T{}, T{}, (const GPUReferenceIter<T, PerturbExtras::Bad> *)orbit_t, (IterType)period};
+    GPUPerturbResults<IterType, float, PerturbExtras::Bad> rf{
+        (IterType)count, (IterType)count, 0.0f, 0.0f, (const GPUReferenceIter<float, PerturbExtras::Bad> *)orbit_f, (IterType)period};
+    const T vcx = pod<T>(cx), vcy = pod<T>(cy), vdx = pod<T>(dx), vdy = pod<T>(dy), vx = pod<T>(cenx), vy = pod<T>(ceny);
+    cudaEventRecord(h->ev0, h->renderer.m_ComputeStream);
+    const uint32_t rc = h->renderer.RenderPerturbBLAScaled<IterType, T>(a, &rt, &rf, vcx, vcy, vdx, vdy, vx, vy, (IterType)n, 1);
+    cudaEventRecord(h->ev1, h->renderer.m_ComputeStream);
+    h->renderer.SyncComputeStream();
+    return rc;
+}
+
 template <class F> uint32_t by_type(int numeric, uint32_t iter_bytes, F &&f) {
     const bool u64 = iter_bytes == 8;
     switch (numeric) {
@@ -264,6 +282,22 @@ uint32_t refh_render_bla(void *p, uint32_t iter_bytes, uint32_t alg, int numeric
 #undef REFH_BLA
 }
 
+uint32_t refh_render_scaled(void *p, uint32_t iter_bytes, uint32_t alg, int numeric, const void *orbit_t,
+                            const void *orbit_f, uint64_t count, uint64_t period, const void *cx, const void *cy,
+                            const void *dx, const void *dy, const void *cenx, const void *ceny, uint64_t n) {
+    Harness *h = (Harness *)p;
+    const bool u64 = iter_bytes == 8;
+#define REFH_SC(T)                                                                                                     \
+    (u64 ? render_scaled_t<uint64_t, T>(h, alg, orbit_t, orbit_f, count, period, cx, cy, dx, dy, cenx, ceny, n)        \
+         : render_scaled_t<uint32_t, T>(h, alg, orbit_t, orbit_f, count, period, cx, cy, dx, dy, cenx, ceny, n))
+    switch (numeric) {
+    case 1: return REFH_SC(double);
+    case 3: return REFH_SC(HDRFloat<float>);
+    default: return 10100;
+    }
+#undef REFH_SC
+}
+
 uint32_t refh_render_direct(void *p, uint32_t iter_bytes, uint32_t alg, int numeric, const void *cx, const void *cy,
                             const void *dx, const void *dy, uint64_t n, int prec) {
     Harness *h = (Harness *)p;
@@ -277,6 +311,17 @@ uint32_t refh_render_direct(void *p, uint32_t iter_bytes, uint32_t alg, int nume
         rc = iter_bytes == 8 ? h->renderer.Render<uint64_t, double>(a, pod<double>(cx), pod<double>(cy), pod<double>(dx), pod<double>(dy), (uint64_t)n, prec)
                              : h->renderer.Render<uint32_t, double>(a, pod<double>(cx), pod<double>(cy), pod<double>(dx), pod<double>(dy), (uint32_t)n, prec);
     }
+#define REFH_DIRECT(TAG, T)                                                                                            \
+    else if (numeric == TAG) {                                                                                         \
+        rc = iter_bytes == 8 ? h->renderer.Render<uint64_t, T>(a, pod<T>(cx), pod<T>(cy), pod<T>(dx), pod<T>(dy), (uint64_t)n, prec) \
+                             : h->renderer.Render<uint32_t, T>(a, pod<T>(cx), pod<T>(cy), pod<T>(dx), pod<T>(dy), (uint32_t)n, prec); \
+    }
+    REFH_DIRECT(2, MattDblflt)        // Gpu2x32
+    REFH_DIRECT(6, MattDbldbl)        // Gpu2x64
+    REFH_DIRECT(7, MattQFltflt)       // Gpu4x32
+    REFH_DIRECT(8, MattQDbldbl)       // Gpu4x64
+    REFH_DIRECT(4, HDRFloat<double>)  // GpuHDRx32 (converted to HDRFloat<CudaDblflt> inside Render)
+#undef REFH_DIRECT
     cudaEventRecord(h->ev1, h->renderer.m_ComputeStream);
     return rc;
 }

@@ -43,9 +43,31 @@ SMALL_CASES_3 = [
     ("v1_hdr2x32_lav2_u64", 1, 50, 37, A.GpuHDRx2x32PerturbedLAv2, None, 8),
     ("v19_hdr2x32_lav2_capped", 19, 64, 36, A.GpuHDRx2x32PerturbedLAv2, 200000, 4),
 ]
-ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3
-CASE_SETS = {"1": SMALL_CASES, "2": SMALL_CASES_2, "3": SMALL_CASES_3}
-GOLDEN_FILES = {"1": "ref_gpu_small.npz", "2": "ref_gpu_small2.npz", "3": "ref_gpu_small3.npz"}
+# fourth fixture file (tests/golden/ref_gpu_small4.npz): scaled kernels (views 19: orbit elements flagged `bad`)
+# and the extended-precision direct kernels
+SMALL_CASES_4 = [
+    ("v100_scaled_f64", 100, 96, 54, A.Gpu1x32PerturbedScaled, None, 4),
+    ("v101_scaled_f64_u64", 101, 50, 37, A.Gpu1x32PerturbedScaled, None, 8),
+    ("v19_scaled_f64_bad", 19, 64, 36, A.Gpu1x32PerturbedScaled, 200000, 4),
+    ("v1_scaled_hdr32", 1, 96, 54, A.GpuHDRx32PerturbedScaled, None, 4),
+    ("v5_scaled_hdr32", 5, 64, 36, A.GpuHDRx32PerturbedScaled, 20000, 4),
+    ("v19_scaled_hdr32_bad_u64", 19, 50, 37, A.GpuHDRx32PerturbedScaled, 200000, 8),
+    ("v0_gpu2x32", 0, 96, 54, A.Gpu2x32, 1024, 4),
+    ("v100_gpu2x32_u64", 100, 50, 37, A.Gpu2x32, 20000, 8),
+    ("v0_gpu2x64", 0, 96, 54, A.Gpu2x64, 1024, 4),
+    ("v102_gpu2x64_u64", 102, 50, 37, A.Gpu2x64, 20000, 8),
+    ("v0_gpuhdrx32", 0, 96, 54, A.GpuHDRx32, 512, 4),
+    ("v100_gpuhdrx32_u64", 100, 50, 37, A.GpuHDRx32, 5000, 8),
+    ("v0_gpu4x32", 0, 96, 54, A.Gpu4x32, 256, 4),
+    ("v0_gpu4x64", 0, 96, 54, A.Gpu4x64, 256, 4),
+]
+# Gpu4x32 / Gpu4x64: the four-limb products are split exactly here (one FMA) while the reference build leaves a
+# Dekker split to the compiler's contraction (fs_qd.cuh); frames agree to >= 99.9 % of pixels, not bit for bit.
+NOT_BIT_EXACT = {"v0_gpu4x32": 0.999, "v0_gpu4x64": 0.999}
+ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3 + SMALL_CASES_4
+CASE_SETS = {"1": SMALL_CASES, "2": SMALL_CASES_2, "3": SMALL_CASES_3, "4": SMALL_CASES_4}
+GOLDEN_FILES = {"1": "ref_gpu_small.npz", "2": "ref_gpu_small2.npz", "3": "ref_gpu_small3.npz",
+                "4": "ref_gpu_small4.npz"}
 
 
 def golden_file_of(name):
@@ -84,6 +106,8 @@ def inputs_crc(coords, orbit, table):
                 las[:, off:off + 4] = 0
         crc = zlib.crc32(las.tobytes(), crc)
         crc = zlib.crc32(table.stages_numpy().tobytes(), crc)
+    if table is not None and hasattr(table, "as_numpy"):   # scaled kernel: the binary32 orbit
+        crc = zlib.crc32(table.as_numpy().tobytes(), crc)
     if table is not None and hasattr(table, "level_counts"):
         for lv in range(table.num_levels):
             crc = zlib.crc32(table.level_numpy(lv).tobytes(), crc)
@@ -101,6 +125,8 @@ def oracle_render(alg, w, h, coords, orbit, table, n, ib, **kw):
             return oracle_cpu.render_lav2(alg, w, h, coords, orbit, table, n, iter_bytes=ib, **kw)[0]
         if fam == "bla":
             return oracle_cpu.render_bla(alg, w, h, coords, orbit, table, n, iter_bytes=ib, **kw)[0]
+        if fam == "scaled":
+            return oracle_cpu.render_scaled(alg, w, h, coords, orbit, table, n, iter_bytes=ib, **kw)[0]
         return oracle_cpu.render_direct(alg, w, h, coords, n, 1, iter_bytes=ib, threads=kw["threads"])[0]
     except NotImplementedError:
         return None
@@ -114,7 +140,7 @@ def make_inputs(view_id, w, h, alg, n_iter, iter_bytes):
     n_iter = n_iter or p.num_iterations
     t = traits(alg)
     view = View(p.min_x, p.min_y, p.max_x, p.max_y, w, h)
-    coords = view.coords(t.numeric)
+    coords = view.coords(t.numeric, direct=(t.family == "direct"))
     orbit = la = None
     if t.family == "lav2":
         orbit = Orbit(view, t.numeric, n_iter, True)
@@ -123,6 +149,10 @@ def make_inputs(view_id, w, h, alg, n_iter, iter_bytes):
         from fractalshark_b200.host_inputs import BlaTable
         orbit = Orbit(view, t.numeric, n_iter, True)
         la = BlaTable(orbit)   # rides in the `la` slot of the case tuple
+    elif t.family == "scaled":
+        base = Orbit(view, t.numeric, n_iter, True)
+        orbit = base.with_bad()             # GPUReferenceIter<T, Bad>
+        la = base.with_bad(to_float=True)   # its binary32 copy rides in the `la` slot
     return view, coords, orbit, la, n_iter
 
 
@@ -140,6 +170,8 @@ def render(renderer_cls, w, h, alg, coords, orbit, la, n_iter, iter_bytes, want_
         rc = r.RenderPerturbLAv2(alg, coords, n_iter)
     elif fam == "bla":
         rc = r.RenderPerturbBLA(alg, orbit, la, coords, n_iter)
+    elif fam == "scaled":
+        rc = r.RenderPerturbBLAScaled(alg, orbit, la, coords, n_iter)
     else:
         rc = r.Render(alg, coords, n_iter, 1)
     assert rc == 0, rc

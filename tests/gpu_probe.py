@@ -23,7 +23,7 @@ def run(view_id, w, h, alg, n_iter=None, iter_bytes=4, with_ref=True):
     n_iter = n_iter or p.num_iterations
     t = traits(alg)
     v = View(p.min_x, p.min_y, p.max_x, p.max_y, w, h)
-    coords = v.coords(t.numeric)
+    coords = v.coords(t.numeric, direct=(t.family == 'direct'))
     print(f"view {view_id} {w}x{h} {alg.name} n_iter={n_iter} iter_bytes={iter_bytes}", flush=True)
     orbit = la = None
     if t.family == "lav2":
@@ -34,6 +34,11 @@ def run(view_id, w, h, alg, n_iter=None, iter_bytes=4, with_ref=True):
         t0 = time.time(); orbit = Orbit(v, t.numeric, n_iter, True); t1 = time.time()
         la = BlaTable(orbit)
         print(f"  orbit count={orbit.count} period={orbit.period} ({t1-t0:.2f}s) bla: levels={la.num_levels} lm2={la.lm2} ({time.time()-t1:.2f}s)", flush=True)
+    if t.family == "scaled":
+        base = Orbit(v, t.numeric, n_iter, True)
+        orbit, la = base.with_bad(), base.with_bad(True)
+        nbad = int(orbit.as_numpy()[:, 0].sum())
+        print(f"  orbit count={orbit.count} period={orbit.period} bad={nbad}", flush=True)
     outs = {}
     for name, R in (("new", GPURenderer), ("ref", ref_renderer.RefGPURenderer)):
         if name == "ref" and not with_ref:
@@ -48,6 +53,8 @@ def run(view_id, w, h, alg, n_iter=None, iter_bytes=4, with_ref=True):
                 rc = r.RenderPerturbLAv2(alg, coords, n_iter)
             elif t.family == "bla":
                 rc = r.RenderPerturbBLA(alg, orbit, la, coords, n_iter)
+            elif t.family == "scaled":
+                rc = r.RenderPerturbBLAScaled(alg, orbit, la, coords, n_iter)
             else:
                 rc = r.Render(alg, coords, n_iter, 1)
             assert rc == 0, rc

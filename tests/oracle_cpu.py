@@ -78,6 +78,25 @@ def render_bla(alg, w, h, coords, orbit, blas, n_iter, iter_bytes=4, rows=None, 
     return out, int(steps)
 
 
+def render_scaled(alg, w, h, coords, orbit_t, orbit_f, n_iter, iter_bytes=4, rows=None, col_step=1, row_step=1,
+                  threads=1):
+    """CPU restatement of mandel_1x_float_perturb_scaled (both orbits in the Bad layout)."""
+    t = traits(alg)
+    hp, wp = _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)
+    out = np.zeros((hp, wp), dtype=np.uint32 if iter_bytes == 4 else np.uint64)
+    rb, re = rows if rows is not None else (0, h)
+    fn = lib().orc_render_scaled
+    fn.restype = C.c_uint64
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                   C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    steps = fn(int(t.numeric), iter_bytes, orbit_t.data_ptr, orbit_f.data_ptr, orbit_t.count, w, h, _buf(coords["dx"]),
+               _buf(coords["dy"]), _buf(coords["center_x"]), _buf(coords["center_y"]), n_iter, out.ctypes.data, rb, re,
+               col_step, row_step, threads)
+    if steps == 2 ** 64 - 1:
+        raise NotImplementedError(f"oracle has no restatement for {alg!r}")
+    return out, int(steps)
+
+
 def render_direct(alg, w, h, coords, n_iter, prec=1, iter_bytes=4, rows=None, threads=1):
     t = traits(alg)
     hp, wp = _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)

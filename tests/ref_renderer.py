@@ -36,6 +36,8 @@ def lib():
         L.refh_render_direct.argtypes = [V, U32, U32, I32, V, V, V, V, U64, I32]
         L.refh_render_bla.argtypes = [V, U32, U32, I32, V, U64, U64, V, V, U32, I32, V, V, V, V, V, V, U64]
         L.refh_render_bla.restype = U32
+        L.refh_render_scaled.argtypes = [V, U32, U32, I32, V, V, U64, U64, V, V, V, V, V, V, U64]
+        L.refh_render_scaled.restype = U32
         L.refh_render_current.argtypes = [V, U32, U64, V, V, V]
         L.refh_sync.argtypes = [V]
         L.refh_last_render_ms.argtypes = [V, C.POINTER(C.c_float)]
@@ -108,6 +110,16 @@ class RefGPURenderer:
                                              b.num_levels, b.lm2, _buf(coords["cx"]), _buf(coords["cy"]),
                                              _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]),
                                              _buf(coords["center_y"]), n_iterations))
+
+    def RenderPerturbBLAScaled(self, algorithm, double_perturb, float_perturb, coords, n_iterations,
+                               iteration_precision=1):
+        t = traits(algorithm)
+        d, f = double_perturb.descriptor(), float_perturb.descriptor()
+        return int(self._lib.refh_render_scaled(self._h, self._iter_bytes, int(algorithm), int(t.numeric), d.elements,
+                                                f.elements, d.uncompressed_count, d.period_maybe_zero,
+                                                _buf(coords["cx"]), _buf(coords["cy"]), _buf(coords["dx"]),
+                                                _buf(coords["dy"]), _buf(coords["center_x"]),
+                                                _buf(coords["center_y"]), n_iterations))
 
     def RenderCurrent(self, n_iterations, want_iters=True, want_colors=False, progressive=False):
         hp, wp = _round_up(self._h_px, NB_THREADS_H), _round_up(self._w, NB_THREADS_W)
