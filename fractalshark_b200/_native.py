@@ -76,6 +76,9 @@ HOST_SYMBOLS = {
     "fsh_view_coords": (_I32, [_V, _I32, _V, _V, _V, _V, _V, _V]),
     "fsh_orbit_compute": (_V, [_V, _I32, _U64, _I32]),
     "fsh_orbit_with_bad": (_V, [_V, _I32]),
+    "fsh_orbit_compress": (_V, [_V, _I32]),
+    "fsh_orbit_uncompressed_count": (_U64, [_V]),
+    "fsh_orbit_replay_data": (_V, [_V]),
     "fsh_orbit_destroy": (None, [_V]),
     "fsh_orbit_data": (_V, [_V]),
     "fsh_orbit_count": (_U64, [_V]),

@@ -19,6 +19,7 @@
 #include "fs_direct.cuh"
 #include "fs_direct_ext.cuh"
 #include "fs_lav2.cuh"
+#include "fs_orbit_rc.cuh"
 #include "fs_post.cuh"
 #include "fs_scaled_kernel.cuh"
 
@@ -157,6 +158,12 @@ void reset_buffers(fs_renderer *r) {
 
 bool memory_initialized(const fs_renderer *r) { return r->iter_buf && r->red_dev && r->color_buf; }
 
+template <class T> T load_pod_early(const void *p) {
+    T v;
+    memcpy(&v, p, sizeof(T));
+    return v;
+}
+
 size_t orbit_elem_bytes(int numeric, int pextras) {
     size_t base;
     switch (numeric) {
@@ -181,12 +188,76 @@ __global__ void __launch_bounds__(256) build_fast_table_kernel(const uint4 *__re
     }
 }
 
+// Expands an uploaded waypoint list into the uncompressed layout (fs_orbit_rc.cuh)
+template <class Num>
+uint32_t expand_orbit(fs_renderer *r, const void *wire, uint64_t n_way, uint64_t n_full, const void *x_low, const void *y_low,
+                      void *out) {
+    using Real = typename Num::Real;
+    const Real X = load_pod_early<Real>(x_low), Y = load_pod_early<Real>(y_low);
+    const uint64_t want = (n_way + 127) / 128;
+    const unsigned grid = (unsigned)(want < (uint64_t)r->num_sms * 16 ? (want ? want : 1) : (uint64_t)r->num_sms * 16);
+    orbit_expand_kernel<Num><<<grid, 128, 0, r->compute>>>(static_cast<const unsigned char *>(wire), n_way, n_full, X, Y, out);
+    r->launches++;
+    return cudaGetLastError();
+}
+
 uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, uint64_t generation, const fs_orbit *src) {
     const size_t eb = orbit_elem_bytes(numeric, pextras);
     if (eb == 0) return FS_ERROR_UNSUPPORTED;
     free_blob(r, dst.data);
     free_blob(r, dst.fast);
     dst = OrbitDev{};
+    if (pextras == FS_PEXTRAS_SIMPLE_COMPRESSION) {
+        // waypoints -> device -> full orbit in the Disable layout; the staging copy is freed in stream order
+        if (!src->orbit_x_low || !src->orbit_y_low || src->compressed_count == 0 ||
+            src->uncompressed_count < src->compressed_count)
+            return FS_ERROR_6_NO_ORBIT;
+        const size_t full_eb = orbit_elem_bytes(numeric, FS_PEXTRAS_DISABLE);
+        const size_t full_bytes = full_eb * src->uncompressed_count;
+        void *wire = nullptr;
+        cudaError_t e = cudaMallocAsync(&wire, eb * src->compressed_count, r->compute);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(wire, src->elements, eb * src->compressed_count, cudaMemcpyDefault, r->compute);
+        if (e != cudaSuccess) return e;
+        e = cudaMallocAsync(&dst.data.ptr, full_bytes + 64, r->compute);
+        if (e != cudaSuccess) return e;
+        dst.data.bytes = full_bytes;
+        e = cudaMemsetAsync(static_cast<char *>(dst.data.ptr) + full_bytes, 0, 64, r->compute);
+        if (e != cudaSuccess) return e;
+        uint32_t rc;
+        switch (numeric) {
+        case FS_NUM_F32: rc = expand_orbit<NumPlain<float>>(r, wire, src->compressed_count, src->uncompressed_count, src->orbit_x_low, src->orbit_y_low, dst.data.ptr); break;
+        case FS_NUM_F64: rc = expand_orbit<NumPlain<double>>(r, wire, src->compressed_count, src->uncompressed_count, src->orbit_x_low, src->orbit_y_low, dst.data.ptr); break;
+        case FS_NUM_2X32: rc = expand_orbit<Num2x32>(r, wire, src->compressed_count, src->uncompressed_count, src->orbit_x_low, src->orbit_y_low, dst.data.ptr); break;
+        case FS_NUM_HDR32: rc = expand_orbit<NumHdr<float>>(r, wire, src->compressed_count, src->uncompressed_count, src->orbit_x_low, src->orbit_y_low, dst.data.ptr); break;
+        case FS_NUM_HDR64: rc = expand_orbit<NumHdr<double>>(r, wire, src->compressed_count, src->uncompressed_count, src->orbit_x_low, src->orbit_y_low, dst.data.ptr); break;
+        case FS_NUM_HDR2X32: rc = expand_orbit<NumHdr2x32>(r, wire, src->compressed_count, src->uncompressed_count, src->orbit_x_low, src->orbit_y_low, dst.data.ptr); break;
+        default: rc = FS_ERROR_UNSUPPORTED; break;
+        }
+        cudaFreeAsync(wire, r->compute);
+        if (rc) return rc;
+        if (numeric == FS_NUM_HDR32 && src->uncompressed_count > 1 && src->uncompressed_count <= scaled::kMaxElems && r->use_scaled) {
+            const size_t fbytes = sizeof(scaled::FastElem) * src->uncompressed_count;
+            e = cudaMallocAsync(&dst.fast.ptr, fbytes, r->compute);
+            if (e != cudaSuccess) return e;
+            dst.fast.bytes = fbytes;
+            const uint64_t want = (src->uncompressed_count + 255) / 256;
+            const unsigned grid = (unsigned)(want < (uint64_t)r->num_sms * 8 ? want : (uint64_t)r->num_sms * 8);
+            build_fast_table_kernel<<<grid, 256, 0, r->compute>>>(static_cast<const uint4 *>(dst.data.ptr), src->uncompressed_count,
+                                                                  static_cast<scaled::FastElem *>(dst.fast.ptr));
+            r->launches++;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+        dst.compressed = src->compressed_count;
+        dst.uncompressed = src->uncompressed_count;
+        dst.period = src->period_maybe_zero;
+        dst.numeric = numeric;
+        dst.pextras = pextras;
+        dst.generation = generation;
+        dst.valid = true;
+        return 0;
+    }
     const size_t bytes = eb * src->compressed_count;
     // one zeroed element of padding: the reference's FP64 BLA kernel can read one element past the end after an
     // escaping skip (BLAKernels.cuh:128-134, its own TODO); the value there does not reach the output
@@ -770,7 +841,8 @@ uint32_t fs_render_perturb_lav2(fs_renderer *r, uint32_t algorithm, int32_t nume
     if (!r || !memory_initialized(r)) return 0; // GPU_Render.cu:1007-1009
     DeviceGuard g(r->device);
     if (!r->orbit1.valid || r->orbit1.numeric != numeric || r->orbit1.pextras != pextras) return FS_ERROR_6_NO_ORBIT;
-    if (pextras != FS_PEXTRAS_DISABLE) return FS_ERROR_UNSUPPORTED;
+    // compressed orbits were expanded at upload (fs_orbit_rc.cuh): the same kernels serve both layouts
+    if (pextras != FS_PEXTRAS_DISABLE && pextras != FS_PEXTRAS_SIMPLE_COMPRESSION) return FS_ERROR_UNSUPPORTED;
     return dispatch_num_iter(numeric, r->iter_bytes, [&](auto num, auto it) -> uint32_t {
         return launch_lav2<decltype(num), decltype(it)>(r, mode, dx, dy, center_x, center_y, n_iterations);
     });

@@ -187,6 +187,9 @@ struct fsh_view {
 
 struct fsh_orbit {
     int numeric = 0;
+    int pextras = 0;                  // 0 Disable, 1 Bad, 2 SimpleCompression
+    uint64_t uncompressed_count = 0;  // SimpleCompression: GetCountOrbitEntries(); `count` is then the compressed size
+    std::shared_ptr<fsh_orbit> plain; // SimpleCompression: the host-side replay of this orbit (RuntimeDecompressor view)
     std::shared_ptr<fsh_orbit> base; // 2x32 types: the double / HDR-double orbit they were converted from
     std::vector<unsigned char> data;
     uint64_t count = 0, period = 0;
@@ -369,7 +372,7 @@ template <class N, class IterT> struct LaBuilder {
     using LA = WireLA<N, IterT>;
     using AT = WireAT<N, IterT>;
     static constexpr int lowBound = 64;     // LAReference.h:56
-    static constexpr int periodDivisor = 2; // LAReference.cpp:17-19 (8 with orbit compression)
+    int periodDivisor = 2; // LAReference.cpp:17-19: 2, or 8 when the orbit is compressed (SimpleCompression)
     static constexpr int MaxLAStages = 1024;
 
     const fsh_orbit *orbit;
@@ -751,9 +754,10 @@ template <class ND, class NS, class IterT> WireAT<ND, IterT> convert_at(const Wi
 }
 
 // LA table for a 2x32 target: built on the double-typed base orbit with UseSmallExponents, then converted.
-template <class NS, class ND, class IterT> fsh_la *build_la_2x32(const fsh_orbit *base) {
+template <class NS, class ND, class IterT> fsh_la *build_la_2x32(const fsh_orbit *base, int period_divisor = 2) {
     LaBuilder<NS, IterT> b;
     b.orbit = base;
+    b.periodDivisor = period_divisor;
     b.small_exp = true;
     b.build();
     fsh_la *r = new fsh_la();
@@ -772,6 +776,100 @@ template <class NS, class ND, class IterT> fsh_la *build_la_2x32(const fsh_orbit
     r->use_at = b.use_at;
     r->is_valid = b.is_valid;
     return r;
+}
+
+// ---- SimpleCompression ---------------------------------------------------------------------------------------
+// One replay step in the low type, host flavour (no contraction: each operator rounds once):
+//   zx' = zx*zx - zy*zy + OrbitXLow ; zy' = T{2}*zx_old*zy + OrbitYLow, both HdrReduce'd
+template <class N> struct RcHost;
+template <class M> struct RcHost<HostPlain<M>> {
+    static void step(M &zx, M &zy, M X, M Y) {
+        const M a = zx * zx, b = zy * zy, o = zx;
+        zx = (a - b) + X;
+        zy = ((M(2) * o) * zy) + Y;
+    }
+    // err = (|z - it|^2) * 10^exp >= |it|^2
+    static bool drifted(M zx, M zy, M ix, M iy, M scale) {
+        const M ex = zx - ix, ey = zy - iy;
+        const M norm = ix * ix + iy * iy;
+        const M err = (ex * ex + ey * ey) * scale;
+        return err >= norm;
+    }
+    static M scale(int e) { return (M)pow(10, e); }
+};
+template <class M> struct RcHost<HostHdr<M>> {
+    using R = Hdr<M>;
+    static void step(R &zx, R &zy, R X, R Y) {
+        const R o = zx;
+        zx = add(sub(mul(zx, zx), mul(zy, zy)), X);
+        reduce(zx);
+        zy = add(mul(mul(hdr_make<M>(1, M(1)), o), zy), Y);
+        reduce(zy);
+    }
+    static bool drifted(R zx, R zy, R ix, R iy, R scale) {
+        const R ex = sub(zx, ix), ey = sub(zy, iy);
+        R norm = add(mul(ix, ix), mul(iy, iy));
+        reduce(norm);
+        R err = mul(add(mul(ex, ex), mul(ey, ey)), scale);
+        reduce(err);
+        return cmp_pr(err, norm) >= 0;
+    }
+    static R scale(int e) { return hdr_from<M>((M)pow(10, e)); } // static_cast<T>(std::pow(10, exp)): HDRFloat(double)
+};
+
+template <class N> fsh_orbit *compress_orbit(const fsh_orbit *src, int32_t error_exp) {
+    using Real = typename N::Real;
+    using IO = ElemIO<N>;
+    using RC = RcHost<N>;
+    fsh_orbit *o = new fsh_orbit();
+    o->numeric = src->numeric;
+    o->pextras = 2;
+    o->period = src->period;
+    o->elem_bytes = 8 + IO::kBytes;
+    o->uncompressed_count = src->count;
+    memcpy(o->max_radius, src->max_radius, sizeof(o->max_radius));
+    memcpy(o->x_low, src->x_low, sizeof(o->x_low));
+    memcpy(o->y_low, src->y_low, sizeof(o->y_low));
+    Real X, Y;
+    memcpy(&X, src->x_low, sizeof(Real));
+    memcpy(&Y, src->y_low, sizeof(Real));
+    auto plain = std::make_shared<fsh_orbit>();
+    plain->numeric = src->numeric;
+    plain->count = src->count;
+    plain->period = src->period;
+    plain->elem_bytes = IO::kBytes;
+    plain->data.assign((size_t)src->count * IO::kBytes, 0);
+    memcpy(plain->max_radius, src->max_radius, sizeof(o->max_radius));
+    memcpy(plain->x_low, src->x_low, sizeof(o->x_low));
+    memcpy(plain->y_low, src->y_low, sizeof(o->y_low));
+    auto push = [&](uint64_t index, Real x, Real y) {
+        const size_t off = o->data.size();
+        o->data.resize(off + o->elem_bytes, 0);
+        const uint64_t raw = index & 0x7FFFFFFFFFFFFFFFull; // CompressionIndex : 63, Rebase : 1 (= 0)
+        memcpy(o->data.data() + off, &raw, 8);
+        IO::put(o->data.data() + off + 8, x, y);
+        o->count++;
+    };
+    const Real scale = RC::scale(error_exp);
+    // entry 0 is the zero element pushed by InitResults (PerturbationResults.cpp:861-863); the compressor's
+    // running value starts at (OrbitXLow, OrbitYLow), the replay of entry 0 (:2336)
+    Real ix, iy;
+    IO::get(src->data.data(), ix, iy);
+    push(0, ix, iy);
+    IO::put(plain->data.data(), ix, iy);
+    Real zx = X, zy = Y;
+    for (uint64_t i = 1; i < src->count; i++) {
+        IO::get(src->data.data() + i * IO::kBytes, ix, iy);
+        if (RC::drifted(zx, zy, ix, iy, scale)) {
+            push(i, ix, iy);
+            zx = ix;
+            zy = iy;
+        }
+        IO::put(plain->data.data() + i * IO::kBytes, zx, zy); // value the decompressor reproduces at index i
+        RC::step(zx, zy, X, Y);
+    }
+    o->plain = plain;
+    return o;
 }
 
 // Orbit for a 2x32 target from its double-typed base (CopyFullOrbitVector, PerturbationResults.cpp:241-290)
@@ -804,9 +902,10 @@ void convert_orbit_2x32(const std::shared_ptr<fsh_orbit> &base, fsh_orbit *o, bo
     conv3(base->y_low, o->y_low);
 }
 
-template <class N, class IterT> fsh_la *build_la(const fsh_orbit *o) {
+template <class N, class IterT> fsh_la *build_la(const fsh_orbit *o, int period_divisor = 2) {
     LaBuilder<N, IterT> b;
     b.orbit = o;
+    b.periodDivisor = period_divisor;
     b.build();
     fsh_la *r = new fsh_la();
     r->las.resize(b.las.size() * sizeof(b.las[0]));
@@ -1195,6 +1294,66 @@ fsh_orbit *fsh_orbit_with_bad(const fsh_orbit *src, int32_t to_float) {
     }
     return o;
 }
+// SimpleCompression (RefOrbitCompressor, PerturbationResults.cpp:2334-2381): waypoints {CompressionIndex, x, y}
+// wherever replaying z <- z^2 + c in the low type drifts by more than 10^-error_exp relative; the orbit between
+// waypoints is recomputed by the consumer.  Returns the compressed orbit (GPUReferenceIter<T, SimpleCompression>[],
+// 8-byte index prefix); `plain` holds the host replay (RuntimeDecompressor, PerturbationResultsHelpers.h:34-197),
+// which is what the LA table is built from.  2x32 targets compress their double-typed base and convert the
+// waypoints (CopyFullOrbitVector, PerturbationResults.cpp:264-267).
+fsh_orbit *fsh_orbit_compress(const fsh_orbit *src, int32_t error_exp) {
+    if (src->pextras != 0) return nullptr;
+    switch (src->numeric) {
+    case NUM_F32: return compress_orbit<HostPlain<float>>(src, error_exp);
+    case NUM_F64: return compress_orbit<HostPlain<double>>(src, error_exp);
+    case NUM_HDR32: return compress_orbit<HostHdr<float>>(src, error_exp);
+    case NUM_HDR64: return compress_orbit<HostHdr<double>>(src, error_exp);
+    case NUM_2X32:
+    case NUM_HDR2X32: {
+        const bool hdr = src->numeric == NUM_HDR2X32;
+        std::shared_ptr<fsh_orbit> cb(hdr ? compress_orbit<HostHdr<double>>(src->base.get(), error_exp)
+                                          : compress_orbit<HostPlain<double>>(src->base.get(), error_exp));
+        fsh_orbit *o = new fsh_orbit();
+        o->numeric = src->numeric;
+        o->pextras = 2;
+        o->count = cb->count;
+        o->uncompressed_count = cb->uncompressed_count;
+        o->period = cb->period;
+        o->elem_bytes = 8 + (hdr ? 24 : 16);
+        o->data.assign((size_t)o->count * o->elem_bytes, 0);
+        for (uint64_t i = 0; i < cb->count; i++) {
+            const unsigned char *p = cb->data.data() + i * cb->elem_bytes;
+            unsigned char *q = o->data.data() + i * o->elem_bytes;
+            memcpy(q, p, 8);
+            if (hdr) {
+                Hdr<double> x, y;
+                ElemIO<HostHdr<double>>::get(p + 8, x, y);
+                const Hdr<df32> cx = to_df(x), cy = to_df(y);
+                memcpy(q + 8, &cx.m, 8); memcpy(q + 16, &cx.e, 4); memcpy(q + 20, &cy.e, 4); memcpy(q + 24, &cy.m, 8);
+            } else {
+                double x, y;
+                ElemIO<HostPlain<double>>::get(p + 8, x, y);
+                const df32 cx = to_df(x), cy = to_df(y);
+                memcpy(q + 8, &cx, 8); memcpy(q + 16, &cy, 8);
+            }
+        }
+        memcpy(o->max_radius, src->max_radius, sizeof(o->max_radius));
+        memcpy(o->x_low, src->x_low, sizeof(o->x_low));
+        memcpy(o->y_low, src->y_low, sizeof(o->y_low));
+        // the table is built on the double-typed replay and converted (build_la_2x32 reads plain->base)
+        o->plain = std::make_shared<fsh_orbit>();
+        o->plain->numeric = src->numeric;
+        o->plain->base = cb->plain;
+        return o;
+    }
+    default: return nullptr;
+    }
+}
+uint64_t fsh_orbit_uncompressed_count(const fsh_orbit *o) { return o->pextras == 2 ? o->uncompressed_count : o->count; }
+// host replay of a compressed orbit in the Disable layout (what RuntimeDecompressor hands to the host code)
+const void *fsh_orbit_replay_data(const fsh_orbit *o) {
+    if (o->pextras != 2 || !o->plain || o->plain->data.empty()) return nullptr;
+    return o->plain->data.data();
+}
 void fsh_orbit_destroy(fsh_orbit *o) { delete o; }
 const void *fsh_orbit_data(const fsh_orbit *o) { return o->data.data(); }
 uint64_t fsh_orbit_count(const fsh_orbit *o) { return o->count; }
@@ -1206,17 +1365,21 @@ const void *fsh_orbit_max_radius(const fsh_orbit *o) { return o->max_radius; }
 
 fsh_la *fsh_la_build(const fsh_orbit *o, uint32_t iter_bytes) {
     const bool u64 = iter_bytes == 8;
+    // compressed orbit: the table is built from what the host-side RuntimeDecompressor replays
+    // (LAReference.cpp reads the orbit through GetComplex), with the coarser period divisor
+    const int pd = o->pextras == 2 ? 8 : 2;
+    if (o->pextras == 2) o = o->plain.get();
     switch (o->numeric) {
-    case NUM_F32: return u64 ? build_la<HostPlain<float>, uint64_t>(o) : build_la<HostPlain<float>, uint32_t>(o);
-    case NUM_F64: return u64 ? build_la<HostPlain<double>, uint64_t>(o) : build_la<HostPlain<double>, uint32_t>(o);
-    case NUM_HDR32: return u64 ? build_la<HostHdr<float>, uint64_t>(o) : build_la<HostHdr<float>, uint32_t>(o);
-    case NUM_HDR64: return u64 ? build_la<HostHdr<double>, uint64_t>(o) : build_la<HostHdr<double>, uint32_t>(o);
+    case NUM_F32: return u64 ? build_la<HostPlain<float>, uint64_t>(o, pd) : build_la<HostPlain<float>, uint32_t>(o, pd);
+    case NUM_F64: return u64 ? build_la<HostPlain<double>, uint64_t>(o, pd) : build_la<HostPlain<double>, uint32_t>(o, pd);
+    case NUM_HDR32: return u64 ? build_la<HostHdr<float>, uint64_t>(o, pd) : build_la<HostHdr<float>, uint32_t>(o, pd);
+    case NUM_HDR64: return u64 ? build_la<HostHdr<double>, uint64_t>(o, pd) : build_la<HostHdr<double>, uint32_t>(o, pd);
     case NUM_2X32:
-        return u64 ? build_la_2x32<HostPlain<double>, HostDf, uint64_t>(o->base.get())
-                   : build_la_2x32<HostPlain<double>, HostDf, uint32_t>(o->base.get());
+        return u64 ? build_la_2x32<HostPlain<double>, HostDf, uint64_t>(o->base.get(), pd)
+                   : build_la_2x32<HostPlain<double>, HostDf, uint32_t>(o->base.get(), pd);
     case NUM_HDR2X32:
-        return u64 ? build_la_2x32<HostHdr<double>, HostHdrDf, uint64_t>(o->base.get())
-                   : build_la_2x32<HostHdr<double>, HostHdrDf, uint32_t>(o->base.get());
+        return u64 ? build_la_2x32<HostHdr<double>, HostHdrDf, uint64_t>(o->base.get(), pd)
+                   : build_la_2x32<HostHdr<double>, HostHdrDf, uint32_t>(o->base.get(), pd);
     default: return nullptr;
     }
 }

@@ -68,8 +68,11 @@ class GPURenderer:
                                                   palette_generation, int(expected_reuse)))
 
     def InitializePerturb(self, generation1: int, perturb1, generation2: int = 0, perturb2=None, la=None,
-                          pextras: PerturbExtras = PerturbExtras.Disable) -> int:
-        """``perturb1``/``perturb2`` are :class:`host_inputs.Orbit`, ``la`` a :class:`host_inputs.LaTable`."""
+                          pextras: PerturbExtras | None = None) -> int:
+        """``perturb1``/``perturb2`` are :class:`host_inputs.Orbit`, ``la`` a :class:`host_inputs.LaTable`.
+        ``pextras`` defaults to the layout of ``perturb1`` (Disable, or SimpleCompression for ``Orbit.compress()``)."""
+        if pextras is None:
+            pextras = PerturbExtras(getattr(perturb1, "pextras", 0))
         d1 = perturb1.descriptor()
         d2 = perturb2.descriptor() if perturb2 is not None else None
         dl = la.descriptor() if la is not None else None

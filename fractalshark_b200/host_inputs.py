@@ -65,6 +65,9 @@ class Orbit:
         self.count = int(self._lib.fsh_orbit_count(self._h))
         self.period = int(self._lib.fsh_orbit_period(self._h))
         self.elem_bytes = int(self._lib.fsh_orbit_elem_bytes(self._h))
+        self.uncompressed_count = self.count
+
+    pextras = 0  # PerturbExtras of the element layout (0 Disable, 1 Bad, 2 SimpleCompression)
 
     @classmethod
     def _wrap(cls, view, numeric, handle):
@@ -76,6 +79,19 @@ class Orbit:
         o.count = int(o._lib.fsh_orbit_count(handle))
         o.period = int(o._lib.fsh_orbit_period(handle))
         o.elem_bytes = int(o._lib.fsh_orbit_elem_bytes(handle))
+        o.uncompressed_count = int(o._lib.fsh_orbit_uncompressed_count(handle))
+        return o
+
+    def compress(self, error_exp: int = 20) -> "Orbit":
+        """``GPUReferenceIter<T, PerturbExtras::SimpleCompression>[]``: the waypoints RefOrbitCompressor keeps for a
+        relative replay error of 10^-error_exp (default 20, Fractal.h:138-141).  ``count`` is then the compressed
+        size, ``uncompressed_count`` the number of orbit entries; LaTable() of such an orbit is built from its host
+        replay with the reference's coarser period divisor."""
+        h = self._lib.fsh_orbit_compress(self._h, int(error_exp))
+        if not h:
+            raise ValueError("orbit cannot be compressed")
+        o = Orbit._wrap(self._view, self.numeric, h)
+        o.pextras = 2
         return o
 
     def with_bad(self, to_float: bool = False) -> "Orbit":
@@ -101,7 +117,7 @@ class Orbit:
         return np.frombuffer(buf, dtype=np.uint8).reshape(self.count, self.elem_bytes)
 
     def descriptor(self) -> N.FsOrbit:
-        return N.FsOrbit(self.data_ptr, self.count, self.count, self.period,
+        return N.FsOrbit(self.data_ptr, self.count, self.uncompressed_count, self.period,
                          int(self._lib.fsh_orbit_x_low(self._h)), int(self._lib.fsh_orbit_y_low(self._h)))
 
 

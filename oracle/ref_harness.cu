@@ -92,11 +92,11 @@ struct Harness {
 
 // Build a host LAReference<...> image without running its constructor: only the members read by
 // GPU_LAReference's upload constructor (GPU_LAReference.h:78-162) are populated.
-template <typename IterType, class T, class SubType>
-const LAReference<IterType, T, SubType, PerturbExtras::Disable> *
+template <typename IterType, class T, class SubType, PerturbExtras PExtras = PerturbExtras::Disable>
+const LAReference<IterType, T, SubType, PExtras> *
 make_la(Harness *h, const void *las, uint64_t num_las, const void *stages, uint64_t num_stages, const void *at,
         uint64_t stage_count, int use_at, int is_valid) {
-    using LR = LAReference<IterType, T, SubType, PerturbExtras::Disable>;
+    using LR = LAReference<IterType, T, SubType, PExtras>;
     h->la_storage.assign(sizeof(LR) + 64, 0);
     unsigned char *p = h->la_storage.data();
     p += (64 - (reinterpret_cast<uintptr_t>(p) & 63)) & 63;
@@ -105,7 +105,7 @@ make_la(Harness *h, const void *las, uint64_t num_las, const void *stages, uint6
     if (at) memcpy(&lr->m_AT, at, sizeof(lr->m_AT));
     lr->m_LAStageCount = (IterType)stage_count;
     lr->m_IsValid = is_valid != 0;
-    lr->m_LAs.m_Data = (LAInfoDeep<IterType, T, SubType, PerturbExtras::Disable> *)las;
+    lr->m_LAs.m_Data = (LAInfoDeep<IterType, T, SubType, PExtras> *)las;
     lr->m_LAs.m_UsedSizeInElts = num_las;
     lr->m_LAs.m_CapacityInElts = num_las;
     lr->m_LAStages.m_Data = (LAStageInfo<IterType> *)stages;
@@ -130,6 +130,33 @@ uint32_t init_perturb_t(Harness *h, uint64_t gen, const void *orbit, uint64_t co
     const LAReference<IterType, T, SubType, PerturbExtras::Disable> *la = nullptr;
     if (las) la = make_la<IterType, T, SubType>(h, las, num_las, stages, num_stages, at, stage_count, use_at, is_valid);
     return h->renderer.InitializePerturb<IterType, T, SubType, PerturbExtras::Disable, T>(gen, &res, 0, nullptr, la);
+}
+
+// compressed orbit (PerturbExtras::SimpleCompression): `count` waypoints standing for `full` orbit entries
+template <typename IterType, class T, class SubType>
+uint32_t init_perturb_rc_t(Harness *h, uint64_t gen, const void *orbit, uint64_t count, uint64_t full, uint64_t period,
+                           const void *xlow, const void *ylow, const void *las, uint64_t num_las, const void *stages,
+                           uint64_t num_stages, const void *at, uint64_t stage_count, int use_at, int is_valid) {
+    constexpr PerturbExtras PE = PerturbExtras::SimpleCompression;
+    GPUPerturbResults<IterType, T, PE> res{(IterType)count, (IterType)full, pod<T>(xlow), pod<T>(ylow),
+                                           (const GPUReferenceIter<T, PE> *)orbit, (IterType)period};
+    const LAReference<IterType, T, SubType, PE> *la = nullptr;
+    if (las) la = make_la<IterType, T, SubType, PE>(h, las, num_las, stages, num_stages, at, stage_count, use_at, is_valid);
+    return h->renderer.InitializePerturb<IterType, T, SubType, PE, T>(gen, &res, 0, nullptr, la);
+}
+
+template <typename IterType, class T, class SubType>
+uint32_t render_lav2_rc_t(Harness *h, uint32_t alg, int mode, const void *cx, const void *cy, const void *dx,
+                          const void *dy, const void *cenx, const void *ceny, uint64_t n) {
+    constexpr PerturbExtras PE = PerturbExtras::SimpleCompression;
+    RenderAlgorithm a; *const_cast<RenderAlgorithmEnum *>(&a.Algorithm) = (RenderAlgorithmEnum)alg;
+    const T vcx = pod<T>(cx), vcy = pod<T>(cy), vdx = pod<T>(dx), vdy = pod<T>(dy), vx = pod<T>(cenx), vy = pod<T>(ceny);
+    switch (mode) {
+    case 1: return h->renderer.RenderPerturbLAv2<IterType, T, SubType, LAv2Mode::Full, PE>(a, vcx, vcy, vdx, vdy, vx, vy, (IterType)n);
+    case 2: return h->renderer.RenderPerturbLAv2<IterType, T, SubType, LAv2Mode::PO, PE>(a, vcx, vcy, vdx, vdy, vx, vy, (IterType)n);
+    case 3: return h->renderer.RenderPerturbLAv2<IterType, T, SubType, LAv2Mode::LAO, PE>(a, vcx, vcy, vdx, vdy, vx, vy, (IterType)n);
+    default: return 10100;
+    }
 }
 
 template <typename IterType, class T, class SubType>
@@ -248,6 +275,30 @@ uint32_t refh_init_perturb(void *p, uint32_t iter_bytes, int numeric, uint64_t g
 void refh_clear(void *p, uint32_t iter_bytes) {
     Harness *h = (Harness *)p;
     if (iter_bytes == 8) h->renderer.ClearMemory<uint64_t>(); else h->renderer.ClearMemory<uint32_t>();
+}
+
+uint32_t refh_init_perturb_rc(void *p, uint32_t iter_bytes, int numeric, uint64_t gen, const void *orbit, uint64_t count,
+                              uint64_t full, uint64_t period, const void *xlow, const void *ylow, const void *las,
+                              uint64_t num_las, const void *stages, uint64_t num_stages, const void *at,
+                              uint64_t stage_count, int use_at, int is_valid) {
+    Harness *h = (Harness *)p;
+    return by_type(numeric, iter_bytes, [&](auto it, auto t, auto st) -> uint32_t {
+        return init_perturb_rc_t<decltype(it), decltype(t), decltype(st)>(h, gen, orbit, count, full, period, xlow, ylow, las,
+                                                                         num_las, stages, num_stages, at, stage_count,
+                                                                         use_at, is_valid);
+    });
+}
+
+uint32_t refh_render_lav2_rc(void *p, uint32_t iter_bytes, uint32_t alg, int numeric, int mode, const void *cx,
+                             const void *cy, const void *dx, const void *dy, const void *cenx, const void *ceny,
+                             uint64_t n) {
+    Harness *h = (Harness *)p;
+    cudaEventRecord(h->ev0, h->renderer.m_ComputeStream);
+    const uint32_t rc = by_type(numeric, iter_bytes, [&](auto it, auto t, auto st) -> uint32_t {
+        return render_lav2_rc_t<decltype(it), decltype(t), decltype(st)>(h, alg, mode, cx, cy, dx, dy, cenx, ceny, n);
+    });
+    cudaEventRecord(h->ev1, h->renderer.m_ComputeStream);
+    return rc;
 }
 
 uint32_t refh_render_lav2(void *p, uint32_t iter_bytes, uint32_t alg, int numeric, int mode, const void *cx,

@@ -61,13 +61,27 @@ SMALL_CASES_4 = [
     ("v0_gpu4x32", 0, 96, 54, A.Gpu4x32, 256, 4),
     ("v0_gpu4x64", 0, 96, 54, A.Gpu4x64, 256, 4),
 ]
+# fifth fixture file (tests/golden/ref_gpu_small5.npz): RC algorithms (compressed orbits, PerturbExtras::SimpleCompression)
+SMALL_CASES_5 = [
+    ("v5_hdr32_rclav2", 5, 96, 54, A.GpuHDRx32PerturbedRCLAv2, None, 4),
+    ("v5_hdr32_rclav2_po_u64", 5, 50, 37, A.GpuHDRx32PerturbedRCLAv2PO, 3000, 8),
+    ("v5_hdr32_rclav2_lao", 5, 96, 54, A.GpuHDRx32PerturbedRCLAv2LAO, None, 4),
+    ("v19_hdr32_rclav2_capped", 19, 64, 36, A.GpuHDRx32PerturbedRCLAv2, 200000, 4),
+    ("v100_f64_rclav2", 100, 96, 54, A.Gpu1x64PerturbedRCLAv2, None, 4),
+    ("v100_f64_rclav2_po_u64", 100, 50, 37, A.Gpu1x64PerturbedRCLAv2PO, None, 8),
+    ("v101_f32_rclav2", 101, 96, 54, A.Gpu1x32PerturbedRCLAv2, None, 4),
+    ("v5_hdr64_rclav2", 5, 64, 36, A.GpuHDRx64PerturbedRCLAv2, None, 4),
+    ("v100_2x32_rclav2", 100, 96, 54, A.Gpu2x32PerturbedRCLAv2, None, 4),
+    ("v5_hdr2x32_rclav2", 5, 64, 36, A.GpuHDRx2x32PerturbedRCLAv2, None, 4),
+    ("v1_hdr2x32_rclav2_lao_u64", 1, 50, 37, A.GpuHDRx2x32PerturbedRCLAv2LAO, None, 8),
+]
 # Gpu4x32 / Gpu4x64: the four-limb products are split exactly here (one FMA) while the reference build leaves a
 # Dekker split to the compiler's contraction (fs_qd.cuh); frames agree to >= 99.9 % of pixels, not bit for bit.
 NOT_BIT_EXACT = {"v0_gpu4x32": 0.999, "v0_gpu4x64": 0.999}
-ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3 + SMALL_CASES_4
-CASE_SETS = {"1": SMALL_CASES, "2": SMALL_CASES_2, "3": SMALL_CASES_3, "4": SMALL_CASES_4}
+ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3 + SMALL_CASES_4 + SMALL_CASES_5
+CASE_SETS = {"1": SMALL_CASES, "2": SMALL_CASES_2, "3": SMALL_CASES_3, "4": SMALL_CASES_4, "5": SMALL_CASES_5}
 GOLDEN_FILES = {"1": "ref_gpu_small.npz", "2": "ref_gpu_small2.npz", "3": "ref_gpu_small3.npz",
-                "4": "ref_gpu_small4.npz"}
+                "4": "ref_gpu_small4.npz", "5": "ref_gpu_small5.npz"}
 
 
 def golden_file_of(name):
@@ -144,6 +158,8 @@ def make_inputs(view_id, w, h, alg, n_iter, iter_bytes):
     orbit = la = None
     if t.family == "lav2":
         orbit = Orbit(view, t.numeric, n_iter, True)
+        if int(t.pextras) == 2:   # RC algorithms: waypoints only, LA table from the host replay
+            orbit = orbit.compress()
         la = LaTable(orbit, iter_bytes)
     elif t.family == "bla":
         from fractalshark_b200.host_inputs import BlaTable

@@ -28,7 +28,10 @@ def run(view_id, w, h, alg, n_iter=None, iter_bytes=4, with_ref=True):
     orbit = la = None
     if t.family == "lav2":
         t0 = time.time(); orbit = Orbit(v, t.numeric, n_iter, True); t1 = time.time()
-        la = LaTable(orbit, iter_bytes) if t.mode != 2 else LaTable(orbit, iter_bytes)
+        if int(t.pextras) == 2:
+            orbit = orbit.compress()
+            print(f"  compressed: {orbit.count} waypoints for {orbit.uncompressed_count} entries", flush=True)
+        la = LaTable(orbit, iter_bytes)
         print(f"  orbit count={orbit.count} period={orbit.period} ({t1-t0:.2f}s) la: n={la.num_las} stages={la.stage_count} at={la.use_at} valid={la.is_valid} ({time.time()-t1:.2f}s)", flush=True)
     if t.family == "bla":
         t0 = time.time(); orbit = Orbit(v, t.numeric, n_iter, True); t1 = time.time()

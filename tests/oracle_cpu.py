@@ -49,12 +49,23 @@ def render_lav2(alg, w, h, coords, orbit, la, n_iter, iter_bytes=4, rows=None, c
         out = np.zeros((hp, wp), dtype=dt)
     rb, re = rows if rows is not None else (0, h)
     d = orbit.descriptor()
+    elements = d.elements
+    if getattr(orbit, "pextras", 0) == 2:
+        # compressed orbit: replay the waypoints with the device arithmetic first (Perturb.cuh:246-326)
+        full = np.zeros((d.uncompressed_count, 16), dtype=np.uint8)
+        fn = lib().orc_expand_orbit
+        fn.restype = C.c_uint64
+        fn.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        if fn(int(t.numeric), d.elements, d.compressed_count, d.uncompressed_count, d.orbit_x_low, d.orbit_y_low,
+              full.ctypes.data) != 0:
+            raise NotImplementedError(f"oracle has no compressed-orbit replay for {alg!r}")
+        elements = full.ctypes.data
     if la is not None:
         l = la.descriptor()
         largs = (l.las, l.stages, l.at, l.la_stage_count, l.use_at, l.is_valid)
     else:
         largs = (None, None, None, 0, 0, 0)
-    steps = lib().orc_render_lav2(int(t.numeric), iter_bytes, int(t.mode), d.elements, d.uncompressed_count, *largs,
+    steps = lib().orc_render_lav2(int(t.numeric), iter_bytes, int(t.mode), elements, d.uncompressed_count, *largs,
                                   w, h, _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]),
                                   _buf(coords["center_y"]), n_iter, out.ctypes.data, rb, re, col_step, row_step, threads)
     if steps == 2 ** 64 - 1:

@@ -38,6 +38,10 @@ def lib():
         L.refh_render_bla.restype = U32
         L.refh_render_scaled.argtypes = [V, U32, U32, I32, V, V, U64, U64, V, V, V, V, V, V, U64]
         L.refh_render_scaled.restype = U32
+        L.refh_init_perturb_rc.argtypes = [V, U32, I32, U64, V, U64, U64, U64, V, V, V, U64, V, U64, V, U64, I32, I32]
+        L.refh_init_perturb_rc.restype = U32
+        L.refh_render_lav2_rc.argtypes = [V, U32, U32, I32, I32, V, V, V, V, V, V, U64]
+        L.refh_render_lav2_rc.restype = U32
         L.refh_render_current.argtypes = [V, U32, U64, V, V, V]
         L.refh_sync.argtypes = [V]
         L.refh_last_render_ms.argtypes = [V, C.POINTER(C.c_float)]
@@ -82,6 +86,10 @@ class RefGPURenderer:
             args = (l.las, l.num_las, l.stages, l.num_stages, l.at, l.la_stage_count, l.use_at, l.is_valid)
         else:
             args = (None, 0, None, 0, None, 0, 0, 0)
+        if getattr(perturb1, "pextras", 0) == 2:
+            return int(self._lib.refh_init_perturb_rc(self._h, self._iter_bytes, int(perturb1.numeric), generation1,
+                                                      d.elements, d.compressed_count, d.uncompressed_count,
+                                                      d.period_maybe_zero, d.orbit_x_low, d.orbit_y_low, *args))
         return int(self._lib.refh_init_perturb(self._h, self._iter_bytes, int(perturb1.numeric), generation1,
                                                d.elements, d.uncompressed_count, d.period_maybe_zero, d.orbit_x_low,
                                                d.orbit_y_low, *args))
@@ -97,7 +105,8 @@ class RefGPURenderer:
 
     def RenderPerturbLAv2(self, algorithm, coords, n_iterations):
         t = traits(algorithm)
-        return int(self._lib.refh_render_lav2(self._h, self._iter_bytes, int(algorithm), int(t.numeric), int(t.mode),
+        fn = self._lib.refh_render_lav2_rc if int(t.pextras) == 2 else self._lib.refh_render_lav2
+        return int(fn(self._h, self._iter_bytes, int(algorithm), int(t.numeric), int(t.mode),
                                               _buf(coords["cx"]), _buf(coords["cy"]), _buf(coords["dx"]),
                                               _buf(coords["dy"]), _buf(coords["center_x"]), _buf(coords["center_y"]),
                                               n_iterations))

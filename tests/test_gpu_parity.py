@@ -68,6 +68,10 @@ FULL_CASES = [
     ("v0_gpu2x64_full", 0, 1920, 1080, A.Gpu2x64, 2048, 4, 1.0),
     ("v102_gpu2x64_full", 102, 1920, 1080, A.Gpu2x64, 20000, 4, 1.0),
     ("v100_gpuhdrx32_full", 100, 960, 540, A.GpuHDRx32, 5000, 4, 0.999),
+    ("v5_hdr32_rclav2_full", 5, 3840, 2160, A.GpuHDRx32PerturbedRCLAv2, None, 4, 0.999),
+    ("v19_hdr32_rclav2_full", 19, 960, 540, A.GpuHDRx32PerturbedRCLAv2, 3000000, 4, 0.999),
+    ("v100_f64_rclav2_full", 100, 1920, 1080, A.Gpu1x64PerturbedRCLAv2, None, 4, 1.0),
+    ("v5_hdr2x32_rclav2_po_full", 5, 960, 540, A.GpuHDRx2x32PerturbedRCLAv2PO, 20000, 8, 0.999),
     ("v0_gpu4x32_full", 0, 960, 540, A.Gpu4x32, 1024, 4, -0.999),   # negative: exactness floor only, see NOT_BIT_EXACT
     ("v0_gpu4x64_full", 0, 960, 540, A.Gpu4x64, 1024, 4, -0.999),
 ]
