@@ -4,17 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (libfsgpu.so on N B200s)
     python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU port on host cores
 
-Workload (config.workload): View #5, GpuHDRx32PerturbedLAv2, 3840x2160, AA 1, u32 iterations,
-maxIter 4,718,592 (BASELINE.json configs[2]/[3]; the largest "View 5/14 perturb+LA" case whose orbit this
-image can produce offline).  One step = ClearMemory + one full render of the frame.
+Workload (config.workload): View #14 (default; north_star's target view: 6,632-digit coordinates, zoom 4.7e6516,
+maxIter 2,147,483,646) or View #5 (`--view 5`, maxIter 4,718,592), GpuHDRx32PerturbedLAv2, 3840x2160, AA 1,
+u32 iterations (BASELINE.json metric "View 5/14 perturb+LA", configs[2]/[3]).  The reference orbit comes from
+the in-tree GMP loop (View 14: 21.7 kbit, period 116,695, a few seconds; untimed).  One step = ClearMemory + one
+full render of the frame.
 
 * value       pixel-iterations/s = ReductionResults.Sum / device time of the render kernel(s), inputs
               (orbit, LA table) already resident in HBM; CUDA events on the launching stream, max over ranks.
 * e2e         same metric through the public C-ABI call sequence with HOST buffers inside the timed region:
               InitializePerturb (H2D orbit + LA table), ClearMemory, RenderPerturbLAv2, RenderCurrent
               (AA/palette/reduction + D2H of the iteration buffer and the 24-byte reduction).
-* roofline    FP32 issue: executed steps x FP32 instructions per step / kernel time,
-              against the FFMA issue peak measured live by a micro-kernel on the same GPU.
+* roofline    FP32 issue: executed steps by kind (AT passes, LA steps, perturbation steps; device counters) x FP32
+              instructions per step (9 for an AT pass) / kernel time, against the FFMA issue
+              peak measured live by a micro-kernel on the same GPU.
 * cpu_baseline the oracle's CPU port of the same kernel on a bounded pixel sample (all host threads).
 N > 1: 4-row tile bands are dealt round-robin to ranks (no data-path collective inside the render);
 the orbit/LA blob is replicated by an NCCL broadcast and the iteration buffer is merged on rank 0 with an
@@ -35,10 +38,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT = 3840, 2160
-WORKLOAD = "view5_GpuHDRx32PerturbedLAv2_3840x2160_aa1_u32_maxiter4718592"
-METRIC = "pixel-iters/sec (device-timed) for View 5 perturb+LA"
+VIEW_ID = 14
+WORKLOAD = METRIC = ""
 FP32_INSTR_PER_PERTURB_STEP = 20  # HDRx32 perturbation step, mantissa ops only
 FP32_INSTR_PER_LA_STEP = 22
+FP32_INSTR_PER_AT_PASS = 9       # z <- z^2 + c with |z|^2 test: rr, ii, rr+ii, rr-ii, re*im, 3 FMA + compare (ATInfo.h:155-188)
+
+
+def set_view(view_id):
+    global VIEW_ID, WORKLOAD, METRIC
+    from fractalshark_b200.views import PRESETS
+    VIEW_ID = view_id
+    WORKLOAD = f"view{view_id}_GpuHDRx32PerturbedLAv2_{WIDTH}x{HEIGHT}_aa1_u32_maxiter{PRESETS[view_id].num_iterations}"
+    METRIC = f"pixel-iters/sec (device-timed) for View {view_id} perturb+LA"
 
 
 def _clock_sampler(stop, samples, gpu_index):
@@ -69,8 +81,8 @@ def _clock_summary(samples):
 def build_inputs(width, height):
     from fractalshark_b200 import Numeric
     from fractalshark_b200.host_inputs import LaTable, Orbit, View
-    from fractalshark_b200.views import VIEW5
-    p = VIEW5
+    from fractalshark_b200.views import PRESETS
+    p = PRESETS[VIEW_ID]
     view = View(p.min_x, p.min_y, p.max_x, p.max_y, width, height)
     t0 = time.time()
     orbit = Orbit(view, Numeric.HDR32, p.num_iterations, True)
@@ -85,7 +97,7 @@ def cpu_port_sample(coords, orbit, la, n_iter, threads):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_cpu
     from fractalshark_b200 import RenderAlgorithm
-    row_step = col_step = 6  # ~20 s of CPU work on 16 host threads
+    row_step = col_step = 6 if VIEW_ID == 5 else 4  # ~10-30 s of CPU work on 16 host threads
     t0 = time.time()
     iters, steps = oracle_cpu.render_lav2(RenderAlgorithm.GpuHDRx32PerturbedLAv2, WIDTH, HEIGHT, coords, orbit, la,
                                           n_iter, rows=(0, HEIGHT), col_step=col_step, row_step=row_step,
@@ -114,7 +126,7 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pixel-iters/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32 (HDRx32)",
-            "data": "synthetic (View #5 preset coordinates, orbit + LA table generated in-process)",
+            "data": f"synthetic (View #{VIEW_ID} preset coordinates, orbit + LA table generated in-process)",
             "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": value, "unit": "pixel-iters/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "pixel-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -129,7 +141,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--view", type=int, default=14, choices=[5, 14], help="view preset of the workload")
     args = ap.parse_args()
+    set_view(args.view)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -206,7 +220,10 @@ def main():
     # executed-step count for the roofline: one extra, untimed launch of the counting variant of the kernel
     r.EnableStepCounter(True)
     step_resident()
-    exec_steps = float(r.ReadStepCounter())
+    kinds = r.ReadStepCounters()
+    exec_steps = float(kinds["total"])
+    credited = float(kinds["at"] * FP32_INSTR_PER_AT_PASS + kinds["la"] * FP32_INSTR_PER_LA_STEP +
+                     kinds["perturbation"] * FP32_INSTR_PER_PERTURB_STEP)
     r.EnableStepCounter(False)
     stop.set()
     sampler.join()
@@ -232,9 +249,11 @@ def main():
         s = torch.tensor([local_sum], device="cuda", dtype=torch.int64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         total_sum = int(s.item())
-        es = torch.tensor([exec_steps], device="cuda", dtype=torch.float64)
+        es = torch.tensor([exec_steps, credited, kinds["at"], kinds["la"], kinds["perturbation"]], device="cuda",
+                          dtype=torch.float64)
         dist.all_reduce(es, op=dist.ReduceOp.SUM)
-        exec_steps = float(es.item())
+        exec_steps, credited = float(es[0].item()), float(es[1].item())
+        kinds = {"at": int(es[2].item()), "la": int(es[3].item()), "perturbation": int(es[4].item())}
         if rank == 0:
             merged = dev_iters.cpu().numpy().view(np.uint32)
             assert int(merged[:HEIGHT, :WIDTH].astype(np.int64).sum()) == total_sum
@@ -271,21 +290,22 @@ def main():
 
     # ---- roofline -----------------------------------------------------------------------------------------------
     peak = GPURenderer.MeasureFp32IssuePeak(local_rank)  # FFMA thread-instr/s, measured live
-    # executed steps are dominated by perturbation steps on this view (LA/AT steps < 1 %); credit 20 FP32 each
-    achieved = exec_steps * FP32_INSTR_PER_PERTURB_STEP / (ms_per_step * 1e-3)
+    achieved = credited / (ms_per_step * 1e-3)
     roofline = {"bound": "fp32_issue", "achieved": achieved / 1e12, "peak": peak * world / 1e12, "unit": "T FP32 instr/s",
                 "frac": achieved / (peak * world), "traffic": None,
                 "note": "compute-bound scalar path (SURVEY.md 8d): not HBM, not tensor. achieved = executed "
-                        "steps/launch (device counter) x 20 FP32 mantissa instr per HDRx32 step / kernel time; "
+                        "steps/launch by kind (device counters) x FP32 mantissa instr per step (AT pass 9, LA step 22, "
+                        "HDRx32 perturbation step 20) / kernel time; "
                         "peak = FFMA issue rate measured live by fs_measure_fp32_issue_peak on this GPU "
                         "(MEASURED_PEAKS.json has only HBM/bf16 peaks).",
                 "executed_steps_per_launch": exec_steps,
+                "executed_steps_by_kind": {k: int(kinds[k]) for k in ("at", "la", "perturbation")},
                 "skip_factor": total_sum / max(exec_steps, 1.0)}
 
     line = {"metric": METRIC, "value": value, "unit": "pixel-iters/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32+i32 (HDRx32)",
-            "data": "synthetic (View #5 preset coordinates; orbit via GMP + LA table generated in-process, untimed: "
+            "data": f"synthetic (View #{VIEW_ID} preset coordinates; orbit via GMP + LA table generated in-process, untimed: "
                     f"{gen_times['orbit_s']:.3f}s + {gen_times['la_s']:.3f}s)",
             "config": {"workload": WORKLOAD, "l2": "flushed between timed iterations (256 MiB memset)",
                        "sharding": f"4-row tile bands round-robin over {world} rank(s)",

@@ -707,9 +707,9 @@ uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, u
         cudaDeviceGetAttribute(&r->num_sms, cudaDevAttrMultiProcessorCount, r->device);
         err = cudaMallocAsync(&r->tile_counter, sizeof(unsigned int), r->compute);
         if (err != cudaSuccess) return err;
-        err = cudaMallocAsync(&r->step_counter, sizeof(unsigned long long), r->compute);
+        err = cudaMallocAsync(&r->step_counter, 4 * sizeof(unsigned long long), r->compute);
         if (err != cudaSuccess) return err;
-        cudaMemsetAsync(r->step_counter, 0, sizeof(unsigned long long), r->compute);
+        cudaMemsetAsync(r->step_counter, 0, 4 * sizeof(unsigned long long), r->compute);
     }
     if (r->cached_pal_host != pal || r->cached_pal_gen != pal_gen) {
         if (r->pal_dev) cudaFreeAsync(r->pal_dev, r->compute);
@@ -969,7 +969,7 @@ uint32_t fs_enable_step_counter(fs_renderer *r, int32_t enable) {
     if (!r || !r->compute) return FS_ERROR_UNSUPPORTED;
     DeviceGuard g(r->device);
     r->count_steps = enable != 0;
-    return cudaMemsetAsync(r->step_counter, 0, sizeof(unsigned long long), r->compute);
+    return cudaMemsetAsync(r->step_counter, 0, 4 * sizeof(unsigned long long), r->compute);
 }
 
 uint32_t fs_read_step_counter(fs_renderer *r, uint64_t *steps) {
@@ -980,6 +980,17 @@ uint32_t fs_read_step_counter(fs_renderer *r, uint64_t *steps) {
     if (err != cudaSuccess) return err;
     err = cudaStreamSynchronize(r->compute);
     *steps = v;
+    return err;
+}
+
+uint32_t fs_read_step_counters(fs_renderer *r, uint64_t *counters3) {
+    if (!r || !r->compute || !counters3) return FS_ERROR_UNSUPPORTED;
+    DeviceGuard g(r->device);
+    unsigned long long v[3] = {0, 0, 0};
+    cudaError_t err = cudaMemcpyAsync(v, r->step_counter, sizeof(v), cudaMemcpyDeviceToHost, r->compute);
+    if (err != cudaSuccess) return err;
+    err = cudaStreamSynchronize(r->compute);
+    counters3[0] = v[0]; counters3[1] = v[1]; counters3[2] = v[2];
     return err;
 }
 

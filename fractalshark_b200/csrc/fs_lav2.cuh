@@ -124,7 +124,7 @@ template <class Num> FS_D bool c_is_ge(typename Num::Real a, typename Num::Real 
 // ---- AT shortcut + LA stages of one pixel (LAKernel.cuh:66-127) ---------------------------------------------------
 template <class Num, class IterT, bool Count>
 FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, typename Num::Cplx &dz,
-                         IterT &RefIteration, IterT &iter, unsigned long long &steps) {
+                         IterT &RefIteration, IterT &iter, unsigned long long &steps_at, unsigned long long &steps) {
     using Real = typename Num::Real;
     using Cplx = typename Num::Cplx;
     using LA = LaRec<Num, IterT>;
@@ -152,6 +152,31 @@ FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx
                 const float s = MT<float>::pow2(E);
                 const float thr = R.m * MT<float>::pow2(sh);
                 float re = 0.0f, im = 0.0f;
+                // four passes per escape test: the running maximum of |z|^2 over the chunk decides whether any
+                // pass escaped (an overflowed pass shows as +inf before any NaN can form); if one did, the chunk
+                // is replayed pass by pass from its saved start to stop at the exact pass
+                // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
+                const f32x2 s2 = f2_make(s, s), c2 = f2_make(c.re, c.im);
+                while (i + 4 <= at_max) {
+                    const float re0 = re, im0 = im;
+                    float worst = 0.0f;
+                    f32x2 z2 = f2_make(re, im);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        float rr, ii;
+                        f2_split(f2_mul(z2, z2), rr, ii);
+                        worst = fmaxf(worst, rr + ii);
+                        const float t = fma_(re, im, re * im);
+                        z2 = f2_fma(f2_make(rr - ii, t), s2, c2);
+                        f2_split(z2, re, im);
+                    }
+                    if (!(worst <= thr)) {
+                        re = re0;
+                        im = im0;
+                        break;
+                    }
+                    i += 4;
+                }
                 for (; i < at_max; i++) {
                     const float rr = re * re, ii = im * im;
                     if (!(rr + ii <= thr)) break;
@@ -188,7 +213,7 @@ FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx
             z = add(z2, c);
             }
         }
-        if (Count) steps += i;
+        if (Count) steps_at += i;
         dz = mul(z, A.at.InvZCoeff);
         reduce(dz);
         iter = i * A.at.StepLength;
@@ -247,7 +272,7 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
     const int tiles_x = (A.width + 7) >> 3;
     const int tiles_y = (((A.height + 3) >> 2) - A.shard_index + A.shard_count - 1) / A.shard_count;
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
-    unsigned long long steps = 0;
+    unsigned long long steps = 0, steps_at = 0, steps_la = 0;
 
     for (;;) {
         unsigned int tile = 0;
@@ -270,7 +295,7 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
 
         if constexpr (Mode == Lav2Mode::Full || Mode == Lav2Mode::LAO) {
             if (live) {
-                lav2_la_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps);
+                lav2_la_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps_at, steps_la);
             }
         }
 
@@ -285,9 +310,16 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
     }
 
     if (Count && A.step_counter) {
-        // one atomic per warp
-        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        // one atomic per warp and counter: [0] all executed steps, [1] AT passes, [2] LA steps
+        steps += steps_at + steps_la;
+        for (int o = 16; o > 0; o >>= 1) {
+            steps += __shfl_down_sync(0xffffffffu, steps, o);
+            steps_at += __shfl_down_sync(0xffffffffu, steps_at, o);
+            steps_la += __shfl_down_sync(0xffffffffu, steps_la, o);
+        }
         if (lane == 0 && steps) atomicAdd(A.step_counter, steps);
+        if (lane == 0 && steps_at) atomicAdd(A.step_counter + 1, steps_at);
+        if (lane == 0 && steps_la) atomicAdd(A.step_counter + 2, steps_la);
     }
 }
 

@@ -118,6 +118,27 @@ FS_HD double fma_(double a, double b, double c) {
 #endif
 }
 
+// Packed binary32 pairs (sm_100 FMUL2 / FADD2 / FFMA2): two independent IEEE operations per issued instruction,
+// each lane rounded exactly like its scalar counterpart.  Device only.
+#ifdef __CUDACC__
+struct f32x2 {
+    unsigned long long v;
+};
+FS_D f32x2 f2_make(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+FS_D void f2_split(f32x2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+FS_D f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+FS_D f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+FS_D f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // Mantissa traits: 2^s multipliers and exponent-field surgery, all integer ALU.
 // getMultiplier    HDRFloat.h:497-521   s<=-127 -> 0 ; s>=128 -> FLT_MAX ; else 2^s

@@ -188,6 +188,15 @@ class GPURenderer:
     def EnableStepCounter(self, enable: bool = True) -> int:
         return int(self._lib.fs_enable_step_counter(self._h, int(enable)))
 
+    def ReadStepCounters(self) -> dict:
+        """Executed steps of the renders since EnableStepCounter(True), split by kind."""
+        v = (C.c_uint64 * 3)()
+        rc = self._lib.fs_read_step_counters(self._h, v)
+        if rc:
+            raise RuntimeError(self.ConvertErrorToString(rc))
+        total, at, la = int(v[0]), int(v[1]), int(v[2])
+        return {"total": total, "at": at, "la": la, "perturbation": total - at - la}
+
     def ReadStepCounter(self) -> int:
         v = C.c_uint64(0)
         rc = self._lib.fs_read_step_counter(self._h, C.byref(v))

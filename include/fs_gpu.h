@@ -160,6 +160,9 @@ uint32_t fs_last_render_ms(fs_renderer *r, float *ms);
 /* Count executed steps (perturbation + LA + AT) of subsequent renders into a device counter. */
 uint32_t fs_enable_step_counter(fs_renderer *r, int32_t enable);
 uint32_t fs_read_step_counter(fs_renderer *r, uint64_t *steps);
+/* Same, split: counters3[0] = all executed steps, [1] = AT passes, [2] = LA steps (the LAv2 kernel fills 1 and 2;
+ * perturbation steps = [0] - [1] - [2]). */
+uint32_t fs_read_step_counters(fs_renderer *r, uint64_t *counters3);
 /* HDRx32 perturbation: 1 (default) = scaled plain-float chunks with float+exponent fallback
  * (fs_scaled_loop.cuh), 0 = pure float+exponent loop.  Results are identical; takes effect at the next
  * InitializePerturb upload.  A/B switch for tests and profiling. */
