@@ -75,13 +75,21 @@ SMALL_CASES_5 = [
     ("v5_hdr2x32_rclav2", 5, 64, 36, A.GpuHDRx2x32PerturbedRCLAv2, None, 4),
     ("v1_hdr2x32_rclav2_lao_u64", 1, 50, 37, A.GpuHDRx2x32PerturbedRCLAv2LAO, None, 8),
 ]
+# sixth fixture file (tests/golden/ref_gpu_small6.npz): View 14, the north_star target view (21.7-kbit orbit)
+SMALL_CASES_6 = [
+    ("v14_hdr32_lav2", 14, 96, 54, A.GpuHDRx32PerturbedLAv2, None, 4),
+    ("v14_hdr32_lav2_lao_u64", 14, 50, 37, A.GpuHDRx32PerturbedLAv2LAO, None, 8),
+    ("v14_hdr32_rclav2", 14, 64, 36, A.GpuHDRx32PerturbedRCLAv2, None, 4),
+    ("v14_hdr32_bla", 14, 64, 36, A.GpuHDRx32PerturbedBLA, None, 4),
+]
 # Gpu4x32 / Gpu4x64: the four-limb products are split exactly here (one FMA) while the reference build leaves a
 # Dekker split to the compiler's contraction (fs_qd.cuh); frames agree to >= 99.9 % of pixels, not bit for bit.
 NOT_BIT_EXACT = {"v0_gpu4x32": 0.999, "v0_gpu4x64": 0.999}
-ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3 + SMALL_CASES_4 + SMALL_CASES_5
-CASE_SETS = {"1": SMALL_CASES, "2": SMALL_CASES_2, "3": SMALL_CASES_3, "4": SMALL_CASES_4, "5": SMALL_CASES_5}
+ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3 + SMALL_CASES_4 + SMALL_CASES_5 + SMALL_CASES_6
+CASE_SETS = {"1": SMALL_CASES, "2": SMALL_CASES_2, "3": SMALL_CASES_3, "4": SMALL_CASES_4, "5": SMALL_CASES_5,
+             "6": SMALL_CASES_6}
 GOLDEN_FILES = {"1": "ref_gpu_small.npz", "2": "ref_gpu_small2.npz", "3": "ref_gpu_small3.npz",
-                "4": "ref_gpu_small4.npz", "5": "ref_gpu_small5.npz"}
+                "4": "ref_gpu_small4.npz", "5": "ref_gpu_small5.npz", "6": "ref_gpu_small6.npz"}
 
 
 def golden_file_of(name):
@@ -146,10 +154,29 @@ def oracle_render(alg, w, h, coords, orbit, table, n, ib, **kw):
         return None
 
 
+_ORBIT_CACHE = {}
+
+
+def _cached_orbit(view, view_id, numeric, n_iter):
+    """The reference orbit depends on the view's centre, radius and precision, not on the pixel grid: computed once
+    per (view, numeric type, iteration cap) -- View 14's 21.7-kbit orbit takes several seconds."""
+    from fractalshark_b200.host_inputs import Orbit
+    key = (view_id, int(numeric), int(n_iter))
+    if key not in _ORBIT_CACHE:
+        if len(_ORBIT_CACHE) > 12:
+            _ORBIT_CACHE.clear()
+        _ORBIT_CACHE[key] = Orbit(view, numeric, n_iter, True)
+    return _ORBIT_CACHE[key]
+
+
 def make_inputs(view_id, w, h, alg, n_iter, iter_bytes):
     from fractalshark_b200 import traits
-    from fractalshark_b200.host_inputs import LaTable, Orbit, View
+    from fractalshark_b200.host_inputs import LaTable, View
     from fractalshark_b200.views import PRESETS
+
+    def Orbit(view, numeric, n, _periodicity):
+        return _cached_orbit(view, view_id, numeric, n)
+
     p = PRESETS[view_id]
     n_iter = n_iter or p.num_iterations
     t = traits(alg)
