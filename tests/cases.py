@@ -158,10 +158,12 @@ _ORBIT_CACHE = {}
 
 
 def _cached_orbit(view, view_id, numeric, n_iter):
-    """The reference orbit depends on the view's centre, radius and precision, not on the pixel grid: computed once
-    per (view, numeric type, iteration cap) -- View 14's 21.7-kbit orbit takes several seconds."""
+    """The reference orbit depends on the view's centre, radius (after the aspect-ratio squaring of the bounds) and
+    precision, not on the pixel count: computed once per (view, aspect ratio, numeric type, iteration cap) --
+    View 14's 21.7-kbit orbit takes several seconds."""
+    from fractions import Fraction
     from fractalshark_b200.host_inputs import Orbit
-    key = (view_id, int(numeric), int(n_iter))
+    key = (view_id, Fraction(view.width, view.height), int(numeric), int(n_iter))
     if key not in _ORBIT_CACHE:
         if len(_ORBIT_CACHE) > 12:
             _ORBIT_CACHE.clear()
