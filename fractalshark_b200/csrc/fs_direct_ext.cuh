@@ -164,8 +164,10 @@ __global__ void __launch_bounds__(256) direct_ext_kernel(const DirectExtArgs<typ
         if (lane == 0) tile = atomicAdd(A.tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
-        const int X = (int)(tile % tiles_x) * 8 + (lane & 7);
-        const int Y = ((int)(tile / tiles_x) * A.shard_count + A.shard_index) * 4 + (lane >> 3);
+        int X, Y;
+        tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Y);
+        X += lane & 7;
+        Y += lane >> 3;
         if (X < A.width && Y < A.height) {
             const IterT iter = Pixel::template run<IterT>(A, X, Y);
             steps += iter;

@@ -280,8 +280,10 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
 
-        const int X = (int)(tile % tiles_x) * 8 + (lane & 7);
-        const int Y = ((int)(tile / tiles_x) * A.shard_count + A.shard_index) * 4 + (lane >> 3);
+        int X, Y;
+        tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Y);
+        X += lane & 7;
+        Y += lane >> 3;
         // lanes outside the image stay with the warp (the perturbation loop is warp-synchronous) and do nothing
         const bool live = X < A.width && Y < A.height;
 
