@@ -66,6 +66,7 @@ GPU_SYMBOLS = {
     "fs_read_step_counter": (_U32, [_V, C.POINTER(_U64)]),
     "fs_read_step_counters": (_U32, [_V, C.POINTER(_U64)]),
     "fs_set_scaled_steps": (_U32, [_V, _I32]),
+    "fs_set_split_at": (_U32, [_V, _I32]),
     "fs_device_iter_buffer": (_V, [_V]),
     "fs_kernel_launch_count": (_U64, [_V]),
 }

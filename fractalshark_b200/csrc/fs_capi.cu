@@ -99,6 +99,9 @@ struct fs_renderer {
     unsigned int *tile_counter = nullptr;
     unsigned long long *step_counter = nullptr;
     bool count_steps = false;
+    bool split_at = false;  // HDRx32 + AT: AT shortcut in its own launch ahead of the LA/perturbation launch (fs_lav2.cuh AtPhase);
+                            // measured slower than the fused launch (View 14: 9.7 vs 8.5 ms), kept as an A/B switch
+    DeviceBlob at_state;    // float4 per iteration-buffer cell, allocated on first use
     bool use_scaled = true; // HDRx32: scaled plain-float chunks (fs_scaled_loop.cuh); off = pure float+exponent loop
     OrbitDev orbit1, orbit2;
     OrbitDev bla_orbit;                  // RenderPerturbBLA uploads its orbit and table per call (GPU_Render.cu:1462-1483)
@@ -148,6 +151,7 @@ void reset_perturb(fs_renderer *r) {
 }
 
 void reset_buffers(fs_renderer *r) {
+    free_blob(r, r->at_state);
     if (r->iter_buf) cudaFreeAsync(r->iter_buf, r->compute);
     if (r->red_dev) cudaFreeAsync(r->red_dev, r->compute);
     if (r->color_buf) cudaFreeAsync(r->color_buf, r->compute);
@@ -427,8 +431,35 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     A.n_iterations = (IterT)n_iter;
     A.tile_counter = r->tile_counter;
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
-    begin_render(r);
     const bool count = r->count_steps;
+    // two-launch form (AT, then everything else) for the float+exponent binary32 type when the table has an AT block
+    if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4) {
+        if (r->split_at && have_la && A.la_valid && A.use_at && (mode == FS_LAV2_FULL || mode == FS_LAV2_LAO)) {
+            const size_t need = r->n_cu * sizeof(float4);
+            if (r->at_state.bytes < need) {
+                free_blob(r, r->at_state);
+                cudaError_t e = cudaMallocAsync(&r->at_state.ptr, need, r->compute);
+                if (e != cudaSuccess) return e;
+                r->at_state.bytes = need;
+            }
+            A.at_state = static_cast<float4 *>(r->at_state.ptr);
+            begin_render(r);
+#define FS_LAUNCH_SPLIT(MODE, COUNT)                                                                                   \
+    {                                                                                                                  \
+        auto ka = lav2_kernel<Num, IterT, MODE, COUNT, AtPhase::AtOnly>;                                               \
+        ka<<<resident_ctas(r, ka), 256, 0, r->compute>>>(A);                                                           \
+        cudaMemsetAsync(r->tile_counter, 0, sizeof(unsigned int), r->compute);                                        \
+        auto kb = lav2_kernel<Num, IterT, MODE, COUNT, AtPhase::AfterAt>;                                              \
+        kb<<<resident_ctas(r, kb), 256, 0, r->compute>>>(A);                                                           \
+    }
+            if (mode == FS_LAV2_FULL) { if (count) FS_LAUNCH_SPLIT(Lav2Mode::Full, true) else FS_LAUNCH_SPLIT(Lav2Mode::Full, false) }
+            else { if (count) FS_LAUNCH_SPLIT(Lav2Mode::LAO, true) else FS_LAUNCH_SPLIT(Lav2Mode::LAO, false) }
+#undef FS_LAUNCH_SPLIT
+            r->launches++;
+            return end_render(r);
+        }
+    }
+    begin_render(r);
 #define FS_LAUNCH_LAV2(MODE)                                                                                           \
     if (count) { auto k = lav2_kernel<Num, IterT, MODE, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }     \
     else { auto k = lav2_kernel<Num, IterT, MODE, false>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
@@ -1023,6 +1054,12 @@ uint32_t fs_measure_fp32_issue_peak(int32_t device, double *ffma_per_second) {
     cudaFree(sink);
     *ffma_per_second = best;
     return err;
+}
+
+uint32_t fs_set_split_at(fs_renderer *r, int32_t enable) {
+    if (!r) return FS_ERROR_UNSUPPORTED;
+    r->split_at = enable != 0;
+    return 0;
 }
 
 uint32_t fs_set_scaled_steps(fs_renderer *r, int32_t enable) {

@@ -60,7 +60,18 @@ template <class Num, class IterT> struct Lav2Args {
     IterT n_iterations;
     unsigned int *tile_counter;
     unsigned long long *step_counter; // optional: executed perturbation/LA/AT steps (bench roofline)
+    float4 *at_state;                 // HDRx32 two-launch form: per-pixel AT result {dz.re, dz.im, dz.e}; iter sits in `out`
 };
+
+// How a launch treats the AT shortcut.  Fused = one launch does everything (the reference's structure).  On deep views
+// the AT loop is most of the frame and perfectly regular (every interior pixel runs n/StepLength passes) while what
+// follows it is short and divergent; run back to back inside one warp-tile they serialise (the tile lasts AT + the
+// slowest lane's LA/perturbation tail), which is what bounds a launch once a GPU's share of the frame is small.
+// AtOnly / AfterAt split the frame into two launches over the same tile queue: the first leaves {dz, iter} per pixel
+// (16 B + the iteration cell), the second picks them up.  Same arithmetic, same results.  Measured on View 14 the
+// split is SLOWER (9.7 vs 8.5 ms; 8-way shard 2.03 vs 1.30 ms): each launch pays its own ramp and drain, which is
+// what dominates at that grain, so Fused stays the default (fs_set_split_at is an A/B switch).
+enum class AtPhase : int { Fused = 0, AtOnly = 1, AfterAt = 2 };
 
 // ---- orbit element fetch ----------------------------------------------------------------------
 template <class Num> struct OrbitIO;
@@ -121,14 +132,12 @@ template <> struct OrbitIO<NumHdr2x32> {
 // ---- small vocabulary shims so the kernel reads the same for plain and HDR numbers ------------
 template <class Num> FS_D bool c_is_ge(typename Num::Real a, typename Num::Real b) { return ge_pr(a, b); }
 
-// ---- AT shortcut + LA stages of one pixel (LAKernel.cuh:66-127) ---------------------------------------------------
+// ---- AT shortcut of one pixel (LAKernel.cuh:66-89, ATInfo.h:128-188) -----------------------------------------------
 template <class Num, class IterT, bool Count>
-FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, typename Num::Cplx &dz,
-                         IterT &RefIteration, IterT &iter, unsigned long long &steps_at, unsigned long long &steps) {
+FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, typename Num::Cplx &dz, IterT &iter,
+                  unsigned long long &steps_at) {
     using Real = typename Num::Real;
     using Cplx = typename Num::Cplx;
-    using LA = LaRec<Num, IterT>;
-    // ---- AT (ATInfo.h:128-188) ----
     if (A.la_valid && A.use_at && le_pr(cheb(dc), A.at.ThresholdC)) {
         const IterT at_max = A.n_iterations / A.at.StepLength;
         Cplx c = add(mul(dc, A.at.CCoeff), A.at.RefC);
@@ -219,7 +228,15 @@ FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx
         iter = i * A.at.StepLength;
     }
 
-    // ---- LA stages (LAKernel.cuh:91-127) ----
+}
+
+// ---- LA stages of one pixel (LAKernel.cuh:91-127) ---------------------------------------------------------------
+template <class Num, class IterT, bool Count>
+FS_D void lav2_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, typename Num::Cplx &dz,
+                      IterT &RefIteration, IterT &iter, unsigned long long &steps) {
+    using Real = typename Num::Real;
+    using Cplx = typename Num::Cplx;
+    using LA = LaRec<Num, IterT>;
     IterT stage = A.la_valid ? A.la_stage_count : 0;
     while (stage > 0) {
         stage--;
@@ -263,7 +280,7 @@ FS_D void lav2_la_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx
     }
 }
 
-template <class Num, class IterT, Lav2Mode Mode, bool Count>
+template <class Num, class IterT, Lav2Mode Mode, bool Count, AtPhase Phase = AtPhase::Fused>
 __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A) {
     using Real = typename Num::Real;
     using Cplx = typename Num::Cplx;
@@ -295,9 +312,29 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
         const Cplx dc = Num::c_make(dcX, dcY);
         Cplx dz = Num::c_zero();
 
+        if constexpr (Phase == AtPhase::AtOnly) {
+            if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4) {
+                if (live) {
+                    lav2_at<Num, IterT, Count>(A, dc, dz, iter, steps_at);
+                    const size_t cell = (size_t)Y * A.pitch + X;
+                    A.at_state[cell] = make_float4(dz.re, dz.im, __int_as_float(dz.e), 0.0f);
+                    A.out[cell] = iter;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         if constexpr (Mode == Lav2Mode::Full || Mode == Lav2Mode::LAO) {
             if (live) {
-                lav2_la_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps_at, steps_la);
+                if constexpr (Phase == AtPhase::AfterAt && Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4) {
+                    const size_t cell = (size_t)Y * A.pitch + X;
+                    const float4 st = A.at_state[cell];
+                    dz.re = st.x; dz.im = st.y; dz.e = __float_as_int(st.z);
+                    iter = A.out[cell];
+                } else {
+                    lav2_at<Num, IterT, Count>(A, dc, dz, iter, steps_at);
+                }
+                lav2_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps_la);
             }
         }
 

@@ -208,6 +208,10 @@ class GPURenderer:
         """A/B switch of the HDRx32 perturbation loop (same results either way); applies to the next upload."""
         return int(self._lib.fs_set_scaled_steps(self._h, int(enable)))
 
+    def SetSplitAt(self, enable: bool = True) -> int:
+        """A/B switch: AT shortcut of the HDRx32 LAv2 path in its own launch (default) or fused (same results)."""
+        return int(self._lib.fs_set_split_at(self._h, int(enable)))
+
     def DeviceIterBuffer(self) -> int:
         return int(self._lib.fs_device_iter_buffer(self._h) or 0)
 

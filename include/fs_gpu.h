@@ -167,6 +167,9 @@ uint32_t fs_read_step_counters(fs_renderer *r, uint64_t *counters3);
  * (fs_scaled_loop.cuh), 0 = pure float+exponent loop.  Results are identical; takes effect at the next
  * InitializePerturb upload.  A/B switch for tests and profiling. */
 uint32_t fs_set_scaled_steps(fs_renderer *r, int32_t enable);
+/* HDRx32 LAv2 with an AT block: 1 = the AT shortcut runs in its own launch ahead of the LA/perturbation launch;
+ * 0 (default) = one fused launch as in the reference.  Results are identical; the fused form measured faster. */
+uint32_t fs_set_split_at(fs_renderer *r, int32_t enable);
 /* Device pointer of the iteration buffer (for NCCL gather by the host plumbing). */
 void *fs_device_iter_buffer(fs_renderer *r);
 /* Number of kernels this renderer has launched so far. */

@@ -11,6 +11,9 @@ view, coords, orbit, la, n_iter, _ = bench.build_inputs(3840, 2160)
 r = GPURenderer(0)
 assert r.InitializeMemory(3840, 2160, 1, iter_bytes=4) == 0
 assert r.InitializePerturb(1, orbit, 0, None, la) == 0
+split = "--fused" not in sys.argv
+assert r.SetSplitAt(split) == 0
+print("split AT launch" if split else "fused launch", flush=True)
 for world in (1, 2, 4, 8):
     ms = []
     for s in range(world):

@@ -199,6 +199,26 @@ def test_scaled_chunks_equal_float_exponent_loop(view_id, w, h, alg, n_iter):
     assert steps[0] == steps[1]
 
 
+def test_split_and_fused_at_launches_agree():
+    """The two-launch form of the HDRx32 LAv2 path (AT shortcut first) gives the same frame as the fused launch."""
+    w, h, alg = 960, 540, A.GpuHDRx32PerturbedLAv2
+    for view_id in (14, 5):
+        _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, None, 4)
+        outs = []
+        for split in (True, False):
+            r = GPURenderer()
+            assert r.SetSplitAt(split) == 0
+            assert r.InitializeMemory(w, h, 1, iter_bytes=4) == 0
+            assert r.InitializePerturb(1, orbit, 0, None, la) == 0
+            r.ClearMemory()
+            assert r.RenderPerturbLAv2(alg, coords, n) == 0
+            rc, it, _, _ = r.RenderCurrent(n)
+            assert rc == 0
+            outs.append(it.copy())
+            r.close()
+        np.testing.assert_array_equal(outs[0], outs[1])
+
+
 def test_error_behaviour_matches_reference():
     """Error codes and no-op-before-init behaviour (GPU_Render.cu:322-332, 626-628, 1007-1022)."""
     r = GPURenderer()
