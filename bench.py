@@ -262,12 +262,14 @@ def main():
     value = total_sum / (ms_per_step * 1e-3)
 
     # ---- e2e: public call sequence with host buffers (every step re-uploads orbit + LA, reads results) ------
+    pinned_iters = torch.empty((hp, wp), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+
     def step_e2e(g):
         rc = r.InitializePerturb(g, orbit, 0, None, la)
         assert rc == 0
         r.ClearMemory()
         assert r.RenderPerturbLAv2(alg, coords, n_iter) == 0
-        rc, it, _, rd = r.RenderCurrent(n_iter)
+        rc, it, _, rd = r.RenderCurrent(n_iter, iters_out=pinned_iters)
         assert rc == 0
         return rd["Sum"]
 

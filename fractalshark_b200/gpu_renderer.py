@@ -125,11 +125,17 @@ class GPURenderer:
         return _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)
 
     def RenderCurrent(self, n_iterations: int, want_iters: bool = True, want_colors: bool = False,
-                      progressive: bool = False):
-        """Returns ``(status, iters, colors, reduction)``; arrays are padded like the reference's buffers."""
+                      progressive: bool = False, iters_out=None):
+        """Returns ``(status, iters, colors, reduction)``; arrays are padded like the reference's buffers.
+        ``iters_out``: caller-owned host array of the padded shape to receive the iteration buffer (e.g. pinned
+        memory); the C-ABI borrows whatever pointer it is given, as the reference does (GPU_Render.cu:1768-1788)."""
         hp, wp = self.buffer_shape()
         dt = np.uint32 if self._iter_bytes == 4 else np.uint64
-        iters = np.empty((hp, wp), dtype=dt) if want_iters else None
+        if iters_out is not None:
+            assert iters_out.shape == (hp, wp) and iters_out.dtype == dt and iters_out.flags["C_CONTIGUOUS"]
+            iters, want_iters = iters_out, True
+        else:
+            iters = np.empty((hp, wp), dtype=dt) if want_iters else None
         colors = None
         if want_colors:
             aa = self._aa()
