@@ -97,7 +97,7 @@ def cpu_port_sample(coords, orbit, la, n_iter, threads):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_cpu
     from fractalshark_b200 import RenderAlgorithm
-    row_step = col_step = 6 if VIEW_ID == 5 else 4  # ~10-30 s of CPU work on 16 host threads
+    row_step = col_step = 6 if VIEW_ID == 5 else 2  # ~10-30 s of CPU work on 16 host threads
     t0 = time.time()
     iters, steps = oracle_cpu.render_lav2(RenderAlgorithm.GpuHDRx32PerturbedLAv2, WIDTH, HEIGHT, coords, orbit, la,
                                           n_iter, rows=(0, HEIGHT), col_step=col_step, row_step=row_step,

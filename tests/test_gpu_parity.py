@@ -241,6 +241,56 @@ def test_error_behaviour_matches_reference():
     r.close()
 
 
+EDGE_CASES = [
+    # (view, w, h, algorithm, n_iter, iter_bytes): degenerate and ragged frames, iteration limits 0/1/2, tiny orbits
+    (5, 1, 1, A.GpuHDRx32PerturbedLAv2, None, 4),
+    (5, 17, 9, A.GpuHDRx32PerturbedLAv2, None, 8),
+    (5, 33, 5, A.GpuHDRx32PerturbedRCLAv2, None, 4),
+    (5, 16, 8, A.GpuHDRx32PerturbedLAv2, 1, 4),
+    (5, 16, 8, A.GpuHDRx32PerturbedLAv2PO, 2, 4),
+    (5, 16, 8, A.GpuHDRx32PerturbedBLA, 3, 4),
+    (100, 19, 7, A.Gpu1x32PerturbedScaled, 5, 4),
+    (19, 9, 3, A.GpuHDRx32PerturbedScaled, 50000, 8),
+    (100, 15, 9, A.Gpu2x32PerturbedRCLAv2LAO, None, 4),
+    (0, 7, 3, A.Gpu2x32, 64, 4),
+    (0, 3, 5, A.Gpu4x64, 32, 8),
+    (0, 1, 1, A.Gpu1x64, 10, 4),
+]
+
+
+@pytest.mark.skipif(not ref_renderer.available(), reason="oracle/_ref (reference CUDA kernels) not built")
+@pytest.mark.parametrize("case", EDGE_CASES, ids=[f"v{c[0]}_{c[1]}x{c[2]}_{c[3].name}_{c[4]}" for c in EDGE_CASES])
+def test_edge_shapes_and_limits_vs_reference_kernels(case):
+    """1x1 and ragged frames (not multiples of the 16x8 padding or of the 8x4 work tile), iteration limits of a
+    few steps, both iteration widths: same buffers as the reference kernels, padding cells left cleared."""
+    view_id, w, h, alg, n_iter, ib = case
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
+    got, _, red = cases.render(GPURenderer, w, h, alg, coords, orbit, la, n, ib)
+    ref, _, ref_red = cases.render(ref_renderer.RefGPURenderer, w, h, alg, coords, orbit, la, n, ib)
+    np.testing.assert_array_equal(got[:h, :w], ref[:h, :w])
+    assert not got[h:, :].any() and not got[:, w:].any()
+    assert (red["Min"], red["Max"], red["Sum"]) == (ref_red["Min"], ref_red["Max"], ref_red["Sum"])
+
+
+def test_scaled_and_compressed_entry_points_reject_what_the_reference_does_not_instantiate():
+    _, coords, orbit, la, n = cases.make_inputs(100, 32, 16, A.Gpu1x32PerturbedScaled, None, 4)
+    r = GPURenderer()
+    assert r.RenderPerturbBLAScaled(A.Gpu1x32PerturbedScaled, orbit, la, coords, n) == 0   # not initialised: no-op
+    assert r.InitializeMemory(32, 16, 1) == 0
+    assert r.RenderPerturbBLAScaled(A.Gpu1x32PerturbedScaled, orbit, la, coords, n) == 0
+    # orbits of different length (GPU_Render.cu / Fractal.cpp:2909-2912 "Mismatch on size")
+    _, _, orbit2, la2, _ = cases.make_inputs(101, 32, 16, A.Gpu1x32PerturbedScaled, None, 4)
+    assert r.RenderPerturbBLAScaled(A.Gpu1x32PerturbedScaled, orbit, la2, coords, n) == 10100
+    # a compressed orbit without OrbitXLow/YLow cannot be replayed
+    _, c5, o5, l5, n5 = cases.make_inputs(5, 32, 16, A.GpuHDRx32PerturbedRCLAv2, None, 4)
+    d = o5.descriptor()
+    d.orbit_x_low = None
+    import ctypes as C
+    rc = r._lib.fs_initialize_perturb(r._h, 4, int(o5.numeric), 2, 9, C.byref(d), 0, 0, None, None)
+    assert rc == 10005
+    r.close()
+
+
 def test_native_library_is_the_one_loaded():
     """The CUDA path is the one that ran: libfsgpu.so is mapped into this process."""
     maps = open("/proc/self/maps").read()
