@@ -161,17 +161,18 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                 const float s = MT<float>::pow2(E);
                 const float thr = R.m * MT<float>::pow2(sh);
                 float re = 0.0f, im = 0.0f;
-                // four passes per escape test: the running maximum of |z|^2 over the chunk decides whether any
+                // sixteen passes per escape test: the running maximum of |z|^2 over the chunk decides whether any
                 // pass escaped (an overflowed pass shows as +inf before any NaN can form); if one did, the chunk
                 // is replayed pass by pass from its saved start to stop at the exact pass
                 // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
                 const f32x2 s2 = f2_make(s, s), c2 = f2_make(c.re, c.im);
-                while (i + 4 <= at_max) {
+                constexpr int kAtChunk = 16;
+                while (i + kAtChunk <= at_max) {
                     const float re0 = re, im0 = im;
                     float worst = 0.0f;
                     f32x2 z2 = f2_make(re, im);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < kAtChunk; u++) {
                         float rr, ii;
                         f2_split(f2_mul(z2, z2), rr, ii);
                         worst = fmaxf(worst, rr + ii);
@@ -184,7 +185,7 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                         im = im0;
                         break;
                     }
-                    i += 4;
+                    i += kAtChunk;
                 }
                 for (; i < at_max; i++) {
                     const float rr = re * re, ii = im * im;
