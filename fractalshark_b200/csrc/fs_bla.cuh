@@ -53,20 +53,6 @@ template <class Num, class IterT> struct BlaArgs {
     unsigned long long *step_counter;
 };
 
-// 16-byte vector loads of an aligned record
-template <class T> FS_D T ldg_rec(const T *p) {
-    static_assert(sizeof(T) % 16 == 0, "record size");
-    union U {
-        T t;
-        uint4 v[sizeof(T) / 16];
-        FS_D U() {}
-    } u;
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) u.v[i] = __ldg(q + i);
-    return u.t;
-}
-
 // device-side repack of one level: wire records -> heads + coefs
 template <class Num>
 __global__ void __launch_bounds__(256) bla_repack_kernel(const BlaWire<Num> *__restrict__ src, unsigned long long count,

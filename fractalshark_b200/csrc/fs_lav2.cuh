@@ -73,6 +73,20 @@ template <class Num, class IterT> struct Lav2Args {
 // what dominates at that grain, so Fused stays the default (fs_set_split_at is an A/B switch).
 enum class AtPhase : int { Fused = 0, AtOnly = 1, AfterAt = 2 };
 
+// 16-byte vector loads of an aligned record (one LDG.128 per 16 bytes instead of one load per field)
+template <class T> FS_D T ldg_rec(const T *p) {
+    static_assert(sizeof(T) % 16 == 0, "record size");
+    union U {
+        T t;
+        uint4 v[sizeof(T) / 16];
+        FS_D U() {}
+    } u;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) u.v[i] = __ldg(q + i);
+    return u.t;
+}
+
 // ---- orbit element fetch ----------------------------------------------------------------------
 template <class Num> struct OrbitIO;
 
@@ -248,26 +262,28 @@ FS_D void lav2_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc
         IterT j = RefIteration;
 
         while (iter < A.n_iterations) {
-            // getLA  GPU_LAReference.h:271-303
-            const LA *rec = A.las + (LAIndex + j);
-            const IterT l = rec->StepLength;
+            // getLA  GPU_LAReference.h:271-303.  The record is fetched whole with 128-bit loads (the reference, and a
+            // field-by-field read here, issue one 32-bit load per member: 15 per step).
+            const LA *recp = A.las + (LAIndex + j);
+            const LA rec = ldg_rec(recp);
+            const IterT l = rec.StepLength;
             bool unusable = true;
             Cplx newdz;
             if (iter + l <= A.n_iterations) {
                 // Prepare  GPU_LAInfoDeep.h:90-105: newdz = dz * (2*Ref + dz), reduced
-                newdz = mul(dz, add(Num::c_mul2(rec->Ref), dz));
+                newdz = mul(dz, add(Num::c_mul2(rec.Ref), dz));
                 reduce(newdz);
-                unusable = ge_pr(cheb(newdz), rec->LAThreshold);
+                unusable = ge_pr(cheb(newdz), rec.LAThreshold);
             }
             if (unusable) {
-                RefIteration = rec->NextStageLAIndex;
+                RefIteration = rec.NextStageLAIndex;
                 break;
             }
             iter += l;
             if (Count) steps++;
             // Evaluate  GPU_LAInfoDeep.h:120-123 ; getZ  LAstep.h:181-185
-            dz = add(mul(newdz, rec->ZCoeff), mul(dc, rec->CCoeff));
-            const Cplx z = add(rec[1].Ref, dz);
+            dz = add(mul(newdz, rec.ZCoeff), mul(dc, rec.CCoeff));
+            const Cplx z = add(recp[1].Ref, dz);
             j++;
             Real zn = cheb(z), dn = cheb(dz);
             reduce(zn);
