@@ -97,7 +97,7 @@ def cpu_port_sample(coords, orbit, la, n_iter, threads):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_cpu
     from fractalshark_b200 import RenderAlgorithm
-    row_step = col_step = 6 if VIEW_ID == 5 else 2  # ~10-30 s of CPU work on 16 host threads
+    row_step = col_step = 6 if VIEW_ID == 5 else 1  # ~10-30 s of CPU work on 16 host threads
     t0 = time.time()
     iters, steps = oracle_cpu.render_lav2(RenderAlgorithm.GpuHDRx32PerturbedLAv2, WIDTH, HEIGHT, coords, orbit, la,
                                           n_iter, rows=(0, HEIGHT), col_step=col_step, row_step=row_step,
@@ -294,7 +294,10 @@ def main():
     peak = GPURenderer.MeasureFp32IssuePeak(local_rank)  # FFMA thread-instr/s, measured live
     achieved = credited / (ms_per_step * 1e-3)
     roofline = {"bound": "fp32_issue", "achieved": achieved / 1e12, "peak": peak * world / 1e12, "unit": "T FP32 instr/s",
-                "frac": achieved / (peak * world), "traffic": None,
+                "frac": achieved / (peak * world),
+                # dram__bytes_read.sum + dram__bytes_write.sum of the render kernel, one `ncu --set full` capture per view
+                # (profiles/r1_lav2_v10_view14_summary.md, r1_lav2_v7_summary.md); bytes per launch
+                "traffic": {14: 5.47e6 + 0.18e6, 5: 0.69e6 + 0.09e6}.get(VIEW_ID),
                 "note": "compute-bound scalar path (SURVEY.md 8d): not HBM, not tensor. achieved = executed "
                         "steps/launch by kind (device counters) x FP32 mantissa instr per step (AT pass 9, LA step 22, "
                         "HDRx32 perturbation step 20) / kernel time; "
