@@ -167,15 +167,38 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     alg = RenderAlgorithm.GpuHDRx32PerturbedLAv2
-    view, coords, orbit, la, n_iter, gen_times = build_inputs(WIDTH, HEIGHT)
+    from fractalshark_b200.host_inputs import ReplicatedInputs
 
-    # ---- replicate the orbit + LA blob with an NCCL broadcast (north_star) -------------------------------
-    orbit_np = orbit.as_numpy()
+    # ---- inputs: produced once on rank 0 (GMP orbit, LA table), replicated to the other ranks with NCCL broadcasts
+    # of the packed blobs (north_star); receivers upload straight from the received host buffers -------------------
+    bcast_ms = None
+    if rank == 0:
+        view, coords, orbit, la, n_iter, gen_times = build_inputs(WIDTH, HEIGHT)
     if world > 1:
-        blob = torch.from_numpy(np.ascontiguousarray(orbit_np).reshape(-1)).cuda()
-        dist.broadcast(blob, src=0)
+        meta_box = [None]
+        if rank == 0:
+            meta, blobs = ReplicatedInputs.pack(coords, orbit, la, n_iter)
+            meta["gen_times"] = gen_times
+            meta_box = [meta]
+        dist.broadcast_object_list(meta_box, src=0)
+        meta = meta_box[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dev = []
+        for i, size in enumerate(meta["sizes"]):
+            t = torch.from_numpy(blobs[i]).cuda() if rank == 0 else torch.empty(size, dtype=torch.uint8, device="cuda")
+            dev.append(t)
         torch.cuda.synchronize()
-        assert bytes(blob[:64].cpu().numpy()) == bytes(orbit_np.reshape(-1)[:64]), "orbit replica mismatch"
+        e0.record()
+        for t in dev:
+            if t.numel():
+                dist.broadcast(t, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+        if rank != 0:
+            coords, orbit, la, n_iter = ReplicatedInputs.unpack(meta, [t.cpu().numpy() for t in dev])
+            gen_times = meta["gen_times"]
+        del dev
 
     r = GPURenderer(local_rank)
     assert r.InitializeMemory(WIDTH, HEIGHT, 1, iter_bytes=4) == 0
@@ -324,6 +347,7 @@ def main():
             "sum_pixel_iters": total_sum}
     if gather_ms is not None:
         line["gather_ms"] = gather_ms
+        line["input_broadcast_ms"] = bcast_ms
 
     if rank == 0:
         # reference CUDA kernels (oracle/_ref, the checker) timed on the same GPU and inputs, for context

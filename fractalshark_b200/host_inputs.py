@@ -205,3 +205,71 @@ class BlaTable:
         ptr = self._lib.fsh_blas_levels(self._h)[level]
         buf = (C.c_ubyte * (n * self.elem_bytes)).from_address(ptr)
         return np.frombuffer(buf, dtype=np.uint8).reshape(n, self.elem_bytes)
+
+
+class ReplicatedInputs:
+    """Orbit + LA table + coordinates as plain byte blobs, the form in which they travel between ranks
+    (``pack`` on the rank that produced them, ``unpack`` on the receivers).  The unpacked object offers the
+    ``descriptor()`` / size attributes of :class:`Orbit` and :class:`LaTable`, so the renderer uploads straight from
+    the received host buffers; nothing is recomputed on the receiving rank."""
+
+    class _Orbit:
+        pextras = 0
+
+        def __init__(self, meta, data: np.ndarray, x_low: np.ndarray, y_low: np.ndarray):
+            self.numeric = Numeric(meta["numeric"])
+            self.count = meta["count"]
+            self.uncompressed_count = meta["uncompressed_count"]
+            self.period = meta["period"]
+            self.elem_bytes = meta["elem_bytes"]
+            self.pextras = meta["pextras"]
+            self._data, self._x, self._y = data, x_low, y_low
+
+        def as_numpy(self):
+            return self._data.reshape(self.count, self.elem_bytes)
+
+        def descriptor(self):
+            return N.FsOrbit(self._data.ctypes.data, self.count, self.uncompressed_count, self.period,
+                             self._x.ctypes.data, self._y.ctypes.data)
+
+    class _La:
+        def __init__(self, meta, las: np.ndarray, stages: np.ndarray, at: np.ndarray):
+            self.num_las, self.num_stages, self.stage_count = meta["num_las"], meta["num_stages"], meta["stage_count"]
+            self.use_at, self.is_valid = meta["use_at"], meta["is_valid"]
+            self.las_elem_bytes, self.at_bytes, self.iter_bytes = meta["las_elem_bytes"], meta["at_bytes"], meta["iter_bytes"]
+            self._las, self._stages, self._at = las, stages, at
+
+        def descriptor(self):
+            return N.FsLaReference(self._las.ctypes.data if self.num_las else None, self.num_las,
+                                   self._stages.ctypes.data if self.num_stages else None, self.num_stages,
+                                   self._at.ctypes.data if self.at_bytes else None, self.stage_count,
+                                   int(self.use_at), int(self.is_valid))
+
+    @staticmethod
+    def pack(coords: dict, orbit: "Orbit", la: "LaTable", n_iter: int):
+        """-> (meta dict, [uint8 arrays]) ; the arrays are copies, safe to hand to a collective."""
+        lib = orbit._lib
+        def grab(ptr, nbytes):
+            if not ptr or not nbytes:
+                return np.zeros(0, np.uint8)
+            return np.frombuffer((C.c_ubyte * nbytes).from_address(ptr), dtype=np.uint8).copy()
+        pod = POD_BYTES[orbit.numeric]
+        blobs = [grab(orbit.data_ptr, orbit.count * orbit.elem_bytes),
+                 grab(int(lib.fsh_orbit_x_low(orbit._h)), pod), grab(int(lib.fsh_orbit_y_low(orbit._h)), pod),
+                 grab(int(lib.fsh_la_las(la._h) or 0), la.num_las * la.las_elem_bytes),
+                 grab(int(lib.fsh_la_stages(la._h) or 0), la.num_stages * 2 * la.iter_bytes),
+                 grab(int(lib.fsh_la_at(la._h) or 0), la.at_bytes)]
+        meta = {"numeric": int(orbit.numeric), "count": orbit.count, "uncompressed_count": orbit.uncompressed_count,
+                "period": orbit.period, "elem_bytes": orbit.elem_bytes, "pextras": int(orbit.pextras),
+                "num_las": la.num_las, "num_stages": la.num_stages, "stage_count": la.stage_count,
+                "use_at": bool(la.use_at), "is_valid": bool(la.is_valid), "las_elem_bytes": la.las_elem_bytes,
+                "at_bytes": la.at_bytes, "iter_bytes": la.iter_bytes, "n_iter": int(n_iter),
+                "coords": {k: bytes(v) for k, v in coords.items()}, "sizes": [int(b.size) for b in blobs]}
+        return meta, blobs
+
+    @staticmethod
+    def unpack(meta: dict, blobs):
+        """-> (coords, orbit-like, la-like, n_iter) from what ``pack`` produced."""
+        o = ReplicatedInputs._Orbit(meta, blobs[0], blobs[1], blobs[2])
+        l = ReplicatedInputs._La(meta, blobs[3], blobs[4], blobs[5])
+        return dict(meta["coords"]), o, l, meta["n_iter"]

@@ -63,3 +63,68 @@ def test_merge_shards_helper():
         b[rows] = full[rows]
         bufs.append(b)
     assert np.array_equal(merge_shards(bufs, h), full)
+
+
+def _replicate_worker(rank, world, port, out_q):
+    """Rank 0 produces orbit + LA table + coordinates, packs them, broadcasts the blobs (the way bench.py does over
+    NCCL); rank 1 unpacks without computing anything and reports the CRC of what it would upload."""
+    import zlib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fractalshark_b200 import Numeric
+    from fractalshark_b200.host_inputs import LaTable, Orbit, ReplicatedInputs, View
+    from fractalshark_b200.views import VIEW5
+
+    def crc_of(coords, orbit, la):
+        crc = 0
+        for k in sorted(coords):
+            crc = zlib.crc32(coords[k], crc)
+        d, l = orbit.descriptor(), la.descriptor()
+        import ctypes as C
+        for ptr, n in ((d.elements, orbit.count * orbit.elem_bytes), (l.las, la.num_las * la.las_elem_bytes),
+                       (l.stages, la.num_stages * 2 * la.iter_bytes), (l.at, la.at_bytes)):
+            crc = zlib.crc32(bytes((C.c_ubyte * n).from_address(ptr)), crc)
+        return crc, (d.compressed_count, d.uncompressed_count, d.period_maybe_zero, l.la_stage_count, l.use_at, l.is_valid)
+
+    box = [None]
+    if rank == 0:
+        v = View(VIEW5.min_x, VIEW5.min_y, VIEW5.max_x, VIEW5.max_y, 64, 36)
+        coords = v.coords(Numeric.HDR32)
+        orbit = Orbit(v, Numeric.HDR32, VIEW5.num_iterations, True)
+        la = LaTable(orbit, 4)
+        meta, blobs = ReplicatedInputs.pack(coords, orbit, la, VIEW5.num_iterations)
+        box = [meta]
+        out_q.put(("src", crc_of(coords, orbit, la)))
+    dist.broadcast_object_list(box, src=0)
+    meta = box[0]
+    got = []
+    for i, size in enumerate(meta["sizes"]):
+        t = torch.from_numpy(blobs[i]) if rank == 0 else torch.empty(size, dtype=torch.uint8)
+        if size:
+            dist.broadcast(t, src=0)
+        got.append(t.numpy())
+    if rank == 1:
+        coords, orbit, la, n = ReplicatedInputs.unpack(meta, got)
+        out_q.put(("dst", crc_of(coords, orbit, la), n))
+    dist.destroy_process_group()
+
+
+def test_inputs_replicate_by_broadcast_without_recomputation():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_replicate_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        item = q.get(timeout=180)
+        res[item[0]] = item[1:]
+    for p in procs:
+        p.join(timeout=60)
+    assert res["src"][0] == res["dst"][0]
+    assert res["dst"][1] == 4718592
