@@ -11,6 +11,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -696,7 +697,12 @@ uint32_t fs_test_cuda_is_working(void) {
 
 fs_renderer *fs_create(int32_t device) {
     fs_renderer *r = new (std::nothrow) fs_renderer();
-    if (r) r->device = device;
+    if (r) {
+        r->device = device;
+        // development switches (profiling under ncu without touching the caller): FS_SPLIT_AT=1, FS_SCALED_STEPS=0
+        if (const char *e = getenv("FS_SPLIT_AT")) r->split_at = atoi(e) != 0;
+        if (const char *e = getenv("FS_SCALED_STEPS")) r->use_scaled = atoi(e) != 0;
+    }
     return r;
 }
 
