@@ -104,8 +104,9 @@ def cpu_port_sample(coords, orbit, la, n_iter, threads):
                                           threads=threads)
     dt = time.time() - t0
     total = int(iters[0:HEIGHT:row_step, 0:WIDTH:col_step].sum())
-    return total / dt, dt, f"every {row_step}th row x every {col_step}th column of the frame " \
-                           f"({(HEIGHT // row_step) * (WIDTH // col_step)} pixels, {steps} executed steps, {dt:.1f} s)"
+    what = "the whole frame" if row_step == 1 and col_step == 1 else \
+        f"every {row_step}th row x every {col_step}th column of the frame"
+    return total / dt, dt, f"{what} ({(HEIGHT // row_step) * (WIDTH // col_step)} pixels, {steps} executed steps, {dt:.1f} s)"
 
 
 def run_reference_arm(args, rank, world):
