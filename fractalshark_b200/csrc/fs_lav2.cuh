@@ -159,52 +159,77 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
         Cplx z = Num::c_zero();
         IterT i = 0;
         bool at_done = false;
-        if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4) {
-            // HDRx32 fast form of the loop below.  After the first pass the shared exponent of z is pinned to
-            // E = c.e whenever E <= 0 (2E <= E, so `add` always lands on c's exponent), which turns the
-            // float+exponent recurrence into its own mantissa recurrence with one constant scale 2^E:
+        if constexpr (Num::kHdr && !Num::kDf) {
+            // Fast form of the loop below for the float+exponent types (binary32 and binary64 mantissas).  After the
+            // first pass the shared exponent of z is pinned to E = c.e whenever E <= 0 (2E <= E, so `add` always
+            // lands on c's exponent), which turns the float+exponent recurrence into its own mantissa recurrence
+            // with one constant scale 2^E:
             //     re' = fma(rr - ii, 2^E, c.re)      im' = fma(fma(re, im, re*im), 2^E, c.im)
             // -- the very operations the general loop performs, minus the exponent bookkeeping -- and the escape
             // test `Reduce(nsq) > SqrEscapeRadius` into `nsq.mantissa > R.m * 2^(R.e - 2E)` (both reduced and
             // positive: lexicographic order == numeric order; NaN/Inf escape, as their exponent field does there).
-            // 12 instructions per pass instead of 38; on View 14 this loop is 83 % of the frame.
+            // 7 instructions per pass instead of 38 (HDRx32); on View 14 this loop was 83 % of the frame.
+            using M = typename Num::Mant;
+            constexpr int kMaxShift = MT<M>::BIAS - 1;
             const int E = c.e;
             const Real R = A.at.SqrEscapeRadius;
             const int sh = R.e - 2 * E;
-            if (E <= 0 && E > -EXP_DIFF_IGNORED && R.m >= 1.0f && R.m < 2.0f && sh <= 126 && sh >= -126 && at_max > 0) {
-                const float s = MT<float>::pow2(E);
-                const float thr = R.m * MT<float>::pow2(sh);
-                float re = 0.0f, im = 0.0f;
+            if (E <= 0 && E > -EXP_DIFF_IGNORED && R.m >= M(1) && R.m < M(2) && sh <= kMaxShift && sh >= -kMaxShift &&
+                at_max > 0) {
+                const M s = MT<M>::pow2(E);
+                const M thr = R.m * MT<M>::pow2(sh);
+                M re = M(0), im = M(0);
                 // sixteen passes per escape test: the running maximum of |z|^2 over the chunk decides whether any
                 // pass escaped (an overflowed pass shows as +inf before any NaN can form); if one did, the chunk
                 // is replayed pass by pass from its saved start to stop at the exact pass
-                // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
-                const f32x2 s2 = f2_make(s, s), c2 = f2_make(c.re, c.im);
                 constexpr int kAtChunk = 16;
-                while (i + kAtChunk <= at_max) {
-                    const float re0 = re, im0 = im;
-                    float worst = 0.0f;
-                    f32x2 z2 = f2_make(re, im);
+                if constexpr (sizeof(M) == 4) {
+                    // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
+                    const f32x2 s2 = f2_make(s, s), c2 = f2_make(c.re, c.im);
+                    while (i + kAtChunk <= at_max) {
+                        const float re0 = re, im0 = im;
+                        float worst = 0.0f;
+                        f32x2 z2 = f2_make(re, im);
 #pragma unroll
-                    for (int u = 0; u < kAtChunk; u++) {
-                        float rr, ii;
-                        f2_split(f2_mul(z2, z2), rr, ii);
-                        worst = fmaxf(worst, rr + ii);
-                        const float t = fma_(re, im, re * im);
-                        z2 = f2_fma(f2_make(rr - ii, t), s2, c2);
-                        f2_split(z2, re, im);
+                        for (int u = 0; u < kAtChunk; u++) {
+                            float rr, ii;
+                            f2_split(f2_mul(z2, z2), rr, ii);
+                            worst = fmaxf(worst, rr + ii);
+                            const float t = fma_(re, im, re * im);
+                            z2 = f2_fma(f2_make(rr - ii, t), s2, c2);
+                            f2_split(z2, re, im);
+                        }
+                        if (!(worst <= thr)) {
+                            re = re0;
+                            im = im0;
+                            break;
+                        }
+                        i += kAtChunk;
                     }
-                    if (!(worst <= thr)) {
-                        re = re0;
-                        im = im0;
-                        break;
+                } else {
+                    while (i + kAtChunk <= at_max) {
+                        const M re0 = re, im0 = im;
+                        M worst = M(0);
+#pragma unroll
+                        for (int u = 0; u < kAtChunk; u++) {
+                            const M rr = re * re, ii = im * im;
+                            worst = fmax(worst, rr + ii);
+                            const M t = fma_(re, im, re * im);
+                            re = fma_(rr - ii, s, c.re);
+                            im = fma_(t, s, c.im);
+                        }
+                        if (!(worst <= thr)) {
+                            re = re0;
+                            im = im0;
+                            break;
+                        }
+                        i += kAtChunk;
                     }
-                    i += kAtChunk;
                 }
                 for (; i < at_max; i++) {
-                    const float rr = re * re, ii = im * im;
+                    const M rr = re * re, ii = im * im;
                     if (!(rr + ii <= thr)) break;
-                    const float t = fma_(re, im, re * im);
+                    const M t = fma_(re, im, re * im);
                     re = fma_(rr - ii, s, c.re);
                     im = fma_(t, s, c.im);
                 }

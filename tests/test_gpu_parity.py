@@ -71,6 +71,7 @@ FULL_CASES = [
     ("v14_hdr32_lav2_full", 14, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None, 4, 0.999),   # north_star target view
     ("v14_hdr2x32_lav2_full", 14, 1920, 1080, A.GpuHDRx2x32PerturbedLAv2, None, 4, 0.999),
     ("v14_hdr32_rclav2_u64_full", 14, 1920, 1080, A.GpuHDRx32PerturbedRCLAv2, None, 8, 0.999),
+    ("v14_hdr64_lav2_full", 14, 960, 540, A.GpuHDRx64PerturbedLAv2, None, 4, 0.999),
     ("v19_hdr32_lav2_full", 19, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None, 4, 0.999),
     ("v5_hdr32_rclav2_full", 5, 3840, 2160, A.GpuHDRx32PerturbedRCLAv2, None, 4, 0.999),
     ("v19_hdr32_rclav2_full", 19, 960, 540, A.GpuHDRx32PerturbedRCLAv2, 3000000, 4, 0.999),
