@@ -1,0 +1,54 @@
+// fs_at_fast.cuh -- the AT shortcut (ATInfo::PerformAT, ATInfo.h:155-188) as a mantissa recurrence, for the
+// float+exponent types with a binary32 or binary64 mantissa.  FS_HD so that oracle/lockstep_check.cpp can run the very
+// same functions on the CPU against the oracle's float+exponent restatement of the loop.
+//
+// The reference iterates  z <- z*z + c  on an HDRFloatComplex (two mantissas, one shared exponent) and leaves when
+// Reduce(|z|^2) > SqrEscapeRadius.  c is reduced; when its exponent E is <= 0, z*z has exponent 2E <= E, so `add`
+// (HDRFloatComplex.h:219-247) always lands on c's exponent: from the first pass on the exponent of z IS E, and
+//     re' = fma(rr - ii, 2^E, c.re)          im' = fma(fma(re, im, re*im), 2^E, c.im)
+// with rr = re*re, ii = im*im are exactly the operations the reference performs on the mantissas (for E == 0 it adds
+// c to z*z instead of z*z to c: the same sum, one rounding).  Its escape test compares (exponent, mantissa) pairs
+// of reduced positive numbers, i.e. values:  rr + ii > R.m * 2^(R.e - 2E).  NaN/Inf mantissas leave the loop here as
+// they do there (their exponent field reduces to +128 / +1024).
+// E > 0 (|c| >= 2: pixels far from the centre of a deep view, whose c = RefC + dc*CCoeff is large, or a view whose
+// AT constant itself sits past 2 like View 5's |RefC| ~ 2.008) is left to the general loop: there the reference's
+// exponent doubles every pass and its mantissas run into the denormal range, a behaviour only that loop reproduces.
+#pragma once
+#include "fs_types.cuh"
+
+namespace fs {
+namespace atfast {
+
+template <class M> struct Plan {
+    bool ok; // false: take the general float+exponent loop
+    M s;     // 2^E
+    M thr;   // R.m * 2^(R.e - 2E)
+    int E;
+};
+
+// c: reduced; R = SqrEscapeRadius.  `passes` = n_iterations / StepLength (the plan needs at least one pass: the
+// first pass is what moves z from its initial MIN_BIG exponent to E).
+template <class M> FS_HD Plan<M> plan(HdrC<M> c, Hdr<M> R, bool passes) {
+    Plan<M> p;
+    constexpr int kMaxShift = MT<M>::BIAS - 1;
+    const int sh = R.e - 2 * c.e;
+    p.E = c.e;
+    p.ok = passes && c.e <= 0 && c.e > -EXP_DIFF_IGNORED && R.m >= M(1) && R.m < M(2) && sh <= kMaxShift && sh >= -kMaxShift;
+    p.s = p.ok ? MT<M>::pow2(c.e) : M(0);
+    p.thr = p.ok ? R.m * MT<M>::pow2(sh) : M(0);
+    return p;
+}
+
+// |z|^2 mantissa of the current z
+template <class M> FS_HD M norm(M re, M im) { return re * re + im * im; }
+template <class M> FS_HD bool escaped(M nsq, M thr) { return !(nsq <= thr); }
+// one pass (the caller has already tested `escaped`)
+template <class M> FS_HD void advance(M &re, M &im, M s, M cre, M cim) {
+    const M rr = re * re, ii = im * im;
+    const M t = fma_(re, im, re * im);
+    re = fma_(rr - ii, s, cre);
+    im = fma_(t, s, cim);
+}
+
+} // namespace atfast
+} // namespace fs

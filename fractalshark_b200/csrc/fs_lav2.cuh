@@ -13,6 +13,7 @@
 #include "fs_num.cuh"
 #include "fs_df32.cuh"
 #include "fs_perturb_loop.cuh"
+#include "fs_at_fast.cuh"
 
 namespace fs {
 
@@ -160,24 +161,15 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
         IterT i = 0;
         bool at_done = false;
         if constexpr (Num::kHdr && !Num::kDf) {
-            // Fast form of the loop below for the float+exponent types (binary32 and binary64 mantissas).  After the
-            // first pass the shared exponent of z is pinned to E = c.e whenever E <= 0 (2E <= E, so `add` always
-            // lands on c's exponent), which turns the float+exponent recurrence into its own mantissa recurrence
-            // with one constant scale 2^E:
-            //     re' = fma(rr - ii, 2^E, c.re)      im' = fma(fma(re, im, re*im), 2^E, c.im)
-            // -- the very operations the general loop performs, minus the exponent bookkeeping -- and the escape
-            // test `Reduce(nsq) > SqrEscapeRadius` into `nsq.mantissa > R.m * 2^(R.e - 2E)` (both reduced and
-            // positive: lexicographic order == numeric order; NaN/Inf escape, as their exponent field does there).
-            // 7 instructions per pass instead of 38 (HDRx32); on View 14 this loop was 83 % of the frame.
+            // Fast form of the loop below for the float+exponent types (binary32 and binary64 mantissas): the
+            // recurrence on the mantissas with the exponent pinned to c's (fs_at_fast.cuh has the argument and the
+            // scalar form that oracle/lockstep_check.cpp runs against the oracle).  7 instructions per pass instead
+            // of 38 (HDRx32); on View 14 this loop was 83 % of the frame.
             using M = typename Num::Mant;
-            constexpr int kMaxShift = MT<M>::BIAS - 1;
-            const int E = c.e;
-            const Real R = A.at.SqrEscapeRadius;
-            const int sh = R.e - 2 * E;
-            if (E <= 0 && E > -EXP_DIFF_IGNORED && R.m >= M(1) && R.m < M(2) && sh <= kMaxShift && sh >= -kMaxShift &&
-                at_max > 0) {
-                const M s = MT<M>::pow2(E);
-                const M thr = R.m * MT<M>::pow2(sh);
+            const atfast::Plan<M> plan = atfast::plan<M>(c, A.at.SqrEscapeRadius, at_max > 0);
+            if (plan.ok) {
+                const M s = plan.s, thr = plan.thr;
+                const int E = plan.E;
                 M re = M(0), im = M(0);
                 // sixteen passes per escape test: the running maximum of |z|^2 over the chunk decides whether any
                 // pass escaped (an overflowed pass shows as +inf before any NaN can form); if one did, the chunk
@@ -227,11 +219,8 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                     }
                 }
                 for (; i < at_max; i++) {
-                    const M rr = re * re, ii = im * im;
-                    if (!(rr + ii <= thr)) break;
-                    const M t = fma_(re, im, re * im);
-                    re = fma_(rr - ii, s, c.re);
-                    im = fma_(t, s, c.im);
+                    if (atfast::escaped(atfast::norm(re, im), thr)) break;
+                    atfast::advance(re, im, s, c.re, c.im);
                 }
                 z.re = re;
                 z.im = im;

@@ -13,6 +13,7 @@
 #include <mutex>
 
 #include "../fractalshark_b200/csrc/fs_scaled_loop.cuh"
+#include "../fractalshark_b200/csrc/fs_at_fast.cuh"
 
 namespace {
 
@@ -74,9 +75,71 @@ IterT lockstep_pixel(const Lav2Job<IterT> &J, const fs::scaled::FastElem *tab, i
     }
 }
 
+// AT shortcut: the product's mantissa recurrence (fs_at_fast.cuh) against the oracle's float+exponent loop
+// (oracle_cpu.cpp lav2_prologue, ATInfo.h:155-188), pass by pass: same escape decision at every pass, same mantissas
+// bit for bit, exponent equal to c's after the first pass.
+struct AtStats {
+    uint64_t pixels = 0, refused = 0, passes = 0, mismatches = 0, escaped = 0;
+};
+template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, int Y, uint64_t max_passes, AtStats &st) {
+    const HF DeltaReal = sub(mul(J.dx, hf_from_number((float)X)), J.centerX);
+    const HF negdy{-J.dy.mantissa, J.dy.exp};
+    const HF DeltaImaginary = sub(mul(negdy, hf_from_number((float)Y)), J.centerY);
+    const HC DeltaSub0 = hc_from(DeltaReal, DeltaImaginary);
+    if (!(J.is_valid && J.use_at && cmpPR(cheb(DeltaSub0), J.at->ThresholdC) <= 0)) return;
+    const ATInfoF<IterT> &AT = *J.at;
+    uint64_t n_pass = J.n_iterations / AT.StepLength;
+    if (n_pass > max_passes) n_pass = max_passes;
+    HC c = add(mul(DeltaSub0, AT.CCoeff), AT.RefC);
+    Reduce(c);
+    st.pixels++;
+    const fs::atfast::Plan<float> plan = fs::atfast::plan<float>(fs::HdrC<float>{c.re, c.im, c.exp},
+                                                                 fs::Hdr<float>{AT.SqrEscapeRadius.mantissa, AT.SqrEscapeRadius.exp},
+                                                                 n_pass > 0);
+    if (!plan.ok) { st.refused++; return; }
+    HC z = hc_zero();
+    float re = 0.0f, im = 0.0f;
+    for (uint64_t i = 0; i < n_pass; i++) {
+        const float rr = z.re * z.re, ii = z.im * z.im;
+        HF nsq{rr + ii, z.exp << 1};
+        Reduce(nsq);
+        const bool esc_o = cmpPR(nsq, AT.SqrEscapeRadius) > 0;
+        const bool esc_f = fs::atfast::escaped(fs::atfast::norm(re, im), plan.thr);
+        if (esc_o != esc_f) { st.mismatches++; return; }
+        if (esc_o) { st.escaped++; return; }
+        const int32_t e2 = z.exp + z.exp;
+        HC z2{rr - ii, fmaf(z.re, z.im, z.re * z.im), e2 < MIN_BIG_EXPONENT ? MIN_BIG_EXPONENT : e2};
+        z = add(z2, c);
+        fs::atfast::advance(re, im, plan.s, c.re, c.im);
+        st.passes++;
+        if (bits(z.re) != bits(re) || bits(z.im) != bits(im) || z.exp != plan.E) { st.mismatches++; return; }
+    }
+}
+
 } // namespace
 
 extern "C" {
+
+// stats[5]: pixels that take the AT shortcut, pixels the fast form refused, passes compared, mismatches, pixels escaped
+uint64_t lockstep_at(const void *at, int use_at, int is_valid, int w, int h, const void *dx, const void *dy,
+                     const void *cenx, const void *ceny, uint64_t n_iter, uint64_t max_passes, int col_step, int row_step,
+                     uint64_t *stats) {
+    using IterT = uint32_t;
+    Lav2Job<IterT> J;
+    memset((void *)&J, 0, sizeof(J));
+    J.mode = 1;
+    J.at = (const ATInfoF<IterT> *)at;
+    J.use_at = use_at && at;
+    J.is_valid = is_valid;
+    J.width = w; J.height = h;
+    memcpy(&J.dx, dx, 8); memcpy(&J.dy, dy, 8); memcpy(&J.centerX, cenx, 8); memcpy(&J.centerY, ceny, 8);
+    J.n_iterations = (IterT)n_iter;
+    AtStats st;
+    for (int y = 0; y < h; y += (row_step < 1 ? 1 : row_step))
+        for (int x = 0; x < w; x += (col_step < 1 ? 1 : col_step)) lockstep_at_pixel(J, x, y, max_passes, st);
+    stats[0] = st.pixels; stats[1] = st.refused; stats[2] = st.passes; stats[3] = st.mismatches; stats[4] = st.escaped;
+    return st.mismatches;
+}
 
 // Returns the number of lockstep mismatches (0 = every committed chunk matched the oracle by value).
 // stats[7]: fast steps, slow steps, chunks committed, chunks rejected, entries refused, mismatches, pixels finished in a chunk

@@ -140,11 +140,10 @@ def lockstep_lav2(alg, w, h, coords, orbit, la, n_iter, col_step=1, row_step=1, 
     float+exponent oracle.  Returns (iters, stats dict); stats["mismatches"] must be 0."""
     global _lock
     if _lock is None:
-        L = C.CDLL(LOCKSTEP_LIB)
-        V, I, U64 = C.c_void_p, C.c_int, C.c_uint64
-        L.lockstep_render_lav2.restype = U64
-        L.lockstep_render_lav2.argtypes = [I, V, U64, V, V, V, U64, I, I, I, I, V, V, V, V, U64, V, I, I, I, V]
-        _lock = L
+        _lock = C.CDLL(LOCKSTEP_LIB)
+    V, I, U64 = C.c_void_p, C.c_int, C.c_uint64
+    _lock.lockstep_render_lav2.restype = U64
+    _lock.lockstep_render_lav2.argtypes = [I, V, U64, V, V, V, U64, I, I, I, I, V, V, V, V, U64, V, I, I, I, V]
     t = traits(alg)
     hp, wp = _round_up(h, NB_THREADS_H), _round_up(w, NB_THREADS_W)
     out = np.zeros((hp, wp), dtype=np.uint32)
@@ -157,3 +156,20 @@ def lockstep_lav2(alg, w, h, coords, orbit, la, n_iter, col_step=1, row_step=1, 
     keys = ("fast_steps", "slow_steps", "chunks_committed", "chunks_rejected", "entries_refused", "mismatches",
             "finished_in_chunk")
     return out, dict(zip(keys, [int(x) for x in stats]))
+
+
+def lockstep_at(w, h, coords, la, n_iter, max_passes=20000, col_step=1, row_step=1):
+    """Runs the product's AT mantissa recurrence (fs_at_fast.cuh, host build) pass by pass against the oracle's
+    float+exponent AT loop for every sampled pixel of the frame.  Returns the stats dict (mismatches must be 0)."""
+    global _lock
+    if _lock is None:
+        _lock = C.CDLL(LOCKSTEP_LIB)
+    fn = _lock.lockstep_at
+    fn.restype = C.c_uint64
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    l = la.descriptor()
+    stats = (C.c_uint64 * 5)()
+    fn(l.at, l.use_at, l.is_valid, w, h, _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]),
+       _buf(coords["center_y"]), n_iter, max_passes, col_step, row_step, stats)
+    return dict(zip(("pixels", "refused", "passes", "mismatches", "escaped"), (int(v) for v in stats)))
