@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-GPU_LIB_PATH = os.path.join(_HERE, "libfsgpu.so")
+GPU_LIB_PATH = os.environ.get("FS_GPU_LIB") or os.path.join(_HERE, "libfsgpu.so")  # env override: A/B builds
 HOST_LIB_PATH = os.path.join(_HERE, "libfshost.so")
 
 

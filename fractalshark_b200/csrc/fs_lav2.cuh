@@ -15,6 +15,10 @@
 #include "fs_perturb_loop.cuh"
 #include "fs_at_fast.cuh"
 
+#ifndef FS_AT_PACKED
+#define FS_AT_PACKED 1
+#endif
+
 namespace fs {
 
 enum class Lav2Mode : int { Full = 1, PO = 2, LAO = 3 }; // RenderAlgorithm.h:12-17
@@ -175,7 +179,7 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                 // pass escaped (an overflowed pass shows as +inf before any NaN can form); if one did, the chunk
                 // is replayed pass by pass from its saved start to stop at the exact pass
                 constexpr int kAtChunk = 16;
-                if constexpr (sizeof(M) == 4) {
+                if constexpr (sizeof(M) == 4 && FS_AT_PACKED) {
                     // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
                     const f32x2 s2 = f2_make(s, s), c2 = f2_make(c.re, c.im);
                     while (i + kAtChunk <= at_max) {
