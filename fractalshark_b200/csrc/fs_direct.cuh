@@ -56,6 +56,31 @@ __global__ void __launch_bounds__(256) direct_kernel(const DirectArgs<M, IterT> 
         const M y0 = fma_(DirectOps<M>::from_int(Y), A.dy, A.cy);
         M x = 0, y = 0;
         IterT iter = 0;
+        if constexpr (P == 1) {
+            // Eight steps per branch: every step's bailout test is still evaluated (folded into one predicate, NaN
+            // counts as escaped), and a chunk in which any test failed is discarded and replayed step by step by the
+            // loop below, so the count is the one the per-step loop produces.  7 instead of 10 instructions per
+            // iteration.  Invariant at the top of a chunk: |z|^2 < 4 holds for the current (x, y).
+            constexpr int K = 8;
+            while (iter + (IterT)K <= n_iter && iter + (IterT)K > iter) {
+                const M sx = x, sy = y;
+                bool ok = true;
+#pragma unroll
+                for (int u = 0; u < K; u++) {
+                    const M x2 = x + x;
+                    const M t = DirectOps<M>::fma_rd(-y, y, x0);
+                    y = DirectOps<M>::fma_rd(x2, y, y0);
+                    x = DirectOps<M>::fma_rd(x, x, t);
+                    ok = ok && (fma_(x, x, y * y) < M(4));
+                }
+                if (!ok) {
+                    x = sx;
+                    y = sy;
+                    break;
+                }
+                iter += (IterT)K;
+            }
+        }
         while (fma_(x, x, y * y) < M(4) && iter < n_iter) {
 #pragma unroll
             for (int p = 0; p < P; p++) {
