@@ -182,7 +182,58 @@ FS_D IterT scaled_pixel(const ScaledArgs<Num, IterT> &A, int Xp, int Yp, unsigne
         Y = Ops::to_float(Ops::quot(ny, S));
     };
 
+    // Eight binary32 steps per branch where nothing can happen: every step's tests (escape, rebase by norm, |w|^2
+    // past the re-scaling threshold, a `bad` element; the end of the orbit is excluded by the chunk's range) are still
+    // evaluated and folded into one predicate; a chunk in which any of them fired is discarded and the steps are
+    // taken one by one by the loop below, which is the reference's loop.  One LDG.128 per step (the element a step
+    // arrives at is the one the next step starts from) and ~30 instead of ~40 instructions per step.
+    constexpr int K = 8;
+    int exact_budget = 0; // steps to take one by one after a discarded chunk (whatever fired is within K steps)
     while (iter < A.n_iterations) {
+        // A chunk is attempted only where it can plausibly complete: not within K steps of the end of the orbit or
+        // of the iteration limit, not right after a discarded chunk, and not while |w|^2 is within a factor 2^20 of
+        // the re-scaling threshold (|w| rarely grows by more than ~2.4x per step, so eight steps rarely bridge that gap; pixels
+        // whose w races to the threshold every couple of dozen steps would otherwise throw every other chunk away).
+        // These are performance choices only: what a chunk computes is checked step by step either way.
+        const bool can = exact_budget == 0 && (uint64_t)iter + K <= (uint64_t)A.n_iterations &&
+                         (uint64_t)Ref + K < (uint64_t)last && fma_(X, X, Y * Y) < 0x1p30f;
+        if (can) {
+            const float X0 = X, Y0 = Y;
+            ScaledElemF e = ldg_rec(A.orbit_f + Ref);
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < K; u++) {
+                ok = ok && (e.bad == 0);
+                const float sX = s * X, sY = s * Y;
+                float a = fma_(X, e.x, X * e.x);
+                const float b = fma_(Y, e.y, Y * e.y);
+                const float yx = fma_(Y, e.x, Y * e.x);
+                const float t = fma_(twos, Y, e.y + e.y);
+                a = a - b;
+                const float ny = fma_(X, t, yx);
+                a = fma_(X, sX, a);
+                a = fma_(-Y, sY, a);
+                Y = c0y + ny;
+                X = c0x + a;
+                e = ldg_rec(A.orbit_f + Ref + (u + 1));
+                const float zy = fma_(s, Y, e.y), zx = fma_(s, X, e.x);
+                const float w2 = fma_(X, X, Y * Y);
+                const float zn = fma_(zx, zx, zy * zy);
+                const float nrm = s * (s * w2);
+                ok = ok && (zn < 256.0f) && !(zn < nrm) && !(w2 >= w2threshold);
+            }
+            if (ok) {
+                Ref += (IterT)K;
+                iter += (IterT)K;
+                if (Count) steps += K;
+            } else {
+                X = X0;
+                Y = Y0;
+                exact_budget = K;
+            }
+            continue;
+        }
+        if (exact_budget > 0) exact_budget--;
         const ScaledElemF e = ldg_rec(A.orbit_f + Ref);
         if (Count) steps++;
         if (e.bad == 0) {
