@@ -20,8 +20,9 @@ full render of the frame.
               peak measured live by a micro-kernel on the same GPU.
 * cpu_baseline the oracle's CPU port of the same kernel on a bounded pixel sample (all host threads).
 N > 1: 4-row tile bands are dealt round-robin to ranks (no data-path collective inside the render);
-the orbit/LA blob is replicated by an NCCL broadcast and the iteration buffer is merged on rank 0 with an
-NCCL reduce (disjoint rows, so SUM == gather).
+the orbit/LA blob is replicated by an NCCL broadcast.  The device-timed arm checks the merged frame with an NCCL
+reduce (disjoint rows, so SUM == gather; untimed).  The e2e arm assembles the frame on the HOST: one shared-memory
+frame, page-locked by every rank, into which each rank copies only the bands it rendered (fs_render_current_shard).
 """
 from __future__ import annotations
 
@@ -197,9 +198,19 @@ def main():
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
         if rank != 0:
-            coords, orbit, la, n_iter = ReplicatedInputs.unpack(meta, [t.cpu().numpy() for t in dev])
+            blobs = [t.cpu().numpy() for t in dev]
+            coords, orbit, la, n_iter = ReplicatedInputs.unpack(meta, blobs)
             gen_times = meta["gen_times"]
         del dev
+    else:
+        meta, blobs = ReplicatedInputs.pack(coords, orbit, la, n_iter)
+    # the e2e arm uploads from page-locked host memory: the same tables, copied once into pinned buffers
+    pinned_blobs = []
+    for b in blobs:
+        t = torch.empty(max(int(b.size), 1), dtype=torch.uint8, pin_memory=True)
+        t[:b.size] = torch.from_numpy(b)
+        pinned_blobs.append(t.numpy()[:b.size])
+    _, orbit_pinned, la_pinned, _ = ReplicatedInputs.unpack(meta, pinned_blobs)
 
     r = GPURenderer(local_rank)
     assert r.InitializeMemory(WIDTH, HEIGHT, 1, iter_bytes=4) == 0
@@ -286,14 +297,52 @@ def main():
     value = total_sum / (ms_per_step * 1e-3)
 
     # ---- e2e: public call sequence with host buffers (every step re-uploads orbit + LA, reads results) ------
-    pinned_iters = torch.empty((hp, wp), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    # N=1: the frame lands in a pinned buffer.  N>1: ONE host frame in POSIX shared memory, page-locked in every
+    # rank; each rank copies just the 4-row bands it rendered into their place (fs_render_current_shard), so the
+    # frame is assembled on the host with no collective and 1/N of the frame crosses each GPU's PCIe link.
+    shm, frame_kind = None, "pinned"
+    if world == 1:
+        frame = torch.empty((hp, wp), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    else:
+        from multiprocessing import shared_memory
+        name = "fsb200_frame_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()
+            except FileNotFoundError:
+                pass
+            shm = shared_memory.SharedMemory(name=name, create=True, size=hp * wp * 4)
+        dist.barrier()
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name)
+        frame = np.ndarray((hp, wp), dtype=np.uint32, buffer=shm.buf)
+        if rank == 0:
+            frame[:] = 0
+        frame_kind = "shared memory frame every rank writes its bands into"
+        dist.barrier()
+    # result sink: the kernel stores finished pixels into the host frame while it runs (fs_set_result_sink page-locks
+    # and maps the frame if it is not yet), RenderCurrent then only fetches the 24-byte reduction.  FS_BENCH_SINK=0
+    # measures the copy-after-render path instead.
+    use_sink = os.environ.get("FS_BENCH_SINK", "1") != "0"
+    if use_sink:
+        rc = r.SetResultSink(frame)
+        assert rc == 0, GPURenderer.ConvertErrorToString(rc)
+        frame_kind += "; streamed by the render kernel (result sink)"
+    else:
+        if world > 1:
+            reg = int(torch.cuda.cudart().cudaHostRegister(frame.ctypes.data, hp * wp * 4, 0))
+            assert reg == 0
+        frame_kind += "; copied after the render"
 
     def step_e2e(g):
-        rc = r.InitializePerturb(g, orbit, 0, None, la)
+        rc = r.InitializePerturb(g, orbit_pinned, 0, None, la_pinned)
         assert rc == 0
         r.ClearMemory()
         assert r.RenderPerturbLAv2(alg, coords, n_iter) == 0
-        rc, it, _, rd = r.RenderCurrent(n_iter, iters_out=pinned_iters)
+        if world == 1:
+            rc, it, _, rd = r.RenderCurrent(n_iter, iters_out=frame)
+        else:
+            rc, rd = r.RenderCurrentShard(n_iter, frame)
         assert rc == 0
         return rd["Sum"]
 
@@ -308,10 +357,32 @@ def main():
         e2e_sum = step_e2e(gen)
     barrier()
     e2e_s = (time.time() - t0) / args.steps
+    assert e2e_sum == local_sum
+    # untimed: one more step into a zeroed host frame -- what arrives there is the whole picture of THIS step
+    if rank == 0:
+        frame[:] = 0
+    barrier()
+    gen += 1
+    step_e2e(gen)
+    barrier()
+    if rank == 0:
+        assert int(frame[:HEIGHT, :WIDTH].astype(np.int64).sum()) == total_sum
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+        dist.barrier()
+    if use_sink:
+        assert r.SetResultSink(None) == 0
+    elif world > 1:
+        torch.cuda.cudart().cudaHostUnregister(frame.ctypes.data)
+    if world > 1:
+        del frame
+        shm.close()
+        if rank == 0:
+            shm.unlink()
+    # whole-job host<->device bytes per step: every rank uploads its own copy of the tables, the frame leaves once
+    h2d, d2h = h2d * world, hp * wp * 4 + 24 * world
     e2e_value = total_sum / e2e_s
 
     # ---- roofline -----------------------------------------------------------------------------------------------
@@ -341,7 +412,7 @@ def main():
                        "orbit_entries": orbit.count, "la_records": la.num_las, "la_stages": la.stage_count},
             "clocks": _clock_summary(samples),
             "e2e": {"value": e2e_value, "unit": "pixel-iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3},
+                    "ms_per_step": e2e_s * 1e3, "host_frame": frame_kind},
             "gpu_launches": int(launches_timed),
             "roofline": roofline,
             "wall_ms_per_step_incl_flush": wall_s * 1e3 / args.steps,

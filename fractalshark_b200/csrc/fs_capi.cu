@@ -100,6 +100,10 @@ struct fs_renderer {
     unsigned int *tile_counter = nullptr;
     unsigned long long *step_counter = nullptr;
     bool count_steps = false;
+    // result sink (fs_set_result_sink): a page-locked host frame the LAv2 kernels store finished pixels into while they
+    // run, so the device->host transfer of the frame overlaps the render instead of following it
+    void *sink_host = nullptr, *sink_dev = nullptr;
+    bool sink_registered = false, sink_filled = false;
     bool split_at = false;  // HDRx32 + AT: AT shortcut in its own launch ahead of the LA/perturbation launch (fs_lav2.cuh AtPhase);
                             // measured slower than the fused launch (View 14: 9.7 vs 8.5 ms), kept as an A/B switch
     DeviceBlob at_state;    // float4 per iteration-buffer cell, allocated on first use
@@ -151,7 +155,14 @@ void reset_perturb(fs_renderer *r) {
     r->la = LaDev{};
 }
 
+void drop_sink(fs_renderer *r) {
+    if (r->sink_registered) cudaHostUnregister(r->sink_host);
+    r->sink_host = r->sink_dev = nullptr;
+    r->sink_registered = r->sink_filled = false;
+}
+
 void reset_buffers(fs_renderer *r) {
+    drop_sink(r);
     free_blob(r, r->at_state);
     if (r->iter_buf) cudaFreeAsync(r->iter_buf, r->compute);
     if (r->red_dev) cudaFreeAsync(r->red_dev, r->compute);
@@ -297,28 +308,40 @@ uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, u
     return 0;
 }
 
-// Repack LAInfoDeep[] (reference layout) into 16-byte-aligned LaRec[] and ATInfo into AtDev.
+// Repack LAInfoDeep[] (reference layout) into 16-byte-aligned LaRec[] and ATInfo into AtDev.  The wire records are
+// copied to the device as they are and repacked there, so the call never waits for the stream: with page-locked
+// sources the whole upload is asynchronous and the render launch queues right behind it.
+template <class Num, class IterT>
+__global__ void __launch_bounds__(256) la_repack_kernel(const WireLA<Num, IterT> *wire, LaRec<Num, IterT> *out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const WireLA<Num, IterT> w = wire[i];
+        LaRec<Num, IterT> d;
+        memset(&d, 0, sizeof(d));
+        d.Ref = w.Ref; d.ZCoeff = w.ZCoeff; d.CCoeff = w.CCoeff;
+        d.LAThreshold = w.LAThreshold; d.LAThresholdC = w.LAThresholdC;
+        d.StepLength = w.StepLength; d.NextStageLAIndex = w.NextStageLAIndex;
+        out[i] = d;
+    }
+}
+
 template <class Num, class IterT> uint32_t upload_la_typed(fs_renderer *r, const fs_la_reference *src) {
     using W = WireLA<Num, IterT>;
     using D = LaRec<Num, IterT>;
     LaDev &la = r->la;
-    std::vector<D> host(src->num_las ? src->num_las : 1);
-    const unsigned char *p = static_cast<const unsigned char *>(src->las);
-    for (uint64_t i = 0; i < src->num_las; i++) {
-        W w;
-        memcpy(&w, p + i * sizeof(W), sizeof(W));
-        D d;
-        memset(&d, 0, sizeof(D));
-        d.Ref = w.Ref; d.ZCoeff = w.ZCoeff; d.CCoeff = w.CCoeff;
-        d.LAThreshold = w.LAThreshold; d.LAThresholdC = w.LAThresholdC;
-        d.StepLength = w.StepLength; d.NextStageLAIndex = w.NextStageLAIndex;
-        host[i] = d;
+    const size_t n = src->num_las;
+    cudaError_t err = cudaMallocAsync(&la.las.ptr, (n ? n : 1) * sizeof(D), r->compute);
+    if (err != cudaSuccess) return err;
+    la.las.bytes = (n ? n : 1) * sizeof(D);
+    if (n) {
+        void *wire = nullptr;
+        err = cudaMallocAsync(&wire, n * sizeof(W), r->compute);
+        if (err != cudaSuccess) return err;
+        err = cudaMemcpyAsync(wire, src->las, n * sizeof(W), cudaMemcpyHostToDevice, r->compute);
+        if (err != cudaSuccess) return err;
+        const unsigned int grid = (unsigned int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+        la_repack_kernel<Num, IterT><<<grid, 256, 0, r->compute>>>(static_cast<const W *>(wire), static_cast<D *>(la.las.ptr), n);
+        cudaFreeAsync(wire, r->compute);
     }
-    cudaError_t err = cudaMallocAsync(&la.las.ptr, host.size() * sizeof(D), r->compute);
-    if (err != cudaSuccess) return err;
-    la.las.bytes = host.size() * sizeof(D);
-    err = cudaMemcpyAsync(la.las.ptr, host.data(), la.las.bytes, cudaMemcpyHostToDevice, r->compute);
-    if (err != cudaSuccess) return err;
     const size_t sbytes = (src->num_stages ? src->num_stages : 1) * sizeof(StageRec<IterT>);
     err = cudaMallocAsync(&la.stages.ptr, sbytes, r->compute);
     if (err != cudaSuccess) return err;
@@ -327,10 +350,6 @@ template <class Num, class IterT> uint32_t upload_la_typed(fs_renderer *r, const
         err = cudaMemcpyAsync(la.stages.ptr, src->stages, src->num_stages * sizeof(StageRec<IterT>), cudaMemcpyHostToDevice, r->compute);
         if (err != cudaSuccess) return err;
     }
-    // the staging vector must outlive the async copy (pageable source: the runtime stages it before
-    // returning, but be explicit)
-    err = cudaStreamSynchronize(r->compute);
-    if (err != cudaSuccess) return err;
     AtDev<Num, IterT> at;
     memset(&at, 0, sizeof(at));
     if (src->at) {
@@ -385,7 +404,8 @@ template <class K> int resident_ctas(fs_renderer *r, K kernel) {
     return per_sm * r->num_sms;
 }
 
-void begin_render(fs_renderer *r) {
+void begin_render(fs_renderer *r, bool streams_to_sink = false) {
+    r->sink_filled = streams_to_sink && r->sink_dev != nullptr; // any other render makes the host copy stale
     cudaMemsetAsync(r->tile_counter, 0, sizeof(unsigned int), r->compute);
     cudaEventRecord(r->ev_start, r->compute);
 }
@@ -430,6 +450,7 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     A.centerX = load_pod<Real>(cx);
     A.centerY = load_pod<Real>(cy);
     A.n_iterations = (IterT)n_iter;
+    A.sink = static_cast<IterT *>(r->sink_dev);
     A.tile_counter = r->tile_counter;
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     const bool count = r->count_steps;
@@ -444,7 +465,7 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
                 r->at_state.bytes = need;
             }
             A.at_state = static_cast<float4 *>(r->at_state.ptr);
-            begin_render(r);
+            begin_render(r, true);
 #define FS_LAUNCH_SPLIT(MODE, COUNT)                                                                                   \
     {                                                                                                                  \
         auto ka = lav2_kernel<Num, IterT, MODE, COUNT, AtPhase::AtOnly>;                                               \
@@ -460,7 +481,7 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
             return end_render(r);
         }
     }
-    begin_render(r);
+    begin_render(r, true);
 #define FS_LAUNCH_LAV2(MODE)                                                                                           \
     if (count) { auto k = lav2_kernel<Num, IterT, MODE, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }     \
     else { auto k = lav2_kernel<Num, IterT, MODE, false>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
@@ -823,6 +844,7 @@ uint32_t fs_initialize_perturb(fs_renderer *r, uint32_t iter_bytes, int32_t nume
 
 void fs_clear_memory(fs_renderer *r) {
     if (!r || !r->compute) return;
+    r->sink_filled = false;
     DeviceGuard g(r->device);
     if (r->iter_buf) cudaMemsetAsync(r->iter_buf, 0, r->n_cu * r->iter_bytes, r->compute);
     if (r->red_dev) cudaMemsetAsync(r->red_dev, 0, r->iter_bytes, r->compute);
@@ -945,13 +967,43 @@ uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buf
     uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream) : run_post<uint32_t>(r, n_iterations, stream);
     if (rc) return rc;
     cudaError_t err = cudaSuccess;
-    if (iter_buffer) {
+    if (iter_buffer && !(r->sink_filled && iter_buffer == r->sink_host)) { // a filled sink already holds the frame
         err = cudaMemcpyAsync(iter_buffer, r->iter_buf, r->n_cu * r->iter_bytes, cudaMemcpyDefault, stream);
         if (err != cudaSuccess) return err;
     }
     if (color_buffer) {
         err = cudaMemcpyAsync(color_buffer, r->color_buf, r->n_color_cu * sizeof(Color16), cudaMemcpyDefault, stream);
         if (err != cudaSuccess) return err;
+    }
+    if (reduction_results) {
+        err = cudaMemcpyAsync(reduction_results, r->red_dev, sizeof(Reduction), cudaMemcpyDefault, stream);
+        if (err != cudaSuccess) return err;
+    }
+    return 0;
+}
+
+// Multi-GPU result path: only the 4-row bands this shard rendered leave the device (one strided 2-D copy), so N
+// ranks writing into one host frame (e.g. a registered shared-memory mapping) assemble it with no collective and
+// 1/N of the PCIe bytes each.  The reduction results cover this shard's rows (the others are zero on this device).
+uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *iter_buffer,
+                                 fs_reduction *reduction_results, int32_t progressive) {
+    if (!r || !memory_initialized(r)) return 0;
+    if (r->shard_count <= 1) return fs_render_current(r, n_iterations, iter_buffer, nullptr, reduction_results, progressive);
+    DeviceGuard g(r->device);
+    cudaStream_t stream = progressive ? r->display : r->compute;
+    uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream) : run_post<uint32_t>(r, n_iterations, stream);
+    if (rc) return rc;
+    cudaError_t err = cudaSuccess;
+    if (iter_buffer && !(r->sink_filled && iter_buffer == r->sink_host)) {
+        const size_t row_bytes = (size_t)r->w_block * NB_THREADS_W * r->iter_bytes;
+        const size_t bands = (size_t)r->h_block * NB_THREADS_H / 4; // padded height is a multiple of 8
+        const size_t owned = (bands - r->shard_index + r->shard_count - 1) / r->shard_count;
+        const size_t first = (size_t)r->shard_index * 4 * row_bytes, stride = (size_t)r->shard_count * 4 * row_bytes;
+        if (owned) {
+            err = cudaMemcpy2DAsync((char *)iter_buffer + first, stride, (const char *)r->iter_buf + first, stride,
+                                    4 * row_bytes, owned, cudaMemcpyDefault, stream);
+            if (err != cudaSuccess) return err;
+        }
     }
     if (reduction_results) {
         err = cudaMemcpyAsync(reduction_results, r->red_dev, sizeof(Reduction), cudaMemcpyDefault, stream);
@@ -1060,6 +1112,34 @@ uint32_t fs_measure_fp32_issue_peak(int32_t device, double *ffma_per_second) {
     cudaFree(sink);
     *ffma_per_second = best;
     return err;
+}
+
+// Streams the iteration buffer to the host while the render runs.  `host_iter_buffer` has the layout fs_render_current
+// fills; if it is not page-locked yet it is registered here (and unregistered when the sink is dropped).
+uint32_t fs_set_result_sink(fs_renderer *r, void *host_iter_buffer, uint64_t bytes) {
+    if (!r || !memory_initialized(r)) return FS_ERROR_UNSUPPORTED;
+    DeviceGuard g(r->device);
+    cudaStreamSynchronize(r->compute);
+    drop_sink(r);
+    if (!host_iter_buffer) return 0;
+    if (bytes < r->n_cu * r->iter_bytes) return cudaErrorInvalidValue;
+    void *dev = nullptr;
+    cudaError_t err = cudaHostGetDevicePointer(&dev, host_iter_buffer, 0);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        err = cudaHostRegister(host_iter_buffer, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+        if (err != cudaSuccess) return err;
+        r->sink_registered = true;
+        r->sink_host = host_iter_buffer;
+        err = cudaHostGetDevicePointer(&dev, host_iter_buffer, 0);
+        if (err != cudaSuccess) {
+            drop_sink(r);
+            return err;
+        }
+    }
+    r->sink_host = host_iter_buffer;
+    r->sink_dev = dev;
+    return 0;
 }
 
 uint32_t fs_set_split_at(fs_renderer *r, int32_t enable) {

@@ -66,6 +66,7 @@ template <class Num, class IterT> struct Lav2Args {
     unsigned int *tile_counter;
     unsigned long long *step_counter; // optional: executed perturbation/LA/AT steps (bench roofline)
     float4 *at_state;                 // HDRx32 two-launch form: per-pixel AT result {dz.re, dz.im, dz.e}; iter sits in `out`
+    IterT *sink;                      // optional mapped host copy of `out` (fs_set_result_sink): finished pixels stream out over PCIe
 };
 
 // How a launch treats the AT shortcut.  Fused = one launch does everything (the reference's structure).  On deep views
@@ -380,7 +381,11 @@ __global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A)
                                                 RefIteration, iter, steps);
         }
 
-        if (live) A.out[(size_t)Y * A.pitch + X] = iter;
+        if (live) {
+            const size_t cell = (size_t)Y * A.pitch + X;
+            A.out[cell] = iter;
+            if (A.sink) A.sink[cell] = iter; // 8 lanes per row: one 32-byte posted write
+        }
     }
 
     if (Count && A.step_counter) {

@@ -149,6 +149,33 @@ class GPURenderer:
             rc = self.SyncDisplayStream() if progressive else self.SyncComputeStream()
         return rc, iters, colors, {"Min": int(red.Min), "Max": int(red.Max), "Sum": int(red.Sum)}
 
+    def RenderCurrentShard(self, n_iterations: int, iters_out, progressive: bool = False):
+        """Multi-GPU form: copies only the 4-row bands this shard rendered (``SetShard``) into the same positions of
+        ``iters_out`` -- a caller-owned whole-frame host array, typically one shared-memory frame every rank writes
+        into -- and leaves the other rows untouched.  Returns ``(status, reduction over this shard's rows)``."""
+        hp, wp = self.buffer_shape()
+        dt = np.uint32 if self._iter_bytes == 4 else np.uint64
+        assert iters_out.shape == (hp, wp) and iters_out.dtype == dt and iters_out.flags["C_CONTIGUOUS"]
+        red = N.FsReduction()
+        rc = int(self._lib.fs_render_current_shard(self._h, n_iterations, iters_out.ctypes.data, C.byref(red),
+                                                   int(progressive)))
+        if rc == 0:
+            rc = self.SyncDisplayStream() if progressive else self.SyncComputeStream()
+        return rc, {"Min": int(red.Min), "Max": int(red.Max), "Sum": int(red.Sum)}
+
+    def SetResultSink(self, frame) -> int:
+        """``frame``: whole-frame host array of the padded shape (page-locked, or registered by the call) the LAv2
+        kernels stream finished pixels into while they render; ``RenderCurrent(iters_out=frame)`` /
+        ``RenderCurrentShard(n, frame)`` then skip their copy.  ``None`` removes the sink."""
+        if frame is None:
+            self._sink = None
+            return int(self._lib.fs_set_result_sink(self._h, None, 0))
+        hp, wp = self.buffer_shape()
+        dt = np.uint32 if self._iter_bytes == 4 else np.uint64
+        assert frame.shape == (hp, wp) and frame.dtype == dt and frame.flags["C_CONTIGUOUS"]
+        self._sink = frame  # keep the mapping alive as long as the device may write into it
+        return int(self._lib.fs_set_result_sink(self._h, frame.ctypes.data, frame.nbytes))
+
     def _aa(self) -> int:
         return getattr(self, "_antialiasing", 1)
 

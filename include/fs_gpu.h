@@ -101,7 +101,10 @@ uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, u
                               uint64_t palette_generation, int32_t expected_reuse);
 
 /* GPURenderer::InitializePerturb<IterType,T1,SubType,PExtras,T2>  GPU_Render.h:102-108.
- * perturb2 / la may be NULL exactly as in the reference. */
+ * perturb2 / la may be NULL exactly as in the reference.  The uploads are queued on the compute stream: pageable
+ * sources are consumed before the call returns (as with the reference's cudaMemcpy); PAGE-LOCKED sources are read
+ * asynchronously and must stay unchanged until the stream has passed the upload (fs_sync_compute_stream, or the
+ * result call of the render that follows). */
 uint32_t fs_initialize_perturb(fs_renderer *r, uint32_t iter_bytes, int32_t numeric1, int32_t pextras,
                                uint64_t generation1, const fs_orbit *perturb1, int32_t numeric2, uint64_t generation2,
                                const fs_orbit *perturb2, const fs_la_reference *la);
@@ -136,6 +139,21 @@ uint32_t fs_render_perturb_bla_scaled(fs_renderer *r, uint32_t algorithm, int32_
  * roundup16(w)*roundup8(h) IterType cells, color_buffer roundup16(w/aa)*roundup8(h/aa) cells; any may be NULL. */
 uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buffer, fs_color16 *color_buffer,
                            fs_reduction *reduction_results, int32_t progressive);
+
+/* Sharded form of RenderCurrent (no reference counterpart: the reference drives one GPU, GPU_Render.h:123-129 is the
+ * whole-frame call).  After fs_set_shard(n, i) it copies only the 4-row bands shard i rendered into the same
+ * positions of iter_buffer (whole-frame layout as above), so n processes can fill one host frame without a
+ * collective.  With one shard it is fs_render_current without a colour buffer. */
+uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *iter_buffer,
+                                 fs_reduction *reduction_results, int32_t progressive);
+
+/* Result sink (no reference counterpart; the reference copies the frame after the render, GPU_Render.cu:1768-1788).
+ * Once set, the LAv2 render kernels store every finished pixel into `host_iter_buffer` (page-locked, or registered
+ * here) as well as into the device buffer, so the frame crosses PCIe during the render; a following
+ * fs_render_current / fs_render_current_shard given the same pointer skips its copy.  Rows a shard does not own are
+ * not written.  Other render entries ignore the sink (their RenderCurrent copies as usual).  NULL removes it;
+ * fs_initialize_memory and fs_destroy drop it. */
+uint32_t fs_set_result_sink(fs_renderer *r, void *host_iter_buffer, uint64_t bytes);
 
 uint32_t fs_sync_compute_stream(fs_renderer *r);   /* GPU_Render.h:131 */
 uint32_t fs_sync_display_stream(fs_renderer *r);   /* GPU_Render.h:132 */

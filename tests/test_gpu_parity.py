@@ -144,6 +144,42 @@ def test_full_size_properties_without_reference():
     assert r.SetShard(1, 0) == 0
     np.testing.assert_array_equal(merge_shards(bufs, h)[:h, :w], outs[0][:h, :w])
     assert sums == int(outs[0][:h, :w].astype(np.uint64).sum())
+    # the sharded result call fills ONE host frame band by band (no merge step); rows it does not own stay untouched
+    frame = np.full_like(outs[0], 0xDEADBEEF)
+    for s in range(3):
+        assert r.SetShard(3, s) == 0
+        r.ClearMemory()
+        assert r.RenderPerturbLAv2(alg, coords, n) == 0
+        before = frame.copy()
+        rc, red = r.RenderCurrentShard(n, frame)
+        assert rc == 0
+        rows = rows_of_shard(h, 3, s)
+        other = np.setdiff1d(np.arange(frame.shape[0]), np.concatenate([rows, np.arange(h, frame.shape[0])]))
+        np.testing.assert_array_equal(frame[other], before[other])
+        assert red["Sum"] == int(frame[rows, :w].astype(np.uint64).sum())
+    np.testing.assert_array_equal(frame[:h, :w], outs[0][:h, :w])
+    # result sink: the kernel streams finished pixels into a host frame while it renders; RenderCurrent on the same
+    # frame then skips its copy.  A render entry that does not stream (here: after ClearMemory alone) copies as usual.
+    assert r.SetShard(1, 0) == 0
+    sink = np.full_like(outs[0], 0xDEADBEEF)
+    assert r.SetResultSink(sink) == 0
+    r.ClearMemory()
+    assert r.RenderPerturbLAv2(alg, coords, n) == 0
+    assert r.SyncComputeStream() == 0
+    np.testing.assert_array_equal(sink[:h, :w], outs[0][:h, :w])          # arrived before any RenderCurrent
+    rc, it, _, red = r.RenderCurrent(n, iters_out=sink)
+    assert rc == 0 and it is sink and red["Sum"] == int(outs[0][:h, :w].astype(np.uint64).sum())
+    r.ClearMemory()
+    rc, it, _, red = r.RenderCurrent(n, iters_out=sink)                   # nothing streamed since the clear: plain copy
+    assert rc == 0 and not sink[:h, :w].any()
+    for s_ in range(2):                                                   # two shards stream into the one frame
+        assert r.SetShard(2, s_) == 0
+        r.ClearMemory()
+        assert r.RenderPerturbLAv2(alg, coords, n) == 0
+        rc, red = r.RenderCurrentShard(n, sink)
+        assert rc == 0
+    np.testing.assert_array_equal(sink[:h, :w], outs[0][:h, :w])
+    assert r.SetResultSink(None) == 0
     # sampled rows against the CPU oracle
     want, _ = oracle_cpu.render_lav2(alg, w, h, coords, orbit, la, n, rows=(0, h), row_step=270, col_step=7,
                                      threads=oracle_cpu.hardware_threads())
