@@ -315,6 +315,9 @@ def main():
         dist.barrier()
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name)
+            # rank 0 owns the segment; keep this process's resource tracker from unlinking it a second time at exit
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
         frame = np.ndarray((hp, wp), dtype=np.uint32, buffer=shm.buf)
         if rank == 0:
             frame[:] = 0
