@@ -398,7 +398,8 @@ def main():
                 "traffic": {14: 5.47e6 + 0.18e6, 5: 0.69e6 + 0.09e6}.get(VIEW_ID),
                 "note": "compute-bound scalar path (SURVEY.md 8d): not HBM, not tensor. achieved = executed "
                         "steps/launch by kind (device counters) x FP32 mantissa instr per step (AT pass 9, LA step 22, "
-                        "HDRx32 perturbation step 20) / kernel time; "
+                        "HDRx32 perturbation step 20) / kernel time (the credit is the reference formulation's work per "
+                        "pass; the kernel's lean chunk loop issues 7 FP32 + 2/16 for the escape test per AT pass); "
                         "peak = FFMA issue rate measured live by fs_measure_fp32_issue_peak on this GPU "
                         "(MEASURED_PEAKS.json has only HBM/bf16 peaks).",
                 "executed_steps_per_launch": exec_steps,

@@ -24,6 +24,8 @@ template <class M> struct Plan {
     M s;     // 2^E
     M thr;   // R.m * 2^(R.e - 2E)
     int E;
+    bool mono; // R > 4 and |c| <= R/4: past the escape radius |z| only grows (see lav2_at), so an escape anywhere in a
+               // chunk of passes is still visible in the chunk's last pass
 };
 
 // c: reduced; R = SqrEscapeRadius.  `passes` = n_iterations / StepLength (the plan needs at least one pass: the
@@ -36,6 +38,11 @@ template <class M> FS_HD Plan<M> plan(HdrC<M> c, Hdr<M> R, bool passes) {
     p.ok = passes && c.e <= 0 && c.e > -EXP_DIFF_IGNORED && R.m >= M(1) && R.m < M(2) && sh <= kMaxShift && sh >= -kMaxShift;
     p.s = p.ok ? MT<M>::pow2(c.e) : M(0);
     p.thr = p.ok ? R.m * MT<M>::pow2(sh) : M(0);
+    // real-valued R and |c|^2 (R <= 2^32 for the 32-bit exponent range the table builder uses, LAInfoDeep.h:486-494;
+    // anything that overflows or is NaN fails the comparisons and takes the running-maximum form)
+    const M Rv = R.m * MT<M>::pow2(R.e);
+    const M c2 = (c.re * c.re + c.im * c.im) * p.s * p.s;
+    p.mono = p.ok && R.e < 40 && Rv > M(4) && c2 <= Rv * Rv * M(0.0625);
     return p;
 }
 

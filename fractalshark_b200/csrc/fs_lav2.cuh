@@ -12,11 +12,15 @@
 #pragma once
 #include "fs_num.cuh"
 #include "fs_df32.cuh"
+#include <type_traits>
 #include "fs_perturb_loop.cuh"
 #include "fs_at_fast.cuh"
 
 #ifndef FS_AT_PACKED
 #define FS_AT_PACKED 1
+#endif
+#ifndef FS_AT_LEAN
+#define FS_AT_LEAN 0
 #endif
 
 namespace fs {
@@ -176,53 +180,65 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                 const M s = plan.s, thr = plan.thr;
                 const int E = plan.E;
                 M re = M(0), im = M(0);
-                // sixteen passes per escape test: the running maximum of |z|^2 over the chunk decides whether any
-                // pass escaped (an overflowed pass shows as +inf before any NaN can form); if one did, the chunk
-                // is replayed pass by pass from its saved start to stop at the exact pass
+                // sixteen passes per escape test; if a pass of the chunk escaped, the chunk is replayed pass by pass
+                // from its saved start to stop at the exact pass.  Which pass values decide "some pass escaped":
+                //  * lean form (plan.mono: R > 4 and |c| <= R/4): once |z|^2 > R, |z'| >= |z|^2 - |c| > 3R/4 > 1.5 sqrt(R),
+                //    so |z|^2 stays above R (by a factor > 2.25 per pass, or turns inf/NaN) -- the value entering
+                //    the LAST pass of the chunk tells whether any earlier one was over.  No norm, no max on the
+                //    other fifteen passes.
+                //  * otherwise the running maximum of |z|^2 over the chunk (an overflowed pass shows as +inf before
+                //    any NaN can form).
                 constexpr int kAtChunk = 16;
-                if constexpr (sizeof(M) == 4 && FS_AT_PACKED) {
-                    // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
-                    const f32x2 s2 = f2_make(s, s), c2 = f2_make(c.re, c.im);
-                    while (i + kAtChunk <= at_max) {
-                        const float re0 = re, im0 = im;
-                        float worst = 0.0f;
-                        f32x2 z2 = f2_make(re, im);
+                auto chunks = [&](auto lean_tag) {
+                    constexpr bool kLean = decltype(lean_tag)::value;
+                    if constexpr (sizeof(M) == 4 && FS_AT_PACKED) {
+                        // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
+                        const f32x2 s2 = f2_make(s, s), c2 = f2_make(c.re, c.im);
+                        while (i + kAtChunk <= at_max) {
+                            const float re0 = re, im0 = im;
+                            float worst = 0.0f;
+                            f32x2 z2 = f2_make(re, im);
 #pragma unroll
-                        for (int u = 0; u < kAtChunk; u++) {
-                            float rr, ii;
-                            f2_split(f2_mul(z2, z2), rr, ii);
-                            worst = fmaxf(worst, rr + ii);
-                            const float t = fma_(re, im, re * im);
-                            z2 = f2_fma(f2_make(rr - ii, t), s2, c2);
-                            f2_split(z2, re, im);
+                            for (int u = 0; u < kAtChunk; u++) {
+                                float rr, ii;
+                                f2_split(f2_mul(z2, z2), rr, ii);
+                                if (!kLean) worst = fmaxf(worst, rr + ii);
+                                else if (u == kAtChunk - 1) worst = rr + ii;
+                                const float t = fma_(re, im, re * im);
+                                z2 = f2_fma(f2_make(rr - ii, t), s2, c2);
+                                f2_split(z2, re, im);
+                            }
+                            if (!(worst <= thr)) {
+                                re = re0;
+                                im = im0;
+                                break;
+                            }
+                            i += kAtChunk;
                         }
-                        if (!(worst <= thr)) {
-                            re = re0;
-                            im = im0;
-                            break;
-                        }
-                        i += kAtChunk;
-                    }
-                } else {
-                    while (i + kAtChunk <= at_max) {
-                        const M re0 = re, im0 = im;
-                        M worst = M(0);
+                    } else {
+                        while (i + kAtChunk <= at_max) {
+                            const M re0 = re, im0 = im;
+                            M worst = M(0);
 #pragma unroll
-                        for (int u = 0; u < kAtChunk; u++) {
-                            const M rr = re * re, ii = im * im;
-                            worst = fmax(worst, rr + ii);
-                            const M t = fma_(re, im, re * im);
-                            re = fma_(rr - ii, s, c.re);
-                            im = fma_(t, s, c.im);
+                            for (int u = 0; u < kAtChunk; u++) {
+                                const M rr = re * re, ii = im * im;
+                                if (!kLean) worst = fmax(worst, rr + ii);
+                                else if (u == kAtChunk - 1) worst = rr + ii;
+                                const M t = fma_(re, im, re * im);
+                                re = fma_(rr - ii, s, c.re);
+                                im = fma_(t, s, c.im);
+                            }
+                            if (!(worst <= thr)) {
+                                re = re0;
+                                im = im0;
+                                break;
+                            }
+                            i += kAtChunk;
                         }
-                        if (!(worst <= thr)) {
-                            re = re0;
-                            im = im0;
-                            break;
-                        }
-                        i += kAtChunk;
                     }
-                }
+                };
+                if (FS_AT_LEAN && plan.mono) chunks(std::true_type{});
+                else chunks(std::false_type{});
                 for (; i < at_max; i++) {
                     if (atfast::escaped(atfast::norm(re, im), thr)) break;
                     atfast::advance(re, im, s, c.re, c.im);

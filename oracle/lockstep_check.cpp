@@ -79,7 +79,7 @@ IterT lockstep_pixel(const Lav2Job<IterT> &J, const fs::scaled::FastElem *tab, i
 // (oracle_cpu.cpp lav2_prologue, ATInfo.h:155-188), pass by pass: same escape decision at every pass, same mantissas
 // bit for bit, exponent equal to c's after the first pass.
 struct AtStats {
-    uint64_t pixels = 0, refused = 0, passes = 0, mismatches = 0, escaped = 0;
+    uint64_t pixels = 0, refused = 0, passes = 0, mismatches = 0, escaped = 0, mono = 0;
 };
 template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, int Y, uint64_t max_passes, AtStats &st) {
     const HF DeltaReal = sub(mul(J.dx, hf_from_number((float)X)), J.centerX);
@@ -97,6 +97,7 @@ template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, in
                                                                  fs::Hdr<float>{AT.SqrEscapeRadius.mantissa, AT.SqrEscapeRadius.exp},
                                                                  n_pass > 0);
     if (!plan.ok) { st.refused++; return; }
+    if (plan.mono) st.mono++;
     HC z = hc_zero();
     float re = 0.0f, im = 0.0f;
     for (uint64_t i = 0; i < n_pass; i++) {
@@ -106,7 +107,17 @@ template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, in
         const bool esc_o = cmpPR(nsq, AT.SqrEscapeRadius) > 0;
         const bool esc_f = fs::atfast::escaped(fs::atfast::norm(re, im), plan.thr);
         if (esc_o != esc_f) { st.mismatches++; return; }
-        if (esc_o) { st.escaped++; return; }
+        if (esc_o) {
+            st.escaped++;
+            // the lean chunk test of lav2_at relies on this: with plan.mono an escaped |z|^2 stays escaped (or turns
+            // inf/NaN) on every later pass, so the last pass of a 16-pass chunk still shows it
+            if (plan.mono)
+                for (int k = 0; k < 16; k++) {
+                    fs::atfast::advance(re, im, plan.s, c.re, c.im);
+                    if (!fs::atfast::escaped(fs::atfast::norm(re, im), plan.thr)) { st.mismatches++; return; }
+                }
+            return;
+        }
         const int32_t e2 = z.exp + z.exp;
         HC z2{rr - ii, fmaf(z.re, z.im, z.re * z.im), e2 < MIN_BIG_EXPONENT ? MIN_BIG_EXPONENT : e2};
         z = add(z2, c);
@@ -120,7 +131,8 @@ template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, in
 
 extern "C" {
 
-// stats[5]: pixels that take the AT shortcut, pixels the fast form refused, passes compared, mismatches, pixels escaped
+// stats[6]: pixels that take the AT shortcut, pixels the fast form refused, passes compared, mismatches, pixels escaped,
+// pixels whose plan allows the lean (last-pass-only) chunk test
 uint64_t lockstep_at(const void *at, int use_at, int is_valid, int w, int h, const void *dx, const void *dy,
                      const void *cenx, const void *ceny, uint64_t n_iter, uint64_t max_passes, int col_step, int row_step,
                      uint64_t *stats) {
@@ -137,7 +149,7 @@ uint64_t lockstep_at(const void *at, int use_at, int is_valid, int w, int h, con
     AtStats st;
     for (int y = 0; y < h; y += (row_step < 1 ? 1 : row_step))
         for (int x = 0; x < w; x += (col_step < 1 ? 1 : col_step)) lockstep_at_pixel(J, x, y, max_passes, st);
-    stats[0] = st.pixels; stats[1] = st.refused; stats[2] = st.passes; stats[3] = st.mismatches; stats[4] = st.escaped;
+    stats[0] = st.pixels; stats[1] = st.refused; stats[2] = st.passes; stats[3] = st.mismatches; stats[4] = st.escaped; stats[5] = st.mono;
     return st.mismatches;
 }
 

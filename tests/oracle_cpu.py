@@ -169,7 +169,7 @@ def lockstep_at(w, h, coords, la, n_iter, max_passes=20000, col_step=1, row_step
     fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                    C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
     l = la.descriptor()
-    stats = (C.c_uint64 * 5)()
+    stats = (C.c_uint64 * 6)()
     fn(l.at, l.use_at, l.is_valid, w, h, _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]),
        _buf(coords["center_y"]), n_iter, max_passes, col_step, row_step, stats)
-    return dict(zip(("pixels", "refused", "passes", "mismatches", "escaped"), (int(v) for v in stats)))
+    return dict(zip(("pixels", "refused", "passes", "mismatches", "escaped", "mono"), (int(v) for v in stats)))
