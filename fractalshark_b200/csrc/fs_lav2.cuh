@@ -20,7 +20,10 @@
 #define FS_AT_PACKED 1
 #endif
 #ifndef FS_AT_LEAN
-#define FS_AT_LEAN 0
+#define FS_AT_LEAN 1
+#endif
+#ifndef FS_AT_CHUNK
+#define FS_AT_CHUNK 16
 #endif
 
 namespace fs {
@@ -188,7 +191,7 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                 //    other fifteen passes.
                 //  * otherwise the running maximum of |z|^2 over the chunk (an overflowed pass shows as +inf before
                 //    any NaN can form).
-                constexpr int kAtChunk = 16;
+                constexpr int kAtChunk = FS_AT_CHUNK;
                 auto chunks = [&](auto lean_tag) {
                     constexpr bool kLean = decltype(lean_tag)::value;
                     if constexpr (sizeof(M) == 4 && FS_AT_PACKED) {
