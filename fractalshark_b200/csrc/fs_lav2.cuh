@@ -25,6 +25,15 @@
 #ifndef FS_AT_CHUNK
 #define FS_AT_CHUNK 16
 #endif
+// resident CTAs per SM the compiler must allow for lav2_kernel; undefined = plain __launch_bounds__(256) (HDRx32: 60
+// registers, 4 CTAs; an explicit 1 lets ptxas take 70 registers = 3 CTAs: View 5 29.0 vs 27.7 ms).
+// Measured: 5 (48 registers, 32 B spilled) View 14 7.13 vs 7.29 ms but View 5 28.8 vs 27.7 ms and an 8-way shard 1.17
+// vs 1.08 ms; 6 (40 registers) worse everywhere.
+#ifdef FS_LAV2_MIN_CTAS
+#define FS_LAV2_BOUNDS __launch_bounds__(256, FS_LAV2_MIN_CTAS)
+#else
+#define FS_LAV2_BOUNDS __launch_bounds__(256)
+#endif
 
 namespace fs {
 
@@ -336,7 +345,7 @@ FS_D void lav2_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc
 }
 
 template <class Num, class IterT, Lav2Mode Mode, bool Count, AtPhase Phase = AtPhase::Fused>
-__global__ void __launch_bounds__(256) lav2_kernel(const Lav2Args<Num, IterT> A) {
+__global__ void FS_LAV2_BOUNDS lav2_kernel(const Lav2Args<Num, IterT> A) {
     using Real = typename Num::Real;
     using Cplx = typename Num::Cplx;
 
