@@ -104,6 +104,7 @@ struct fs_renderer {
     // run, so the device->host transfer of the frame overlaps the render instead of following it
     void *sink_host = nullptr, *sink_dev = nullptr;
     bool sink_registered = false, sink_filled = false;
+    int ctas_per_sm_cap = 0; // FS_CTAS_PER_SM: experiment switch, caps the persistent grid below full occupancy
     bool split_at = false;  // HDRx32 + AT: AT shortcut in its own launch ahead of the LA/perturbation launch (fs_lav2.cuh AtPhase);
                             // measured slower than the fused launch (View 14: 9.7 vs 8.5 ms), kept as an A/B switch
     DeviceBlob at_state;    // float4 per iteration-buffer cell, allocated on first use
@@ -401,6 +402,21 @@ uint32_t upload_la(fs_renderer *r, int numeric, uint32_t iter_bytes, const fs_la
 template <class K> int resident_ctas(fs_renderer *r, K kernel) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (r->ctas_per_sm_cap > 0 && per_sm > r->ctas_per_sm_cap) per_sm = r->ctas_per_sm_cap;
+    return per_sm * r->num_sms;
+}
+
+// Grid of the LAv2 kernels.  Full occupancy (4 CTAs/SM for HDRx32) is best while every warp gets many tiles; once a
+// shard is down to a handful of tiles per warp (View 14 at 8 GPUs: 32,400 tiles for 4,736 warps) the launch lasts as
+// long as its slowest warps, and those run faster with fewer co-resident warps competing for the FP32 pipe: 3 CTAs/SM
+// measured 1.035 vs 1.088 ms on that shard, 1.95 vs 1.88 ms on the 4-way shard (13.7 tiles per warp), 7.64 vs 7.30 ms
+// on the whole frame.  Below 8 tiles per warp the grid drops to 3/4 of the occupancy.
+template <class K> int lav2_grid(fs_renderer *r, K kernel) {
+    int per_sm = resident_ctas(r, kernel) / r->num_sms;
+    const uint64_t tiles_x = (r->width + 7) / 8;
+    const uint64_t bands = ((r->height + 3) / 4 + r->shard_count - 1 - r->shard_index) / r->shard_count;
+    const uint64_t warps = (uint64_t)per_sm * r->num_sms * 8;
+    if (r->ctas_per_sm_cap == 0 && per_sm >= 4 && tiles_x * bands < 8 * warps) per_sm = per_sm * 3 / 4;
     return per_sm * r->num_sms;
 }
 
@@ -469,10 +485,10 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
 #define FS_LAUNCH_SPLIT(MODE, COUNT)                                                                                   \
     {                                                                                                                  \
         auto ka = lav2_kernel<Num, IterT, MODE, COUNT, AtPhase::AtOnly>;                                               \
-        ka<<<resident_ctas(r, ka), 256, 0, r->compute>>>(A);                                                           \
+        ka<<<lav2_grid(r, ka), 256, 0, r->compute>>>(A);                                                           \
         cudaMemsetAsync(r->tile_counter, 0, sizeof(unsigned int), r->compute);                                        \
         auto kb = lav2_kernel<Num, IterT, MODE, COUNT, AtPhase::AfterAt>;                                              \
-        kb<<<resident_ctas(r, kb), 256, 0, r->compute>>>(A);                                                           \
+        kb<<<lav2_grid(r, kb), 256, 0, r->compute>>>(A);                                                           \
     }
             if (mode == FS_LAV2_FULL) { if (count) FS_LAUNCH_SPLIT(Lav2Mode::Full, true) else FS_LAUNCH_SPLIT(Lav2Mode::Full, false) }
             else { if (count) FS_LAUNCH_SPLIT(Lav2Mode::LAO, true) else FS_LAUNCH_SPLIT(Lav2Mode::LAO, false) }
@@ -483,8 +499,8 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     }
     begin_render(r, true);
 #define FS_LAUNCH_LAV2(MODE)                                                                                           \
-    if (count) { auto k = lav2_kernel<Num, IterT, MODE, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }     \
-    else { auto k = lav2_kernel<Num, IterT, MODE, false>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
+    if (count) { auto k = lav2_kernel<Num, IterT, MODE, true>; k<<<lav2_grid(r, k), 256, 0, r->compute>>>(A); }         \
+    else { auto k = lav2_kernel<Num, IterT, MODE, false>; k<<<lav2_grid(r, k), 256, 0, r->compute>>>(A); }
     switch (mode) {
     case FS_LAV2_FULL: FS_LAUNCH_LAV2(Lav2Mode::Full) break;
     case FS_LAV2_PO: FS_LAUNCH_LAV2(Lav2Mode::PO) break;
@@ -722,6 +738,7 @@ fs_renderer *fs_create(int32_t device) {
         r->device = device;
         // development switches (profiling under ncu without touching the caller): FS_SPLIT_AT=1, FS_SCALED_STEPS=0
         if (const char *e = getenv("FS_SPLIT_AT")) r->split_at = atoi(e) != 0;
+        if (const char *e = getenv("FS_CTAS_PER_SM")) r->ctas_per_sm_cap = atoi(e);
         if (const char *e = getenv("FS_SCALED_STEPS")) r->use_scaled = atoi(e) != 0;
     }
     return r;
