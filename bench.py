@@ -394,8 +394,8 @@ def main():
     roofline = {"bound": "fp32_issue", "achieved": achieved / 1e12, "peak": peak * world / 1e12, "unit": "T FP32 instr/s",
                 "frac": achieved / (peak * world),
                 # dram__bytes_read.sum + dram__bytes_write.sum of the render kernel, one `ncu --set full` capture per view
-                # (profiles/r1_lav2_v10_view14_summary.md, r1_lav2_v7_summary.md); bytes per launch
-                "traffic": {14: 5.47e6 + 0.18e6, 5: 0.69e6 + 0.09e6}.get(VIEW_ID),
+                # (profiles/r1_lav2_v12_view14_summary.md, r1_lav2_v7_summary.md); bytes per launch
+                "traffic": {14: 5.47e6 + 0.15e6, 5: 0.69e6 + 0.09e6}.get(VIEW_ID),
                 "note": "compute-bound scalar path (SURVEY.md 8d): not HBM, not tensor. achieved = executed "
                         "steps/launch by kind (device counters) x FP32 mantissa instr per step (AT pass 9, LA step 22, "
                         "HDRx32 perturbation step 20) / kernel time (the credit is the reference formulation's work per "
