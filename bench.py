@@ -304,23 +304,14 @@ def main():
     if world == 1:
         frame = torch.empty((hp, wp), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
     else:
-        from multiprocessing import shared_memory
+        from fractalshark_b200.sharding import SharedFrame
         name = "fsb200_frame_%s" % os.environ.get("MASTER_PORT", "0")
         if rank == 0:
-            try:
-                shared_memory.SharedMemory(name=name).unlink()
-            except FileNotFoundError:
-                pass
-            shm = shared_memory.SharedMemory(name=name, create=True, size=hp * wp * 4)
+            shm = SharedFrame(name, (hp, wp), np.uint32, create=True)
         dist.barrier()
         if rank != 0:
-            shm = shared_memory.SharedMemory(name=name)
-            # rank 0 owns the segment; keep this process's resource tracker from unlinking it a second time at exit
-            from multiprocessing import resource_tracker
-            resource_tracker.unregister(shm._name, "shared_memory")
-        frame = np.ndarray((hp, wp), dtype=np.uint32, buffer=shm.buf)
-        if rank == 0:
-            frame[:] = 0
+            shm = SharedFrame(name, (hp, wp), np.uint32)
+        frame = shm.array
         frame_kind = "shared memory frame every rank writes its bands into"
         dist.barrier()
     # result sink: the kernel stores finished pixels into the host frame while it runs (fs_set_result_sink page-locks
@@ -381,9 +372,8 @@ def main():
         torch.cuda.cudart().cudaHostUnregister(frame.ctypes.data)
     if world > 1:
         del frame
+        dist.barrier()
         shm.close()
-        if rank == 0:
-            shm.unlink()
     # whole-job host<->device bytes per step: every rank uploads its own copy of the tables, the frame leaves once
     h2d, d2h = h2d * world, hp * wp * 4 + 24 * world
     e2e_value = total_sum / e2e_s

@@ -4,11 +4,12 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fractalshark_b200.sharding import merge_shards, rows_of_shard
+from fractalshark_b200.sharding import SharedFrame, band_copy_plan, merge_shards, rows_of_shard
 
 
 def test_bands_partition_the_frame():
@@ -51,6 +52,68 @@ def test_two_rank_reduce_is_a_gather():
     for p in procs:
         p.join(timeout=60)
     assert ok == (True, True)
+
+
+def _frame_worker(rank, world, port, h, w, out_q):
+    """The host side of the multi-GPU result path: every rank writes only its bands, with the strided-copy geometry of
+    fs_render_current_shard, into ONE shared-memory frame; rank 0 reads the whole picture.  No data-path collective."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    hp, wp = (h + 7) // 8 * 8, (w + 15) // 16 * 16                  # padded like the library's buffers
+    rng = np.random.default_rng(99)
+    full = rng.integers(1, 1 << 30, size=(hp, wp), dtype=np.uint32)  # the frame every rank would render
+    name = "fsb200_test_frame_%d" % port
+    shm = SharedFrame(name, (hp, wp), np.uint32, create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        shm = SharedFrame(name, (hp, wp), np.uint32)
+    first, stride, n_bands = band_copy_plan(hp, world, rank)
+    for b in range(n_bands):                                        # what the one cudaMemcpy2DAsync does
+        r0 = first + b * stride
+        shm.array[r0:r0 + 4] = full[r0:r0 + 4]
+    dist.barrier()
+    if rank == 0:
+        owned = [set(range(f + b * s, f + b * s + 4)) for (f, s, n) in (band_copy_plan(hp, world, k) for k in range(world))
+                 for b in range(n)]
+        disjoint_cover = sum(len(o) for o in owned) == hp and set().union(*owned) == set(range(hp))
+        rows_agree = all(np.array_equal(np.array(sorted(set().union(*[set(range(f + b * s, f + b * s + 4)) for b in range(n)]) & set(range(h)))),
+                                        rows_of_shard(h, world, k))
+                         for k, (f, s, n) in ((k, band_copy_plan(hp, world, k)) for k in range(world)))
+        out_q.put((bool(np.array_equal(shm.array, full)), disjoint_cover, rows_agree))
+    dist.barrier()
+    shm.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("h,w", [(37, 50), (64, 48)])
+def test_two_ranks_assemble_one_shared_host_frame(h, w):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_frame_worker, args=(r, 2, port, h, w, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok == (True, True, True)
+    assert all(p.exitcode == 0 for p in procs)
+
+
+def test_band_copy_plan_matches_row_ownership():
+    for hp in (8, 40, 2160):
+        for n in (1, 2, 3, 8):
+            rows = []
+            for k in range(n):
+                first, stride, bands = band_copy_plan(hp, n, k)
+                mine = [r for b in range(bands) for r in range(first + b * stride, first + b * stride + 4)]
+                assert mine == rows_of_shard(hp, n, k).tolist()
+                rows += mine
+            assert sorted(rows) == list(range(hp))
 
 
 def test_merge_shards_helper():
