@@ -131,6 +131,29 @@ template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, in
 
 extern "C" {
 
+// The plan lav2_at makes for one pixel: c = (re, im) x 2^ce (reduced), R = rm x 2^re_.  out[0] = ok (mantissa recurrence
+// applies), out[1] = mono (lean chunk test applies), out[2] = E; thr_out = the pre-scaled escape threshold.
+void lockstep_at_plan(float cre, float cim, int ce, float rm, int re_, int *out, float *thr_out) {
+    const fs::atfast::Plan<float> p = fs::atfast::plan<float>(fs::HdrC<float>{cre, cim, ce}, fs::Hdr<float>{rm, re_}, true);
+    out[0] = p.ok; out[1] = p.mono; out[2] = p.E;
+    *thr_out = p.thr;
+}
+
+// With a lean plan: iterate z <- z^2 + c from z = (zre, zim) x 2^E for `passes` passes and report the first pass whose
+// entering |z|^2 is over the threshold (-1: none) and whether every later pass also reads as escaped.
+int lockstep_at_growth(float cre, float cim, int ce, float rm, int re_, float zre, float zim, int passes, int *stays) {
+    const fs::atfast::Plan<float> p = fs::atfast::plan<float>(fs::HdrC<float>{cre, cim, ce}, fs::Hdr<float>{rm, re_}, true);
+    int first = -1;
+    *stays = 1;
+    for (int i = 0; i < passes; i++) {
+        const bool esc = fs::atfast::escaped(fs::atfast::norm(zre, zim), p.thr);
+        if (esc && first < 0) first = i;
+        if (!esc && first >= 0) *stays = 0;
+        fs::atfast::advance(zre, zim, p.s, cre, cim);
+    }
+    return first;
+}
+
 // stats[6]: pixels that take the AT shortcut, pixels the fast form refused, passes compared, mismatches, pixels escaped,
 // pixels whose plan allows the lean (last-pass-only) chunk test
 uint64_t lockstep_at(const void *at, int use_at, int is_valid, int w, int h, const void *dx, const void *dy,

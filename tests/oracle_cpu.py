@@ -173,3 +173,29 @@ def lockstep_at(w, h, coords, la, n_iter, max_passes=20000, col_step=1, row_step
     fn(l.at, l.use_at, l.is_valid, w, h, _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]),
        _buf(coords["center_y"]), n_iter, max_passes, col_step, row_step, stats)
     return dict(zip(("pixels", "refused", "passes", "mismatches", "escaped", "mono"), (int(v) for v in stats)))
+
+
+def at_plan(cre, cim, ce, rm, re_):
+    """(ok, mono, E, thr) of the plan the kernel's AT shortcut makes for c = (cre, cim) x 2^ce, R = rm x 2^re_."""
+    global _lock
+    if _lock is None:
+        _lock = C.CDLL(LOCKSTEP_LIB)
+    out = (C.c_int * 3)()
+    thr = C.c_float()
+    _lock.lockstep_at_plan.restype = None
+    _lock.lockstep_at_plan.argtypes = [C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    _lock.lockstep_at_plan(cre, cim, ce, rm, re_, out, C.byref(thr))
+    return bool(out[0]), bool(out[1]), int(out[2]), float(thr.value)
+
+
+def at_growth(cre, cim, ce, rm, re_, zre, zim, passes):
+    """(first escaped pass or -1, every later pass still reads escaped) for the mantissa recurrence started at z."""
+    global _lock
+    if _lock is None:
+        _lock = C.CDLL(LOCKSTEP_LIB)
+    stays = C.c_int()
+    _lock.lockstep_at_growth.restype = C.c_int
+    _lock.lockstep_at_growth.argtypes = [C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int,
+                                         C.POINTER(C.c_int)]
+    first = _lock.lockstep_at_growth(cre, cim, ce, rm, re_, zre, zim, passes, C.byref(stays))
+    return int(first), bool(stays.value)

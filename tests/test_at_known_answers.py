@@ -116,3 +116,51 @@ def test_perform_at_known_answers_on_the_oracle(case):
     got, _ = oracle_cpu.render_lav2(A.GpuHDRx32PerturbedLAv2LAO, w, h, zero_coords(Numeric.HDR32), _FlatOrbit(Numeric.HDR32),
                                     _AtOnlyTable(at_blob(Numeric.HDR32, sqr, thr, step, ref_c)), n_iter)
     assert (got[:h, :w] == want).all(), got[:h, :w]
+
+
+# ---- the plan of the kernel's AT shortcut (fs_at_fast.cuh), CPU suite ------------------------------------------------
+def test_at_plan_guards(built):
+    """ok / mono decisions of atfast::plan: the mantissa recurrence needs a reduced c with exponent <= 0; the lean
+    chunk test (escape looked at on a chunk's last pass only) additionally needs R > 4 and |c| <= R/4."""
+    # c = 1.5 x 2^-1 = 0.75, R = 256 = 1.0 x 2^8: both forms apply; the threshold is R / 2^(2E)
+    ok, mono, E, thr = oracle_cpu.at_plan(1.5, 0.0, -1, 1.0, 8)
+    assert (ok, mono, E, thr) == (True, True, -1, 1024.0)
+    # |c| >= 2 (exponent 1): the reference's exponent doubles every pass, only the general loop reproduces that
+    assert oracle_cpu.at_plan(1.0, 0.0, 1, 1.0, 8)[:2] == (False, False)
+    # R = 4 is not "> 4" (ATInfo::Usable demands more, ATInfo.h:91-105): recurrence yes, lean test no
+    assert oracle_cpu.at_plan(1.5, 0.0, -1, 1.0, 2)[:2] == (True, False)
+    # R = 5: |c| = 1.5 > R/4 = 1.25 -> running maximum; |c| = 1.0 <= 1.25 -> lean
+    assert oracle_cpu.at_plan(1.5, 0.0, 0, 1.25, 2)[:2] == (True, False)
+    assert oracle_cpu.at_plan(1.0, 0.0, 0, 1.25, 2)[:2] == (True, True)
+    # an unreduced radius mantissa, a radius beyond the range the comparison is prepared for, NaN: general loop / no lean
+    assert oracle_cpu.at_plan(1.0, 0.0, 0, 2.5, 8)[0] is False
+    assert oracle_cpu.at_plan(1.0, 0.0, 0, 1.0, 50)[1] is False
+    assert oracle_cpu.at_plan(float("nan"), 0.0, 0, 1.0, 8)[1] is False
+    # a tiny c (exponent -100) with R = 256: |R.e - 2E| = 208 > 126 cannot be pre-scaled in binary32 -> general loop
+    assert oracle_cpu.at_plan(1.0, 1.0, -100, 1.0, 8)[0] is False
+
+
+def test_at_escape_is_monotone_where_the_plan_says_so(built):
+    """Random starts around the escape radius, random c with |c| <= R/4: once a pass reads as escaped every later pass
+    does (growing, inf or NaN), which is what lets the kernel test only the last pass of a chunk."""
+    rng = np.random.default_rng(5)
+    checked = 0
+    for _ in range(4000):
+        r_e = int(rng.integers(3, 33))                       # R = rm * 2^r_e in (4, 2^33)
+        rm = float(np.float32(rng.uniform(1.0, 2.0)))
+        R = rm * 2.0 ** r_e
+        ce = int(rng.integers(-12, 1))
+        cre, cim = (float(np.float32(v)) for v in rng.uniform(-2.0, 2.0, 2))
+        if max(abs(cre), abs(cim)) < 1.0:                    # keep c reduced: larger mantissa in [1, 2)
+            cre = math.copysign(1.0 + abs(cre) % 1.0, cre or 1.0)
+        ok, mono, E, thr = oracle_cpu.at_plan(cre, cim, ce, rm, r_e)
+        if not (ok and mono):
+            continue
+        # start near the radius: |z| = sqrt(R) * (0.5 .. 2), mantissa units of 2^E
+        mag = math.sqrt(R) * float(rng.uniform(0.5, 2.0)) / 2.0 ** E
+        ang = float(rng.uniform(0, 2 * math.pi))
+        first, stays = oracle_cpu.at_growth(cre, cim, ce, rm, r_e, float(np.float32(mag * math.cos(ang))),
+                                            float(np.float32(mag * math.sin(ang))), 48)
+        assert stays, (cre, cim, ce, rm, r_e, mag, ang, first)
+        checked += first >= 0
+    assert checked > 1000
