@@ -312,13 +312,21 @@ def main():
     else:
         from fractalshark_b200.sharding import SharedFrame
         name = "fsb200_frame_%s" % os.environ.get("MASTER_PORT", "0")
+        shared_ok = [True]
         if rank == 0:
-            shm = SharedFrame(name, (hp, wp), np.uint32, create=True)
-        dist.barrier()
-        if rank != 0:
-            shm = SharedFrame(name, (hp, wp), np.uint32)
-        frame = shm.array
-        frame_kind = "shared memory frame every rank writes its bands into"
+            try:
+                shm = SharedFrame(name, (hp, wp), np.uint32, create=True)
+            except OSError:
+                shared_ok = [False]
+        dist.broadcast_object_list(shared_ok, src=0)
+        if shared_ok[0]:
+            if rank != 0:
+                shm = SharedFrame(name, (hp, wp), np.uint32)
+            frame = shm.array
+            frame_kind = "shared memory frame every rank writes its bands into"
+        else:  # no POSIX shared memory on this host: every rank keeps its bands in a pinned frame of its own
+            frame = torch.zeros((hp, wp), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+            frame_kind = "per-rank pinned frames (no shared memory on this host)"
         dist.barrier()
     # result sink: the kernel stores finished pixels into the host frame while it runs (fs_set_result_sink page-locks
     # and maps the frame if it is not yet), RenderCurrent then only fetches the 24-byte reduction.  FS_BENCH_SINK=0
@@ -329,7 +337,7 @@ def main():
         assert rc == 0, GPURenderer.ConvertErrorToString(rc)
         frame_kind += "; streamed by the render kernel (result sink)"
     else:
-        if world > 1:
+        if shm is not None:
             reg = int(torch.cuda.cudart().cudaHostRegister(frame.ctypes.data, hp * wp * 4, 0))
             assert reg == 0
         frame_kind += "; copied after the render"
@@ -359,13 +367,15 @@ def main():
     e2e_s = (time.time() - t0) / args.steps
     assert e2e_sum == local_sum
     # untimed: one more step into a zeroed host frame -- what arrives there is the whole picture of THIS step
-    if rank == 0:
+    if rank == 0 or shm is None:
         frame[:] = 0
     barrier()
     gen += 1
     step_e2e(gen)
     barrier()
-    if rank == 0:
+    if shm is None and world > 1:
+        assert int(frame[:HEIGHT, :WIDTH].astype(np.int64).sum()) == local_sum
+    elif rank == 0:
         assert int(frame[:HEIGHT, :WIDTH].astype(np.int64).sum()) == total_sum
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -374,12 +384,13 @@ def main():
         dist.barrier()
     if use_sink:
         assert r.SetResultSink(None) == 0
-    elif world > 1:
+    elif shm is not None:
         torch.cuda.cudart().cudaHostUnregister(frame.ctypes.data)
     if world > 1:
         del frame
         dist.barrier()
-        shm.close()
+        if shm is not None:
+            shm.close()
     # whole-job host<->device bytes per step: every rank uploads its own copy of the tables, the frame leaves once
     h2d, d2h = h2d * world, hp * wp * 4 + 24 * world
     e2e_value = total_sum / e2e_s
