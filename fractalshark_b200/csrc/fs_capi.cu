@@ -98,6 +98,10 @@ struct fs_renderer {
     size_t n_cu = 0, n_color_cu = 0;
     uint32_t shard_count = 1, shard_index = 0;
     unsigned int *tile_counter = nullptr;
+    int *yield_quota = nullptr;          // device word next to the counter (TileQueue::yield_quota)
+    int *yield_src = nullptr;            // page-locked constant the display stream copies into it
+    bool yield_requested = false;        // a progressive RenderCurrent already freed SM slots during the current render
+    cudaEvent_t ev_alloc = nullptr;      // orders display-stream work after (re)allocations made on the compute stream
     unsigned long long *step_counter = nullptr;
     bool count_steps = false;
     // result sink (fs_set_result_sink): a page-locked host frame the LAv2 kernels store finished pixels into while they
@@ -420,9 +424,23 @@ template <class K> int lav2_grid(fs_renderer *r, K kernel) {
     return per_sm * r->num_sms;
 }
 
+// CTAs a progressive RenderCurrent asks to leave a running persistent grid (of num_sms x 2..8 CTAs): enough slots for
+// the post kernel to stream the frame in well under a millisecond, ~1 % of the render's throughput
+constexpr int kYieldCtas = 8;
+
+TileQueue render_queue(fs_renderer *r) {
+    TileQueue q;
+    q.counter = r->tile_counter;
+    q.yield_quota = r->yield_quota;
+    q.grab = 1;
+    return q;
+}
+
 void begin_render(fs_renderer *r, bool streams_to_sink = false) {
     r->sink_filled = streams_to_sink && r->sink_dev != nullptr; // any other render makes the host copy stale
-    cudaMemsetAsync(r->tile_counter, 0, sizeof(unsigned int), r->compute);
+    // tile counter and yield quota are adjacent words: one memset
+    cudaMemsetAsync(r->tile_counter, 0, 2 * sizeof(unsigned int), r->compute);
+    r->yield_requested = false;
     cudaEventRecord(r->ev_start, r->compute);
 }
 uint32_t end_render(fs_renderer *r) {
@@ -467,7 +485,7 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     A.centerY = load_pod<Real>(cy);
     A.n_iterations = (IterT)n_iter;
     A.sink = static_cast<IterT *>(r->sink_dev);
-    A.tile_counter = r->tile_counter;
+    A.queue = render_queue(r);
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     const bool count = r->count_steps;
     // two-launch form (AT, then everything else) for the float+exponent binary32 type when the table has an AT block
@@ -566,7 +584,7 @@ uint32_t launch_bla(fs_renderer *r, const fs_blas *blas, const void *dx, const v
     A.centerX = load_pod<Real>(cx);
     A.centerY = load_pod<Real>(cy);
     A.n_iterations = (IterT)n_iter;
-    A.tile_counter = r->tile_counter;
+    A.queue = render_queue(r);
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     begin_render(r);
     if (r->count_steps) { auto k = bla_kernel<Num, IterT, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
@@ -594,7 +612,7 @@ uint32_t launch_scaled(fs_renderer *r, const void *dx, const void *dy, const voi
     A.centerX = load_pod<Real>(cx);
     A.centerY = load_pod<Real>(cy);
     A.n_iterations = (IterT)n_iter;
-    A.tile_counter = r->tile_counter;
+    A.queue = render_queue(r);
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     begin_render(r);
     if (r->count_steps) { auto k = scaled_kernel<Num, IterT, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
@@ -622,7 +640,7 @@ uint32_t launch_direct(fs_renderer *r, const void *cx, const void *cy, const voi
     A.shard_index = (int)r->shard_index;
     A.cx = load_pod<M>(cx); A.cy = load_pod<M>(cy); A.dx = load_pod<M>(dx); A.dy = load_pod<M>(dy);
     A.n_iterations = (IterT)n_iter;
-    A.tile_counter = r->tile_counter;
+    A.queue = render_queue(r);
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     begin_render(r);
     switch (prec) {
@@ -647,7 +665,7 @@ uint32_t launch_direct_ext(fs_renderer *r, const typename Pixel::Coord &cx, cons
     A.shard_index = (int)r->shard_index;
     A.cx = cx; A.cy = cy; A.dx = dx; A.dy = dy;
     A.n_iterations = (IterT)n_iter;
-    A.tile_counter = r->tile_counter;
+    A.queue = render_queue(r);
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     begin_render(r);
     auto k = direct_ext_kernel<Pixel, IterT>;
@@ -748,6 +766,7 @@ void fs_destroy(fs_renderer *r) {
     if (!r) return;
     DeviceGuard g(r->device);
     if (r->compute) {
+        if (r->display) cudaStreamSynchronize(r->display);
         reset_perturb(r);
         reset_buffers(r);
         if (r->pal_dev) cudaFreeAsync(r->pal_dev, r->compute);
@@ -758,6 +777,8 @@ void fs_destroy(fs_renderer *r) {
         if (r->display) cudaStreamDestroy(r->display);
         if (r->ev_start) cudaEventDestroy(r->ev_start);
         if (r->ev_stop) cudaEventDestroy(r->ev_stop);
+        if (r->ev_alloc) cudaEventDestroy(r->ev_alloc);
+        if (r->yield_src) cudaFreeHost(r->yield_src);
     }
     delete r;
 }
@@ -780,14 +801,23 @@ uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, u
         cudaEventCreate(&r->ev_start);
         cudaEventCreate(&r->ev_stop);
         cudaDeviceGetAttribute(&r->num_sms, cudaDevAttrMultiProcessorCount, r->device);
-        err = cudaMallocAsync(&r->tile_counter, sizeof(unsigned int), r->compute);
+        cudaEventCreateWithFlags(&r->ev_alloc, cudaEventDisableTiming);
+        err = cudaMallocAsync(&r->tile_counter, 2 * sizeof(unsigned int), r->compute);
         if (err != cudaSuccess) return err;
+        r->yield_quota = reinterpret_cast<int *>(r->tile_counter + 1);
+        cudaMemsetAsync(r->tile_counter, 0, 2 * sizeof(unsigned int), r->compute);
+        err = cudaMallocHost(&r->yield_src, sizeof(int));
+        if (err != cudaSuccess) return err;
+        *r->yield_src = kYieldCtas;
         err = cudaMallocAsync(&r->step_counter, 4 * sizeof(unsigned long long), r->compute);
         if (err != cudaSuccess) return err;
         cudaMemsetAsync(r->step_counter, 0, 4 * sizeof(unsigned long long), r->compute);
     }
+    bool allocated = false;
     if (r->cached_pal_host != pal || r->cached_pal_gen != pal_gen) {
-        if (r->pal_dev) cudaFreeAsync(r->pal_dev, r->compute);
+        // a progressive RenderCurrent may still be reading the old palette on the display stream
+        if (r->pal_dev) { cudaStreamSynchronize(r->display); cudaFreeAsync(r->pal_dev, r->compute); }
+        allocated = true;
         r->pal_dev = nullptr;
         r->pal_iters = pal_iters;
         r->cached_pal_host = pal;
@@ -799,8 +829,10 @@ uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, u
         }
         r->cached_pal_gen = pal_gen;
     }
-    if (r->width == w && r->height == h && r->aa == antialiasing && r->iter_bytes == iter_bytes && expected_reuse)
+    if (r->width == w && r->height == h && r->aa == antialiasing && r->iter_bytes == iter_bytes && expected_reuse) {
+        if (allocated) { cudaEventRecord(r->ev_alloc, r->compute); cudaStreamWaitEvent(r->display, r->ev_alloc, 0); }
         return 0;
+    }
     if (antialiasing > 4 || antialiasing < 1) return FS_ERROR_3_BAD_ANTIALIASING;
     if (w % antialiasing != 0) return FS_ERROR_4_WIDTH_NOT_MULTIPLE_OF_AA;
     if (h % antialiasing != 0) return FS_ERROR_5_HEIGHT_NOT_MULTIPLE_OF_AA;
@@ -818,7 +850,9 @@ uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, u
     const uint32_t hcb = r->color_h / NB_THREADS_H + (r->color_h % NB_THREADS_H != 0);
     r->n_color_cu = (size_t)wcb * NB_THREADS_W * hcb * NB_THREADS_H;
 
-    // geometry change drops cached orbit/LA uploads (ResetPerturb::Yes, GPU_Render.cu:358)
+    // geometry change drops cached orbit/LA uploads (ResetPerturb::Yes, GPU_Render.cu:358).  The buffers are freed and
+    // allocated in compute-stream order; display-stream work (progressive RenderCurrent) is fenced on both sides.
+    cudaStreamSynchronize(r->display);
     reset_perturb(r);
     reset_buffers(r);
     err = cudaMallocAsync(&r->iter_buf, r->n_cu * iter_bytes, r->compute);
@@ -828,6 +862,8 @@ uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, u
     err = cudaMallocAsync(&r->color_buf, r->n_color_cu * sizeof(Color16), r->compute);
     if (err != cudaSuccess) return err;
     fs_clear_memory(r);
+    cudaEventRecord(r->ev_alloc, r->compute);
+    cudaStreamWaitEvent(r->display, r->ev_alloc, 0);
     return 0;
 }
 
@@ -976,11 +1012,23 @@ uint32_t fs_render_perturb_bla_scaled(fs_renderer *r, uint32_t algorithm, int32_
                : launch_scaled<NumHdr<float>, uint32_t>(r, dx, dy, center_x, center_y, n_iterations);
 }
 
+// A progressive frame asked for while a render kernel holds every SM slot: the display stream raises the yield quota
+// (a 4-byte copy, no SM needed), kYieldCtas CTAs of the persistent grid retire at their next tile boundary, and the
+// high-priority post kernel launched right after takes their slots.  Asked once per render: the slots stay free.
+static void request_yield_if_rendering(fs_renderer *r) {
+    if (r->yield_requested) return;
+    if (cudaStreamQuery(r->compute) != cudaErrorNotReady) return;
+    (void)cudaGetLastError();
+    r->yield_requested = true;
+    cudaMemcpyAsync(r->yield_quota, r->yield_src, sizeof(int), cudaMemcpyHostToDevice, r->display);
+}
+
 uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buffer, fs_color16 *color_buffer,
                            fs_reduction *reduction_results, int32_t progressive) {
     if (!r || !memory_initialized(r)) return 0; // GPU_Render.cu:563-565
     DeviceGuard g(r->device);
     cudaStream_t stream = progressive ? r->display : r->compute;
+    if (progressive) request_yield_if_rendering(r);
     uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream) : run_post<uint32_t>(r, n_iterations, stream);
     if (rc) return rc;
     cudaError_t err = cudaSuccess;
@@ -1008,6 +1056,7 @@ uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *it
     if (r->shard_count <= 1) return fs_render_current(r, n_iterations, iter_buffer, nullptr, reduction_results, progressive);
     DeviceGuard g(r->device);
     cudaStream_t stream = progressive ? r->display : r->compute;
+    if (progressive) request_yield_if_rendering(r);
     uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream) : run_post<uint32_t>(r, n_iterations, stream);
     if (rc) return rc;
     cudaError_t err = cudaSuccess;

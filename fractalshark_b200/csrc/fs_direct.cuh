@@ -28,7 +28,7 @@ template <class M, class IterT> struct DirectArgs {
     int shard_count, shard_index; // 4-row tile bands are dealt round-robin to shards (multi-GPU)
     M cx, cy, dx, dy;
     IterT n_iterations;
-    unsigned int *tile_counter;
+    TileQueue queue;
     unsigned long long *step_counter;
 };
 
@@ -41,16 +41,19 @@ __global__ void __launch_bounds__(256) direct_kernel(const DirectArgs<M, IterT> 
     const IterT n_iter = A.n_iterations - (IterT)(P - 1);
     unsigned long long steps = 0;
 
+    TileCursor cursor;
+    tile_queue_begin(cursor);
     for (;;) {
-        unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(A.tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
-        int X, Y;
-        tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Y);
+        unsigned int tile;
+        if (!next_tile(A.queue, cursor, n_tiles, tile)) break;
+        // tiles (and with them the shard's 4-row bands) are laid out over the OUTPUT rows; the kernel's own Y runs the
+        // other way (row flip, LowPrecisionKernels.cuh:309,699)
+        int X, Yout;
+        tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Yout);
         X += lane & 7;
-        Y += lane >> 3;
-        if (X >= A.width || Y >= A.height) continue;
+        Yout += lane >> 3;
+        if (X >= A.width || Yout >= A.height) continue;
+        const int Y = A.height - 1 - Yout;
 
         const M x0 = fma_(DirectOps<M>::from_int(X), A.dx, A.cx);
         const M y0 = fma_(DirectOps<M>::from_int(Y), A.dy, A.cy);
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) direct_kernel(const DirectArgs<M, IterT> 
             iter += P;
         }
         steps += iter;
-        A.out[(size_t)(A.height - Y - 1) * A.pitch + X] = iter;
+        A.out[(size_t)Yout * A.pitch + X] = iter;
     }
     if (A.step_counter) {
         for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);

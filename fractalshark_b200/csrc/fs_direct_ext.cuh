@@ -21,7 +21,7 @@ template <class C, class IterT> struct DirectExtArgs {
     int shard_count, shard_index;
     C cx, cy, dx, dy;
     IterT n_iterations;
-    unsigned int *tile_counter;
+    TileQueue queue;
     unsigned long long *step_counter;
 };
 
@@ -159,19 +159,20 @@ __global__ void __launch_bounds__(256) direct_ext_kernel(const DirectExtArgs<typ
     const int tiles_y = (((A.height + 3) >> 2) - A.shard_index + A.shard_count - 1) / A.shard_count;
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     unsigned long long steps = 0;
+    TileCursor cursor;
+    tile_queue_begin(cursor);
     for (;;) {
-        unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(A.tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
-        int X, Y;
-        tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Y);
+        unsigned int tile;
+        if (!next_tile(A.queue, cursor, n_tiles, tile)) break;
+        // bands are dealt over the output rows; the kernels' own Y is flipped (LowPrecisionKernels.cuh:309)
+        int X, Yout;
+        tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Yout);
         X += lane & 7;
-        Y += lane >> 3;
-        if (X < A.width && Y < A.height) {
-            const IterT iter = Pixel::template run<IterT>(A, X, Y);
+        Yout += lane >> 3;
+        if (X < A.width && Yout < A.height) {
+            const IterT iter = Pixel::template run<IterT>(A, X, A.height - 1 - Yout);
             steps += iter;
-            A.out[(size_t)(A.height - Y - 1) * A.pitch + X] = iter;
+            A.out[(size_t)Yout * A.pitch + X] = iter;
         }
         __syncwarp();
     }

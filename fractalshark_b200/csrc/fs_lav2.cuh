@@ -79,7 +79,7 @@ template <class Num, class IterT> struct Lav2Args {
     int shard_count, shard_index; // 4-row tile bands are dealt round-robin to shards (multi-GPU)
     typename Num::Real dx, dy, centerX, centerY;
     IterT n_iterations;
-    unsigned int *tile_counter;
+    TileQueue queue;
     unsigned long long *step_counter; // optional: executed perturbation/LA/AT steps (bench roofline)
     float4 *at_state;                 // HDRx32 two-launch form: per-pixel AT result {dz.re, dz.im, dz.e}; iter sits in `out`
     IterT *sink;                      // optional mapped host copy of `out` (fs_set_result_sink): finished pixels stream out over PCIe
@@ -205,8 +205,9 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                     constexpr bool kLean = decltype(lean_tag)::value;
                     if constexpr (sizeof(M) == 4 && FS_AT_PACKED) {
                         // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
-                        const f32x2 s2 = f2_make(s, s), c2 = f2_make(c.re, c.im);
-                        while (i + kAtChunk <= at_max) {
+                        // imaginary part as fma(RN(re*im), 2s, c.im): fs_at_fast.cuh `advance` has the argument
+                        const f32x2 s2 = f2_make(s, s + s), c2 = f2_make(c.re, c.im);
+                        while (at_max - i >= (IterT)kAtChunk) { // i <= at_max always; `i + chunk` could wrap for u32 counts near 2^32
                             const float re0 = re, im0 = im;
                             float worst = 0.0f;
                             f32x2 z2 = f2_make(re, im);
@@ -216,8 +217,7 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                                 f2_split(f2_mul(z2, z2), rr, ii);
                                 if (!kLean) worst = fmaxf(worst, rr + ii);
                                 else if (u == kAtChunk - 1) worst = rr + ii;
-                                const float t = fma_(re, im, re * im);
-                                z2 = f2_fma(f2_make(rr - ii, t), s2, c2);
+                                z2 = f2_fma(f2_make(rr - ii, re * im), s2, c2);
                                 f2_split(z2, re, im);
                             }
                             if (!(worst <= thr)) {
@@ -228,7 +228,8 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                             i += kAtChunk;
                         }
                     } else {
-                        while (i + kAtChunk <= at_max) {
+                        const M s_im = s + s;
+                        while (at_max - i >= (IterT)kAtChunk) {
                             const M re0 = re, im0 = im;
                             M worst = M(0);
 #pragma unroll
@@ -236,9 +237,9 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                                 const M rr = re * re, ii = im * im;
                                 if (!kLean) worst = fmax(worst, rr + ii);
                                 else if (u == kAtChunk - 1) worst = rr + ii;
-                                const M t = fma_(re, im, re * im);
+                                const M p = re * im;
                                 re = fma_(rr - ii, s, c.re);
-                                im = fma_(t, s, c.im);
+                                im = fma_(p, s_im, c.im);
                             }
                             if (!(worst <= thr)) {
                                 re = re0;
@@ -355,11 +356,11 @@ __global__ void FS_LAV2_BOUNDS lav2_kernel(const Lav2Args<Num, IterT> A) {
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     unsigned long long steps = 0, steps_at = 0, steps_la = 0;
 
+    TileCursor cursor;
+    tile_queue_begin(cursor);
     for (;;) {
-        unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(A.tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
+        unsigned int tile;
+        if (!next_tile(A.queue, cursor, n_tiles, tile)) break;
 
         int X, Y;
         tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Y);

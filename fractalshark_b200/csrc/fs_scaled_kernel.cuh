@@ -39,7 +39,7 @@ template <class Num, class IterT> struct ScaledArgs {
     int shard_count, shard_index;
     typename Num::Real dx, dy, centerX, centerY;
     IterT n_iterations;
-    unsigned int *tile_counter;
+    TileQueue queue;
     unsigned long long *step_counter;
 };
 
@@ -293,11 +293,11 @@ __global__ void __launch_bounds__(256) scaled_kernel(const ScaledArgs<Num, IterT
     const int tiles_y = (((A.height + 3) >> 2) - A.shard_index + A.shard_count - 1) / A.shard_count;
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     unsigned long long steps = 0;
+    TileCursor cursor;
+    tile_queue_begin(cursor);
     for (;;) {
-        unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(A.tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
+        unsigned int tile;
+        if (!next_tile(A.queue, cursor, n_tiles, tile)) break;
         int X, Y;
         tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Y);
         X += lane & 7;

@@ -137,6 +137,56 @@ FS_HD void tile_origin(unsigned int tile, int tiles_x, int tiles_y, int shard_co
     Y0 = (centre_out(ky, tiles_y) * shard_count + shard_index) * 4;
 }
 
+#ifdef __CUDACC__
+// ---- the work queue every render kernel pulls its 8x4-pixel tiles from -----------------------------------------
+// counter      tickets handed out so far (device-local, or a peer-mapped word all GPUs of a box pull from)
+// yield_quota  > 0 while a progressive RenderCurrent waits for an SM slot (fs_render_current, progressive = 1, called
+//              during a running render): that many CTAs leave the persistent grid at their next tile boundary, so the
+//              high-priority post kernel is scheduled at once.  The reference's one-CTA-per-screen-block grid gives the
+//              display stream the same chance whenever a block retires (RenderThreadPool.cpp:915-959, 1923-1948).
+// grab         tickets taken per atomic (1 locally; a few over NVLink so the round trip is paid once per group)
+struct TileQueue {
+    unsigned int *counter;
+    int *yield_quota;
+    unsigned int grab;
+};
+struct TileCursor {
+    unsigned int cur, end;
+};
+// One flag per CTA: set by the warp that took a retirement token, seen by the CTA's other warps at their next fetch.
+static __shared__ int fs_cta_retire;
+FS_D void tile_queue_begin(TileCursor &tc) {
+    tc.cur = tc.end = 0;
+    if (threadIdx.x == 0) fs_cta_retire = 0;
+    __syncthreads();
+}
+// Warp-uniform: every lane gets the same ticket.  Returns false when the queue is exhausted or the CTA retires.
+FS_D bool next_tile(const TileQueue &q, TileCursor &tc, unsigned int n_tiles, unsigned int &tile) {
+    if (tc.cur == tc.end) {
+        unsigned int base = 0xffffffffu;
+        if ((threadIdx.x & 31) == 0) {
+            bool retire = *(volatile int *)&fs_cta_retire != 0;
+            if (!retire && q.yield_quota && *(volatile int *)q.yield_quota > 0) {
+                if (atomicSub(q.yield_quota, 1) > 0) {
+                    *(volatile int *)&fs_cta_retire = 1;
+                    retire = true;
+                } else {
+                    atomicAdd(q.yield_quota, 1);
+                }
+            }
+            if (!retire) base = atomicAdd(q.counter, q.grab);
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        tc.cur = base;
+        tc.end = base >= n_tiles ? base : base + q.grab; // an exhausted queue is asked again (and fails again) next time
+    }
+    tile = tc.cur;
+    if (tile >= n_tiles) return false;
+    tc.cur++;
+    return true;
+}
+#endif
+
 // Packed binary32 pairs (sm_100 FMUL2 / FADD2 / FFMA2): two independent IEEE operations per issued instruction,
 // each lane rounded exactly like its scalar counterpart.  Device only.
 #ifdef __CUDACC__

@@ -76,6 +76,8 @@ class GPURenderer:
         d1 = perturb1.descriptor()
         d2 = perturb2.descriptor() if perturb2 is not None else None
         dl = la.descriptor() if la is not None else None
+        # page-locked sources are read asynchronously (include/fs_gpu.h): keep them alive until the next upload
+        self._keep = [perturb1, perturb2, la, d1, d2, dl]
         return int(self._lib.fs_initialize_perturb(
             self._h, self._iter_bytes, int(perturb1.numeric), int(pextras), generation1, C.byref(d1),
             int(perturb2.numeric) if perturb2 is not None else 0, generation2,

@@ -131,6 +131,42 @@ template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, in
 
 extern "C" {
 
+// Identity behind the 6-rounding AT pass (fs_at_fast.cuh `advance`): fma(a, b, RN(a*b)) == 2*RN(a*b) for binary32 and
+// binary64, checked on `count` pseudo-random operand pairs whose exponents are drawn to cover normal, denormal-product,
+// overflow and binade-edge cases (operands with few mantissa bits make exact ties frequent).  Returns the mismatches.
+uint64_t lockstep_twice_product_identity(uint64_t count, uint64_t seed) {
+    uint64_t bad = 0, x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (uint64_t i = 0; i < count; i++) {
+        const uint64_t r = next(), q = next();
+        // binary32: exponent fields chosen so products land anywhere from deep underflow to overflow
+        uint32_t ma = (uint32_t)(r & 0x7fffffu), mb = (uint32_t)((r >> 23) & 0x7fffffu);
+        if (q & 1) ma &= 0x7ff000u;       // short mantissas: exact halfway cases in the denormal range
+        if (q & 2) mb &= 0x7e0000u;
+        const uint32_t ea = (uint32_t)((q >> 8) % 255u), eb = (q & 4) ? (uint32_t)((254u + 22u - ea + (q >> 20) % 9u) % 255u)
+                                                                      : (uint32_t)((q >> 16) % 255u);
+        float a, b;
+        const uint32_t ba = ((uint32_t)(r >> 63) << 31) | (ea << 23) | ma, bb = ((uint32_t)((r >> 62) & 1) << 31) | (eb << 23) | mb;
+        memcpy(&a, &ba, 4); memcpy(&b, &bb, 4);
+        const float p = a * b;
+        const float t = __builtin_fmaf(a, b, p), u = p + p;
+        if (bits(t) != bits(u) && !(t != t && u != u)) bad++;
+        // binary64
+        const uint64_t da = (r & 0x800fffffffffffffull) | ((uint64_t)((q >> 24) % 2047u) << 52);
+        const uint64_t db = (next() & 0x800fffffffffffffull & ((q & 8) ? 0xffffffff00000000ull : ~0ull)) |
+                            ((uint64_t)((q & 16) ? (2046u + 51u - (q >> 24) % 2047u + (q >> 40) % 9u) % 2047u : (q >> 36) % 2047u) << 52);
+        double A, B;
+        memcpy(&A, &da, 8); memcpy(&B, &db, 8);
+        const double P = A * B;
+        const double T = __builtin_fma(A, B, P), U = P + P;
+        uint64_t tb, ub;
+        memcpy(&tb, &T, 8); memcpy(&ub, &U, 8);
+        if (tb != ub && !(T != T && U != U)) bad++;
+    }
+    return bad;
+}
+
+
 // The plan lav2_at makes for one pixel: c = (re, im) x 2^ce (reduced), R = rm x 2^re_.  out[0] = ok (mantissa recurrence
 // applies), out[1] = mono (lean chunk test applies), out[2] = E; thr_out = the pre-scaled escape threshold.
 void lockstep_at_plan(float cre, float cim, int ce, float rm, int re_, int *out, float *thr_out) {

@@ -82,14 +82,36 @@ SMALL_CASES_6 = [
     ("v14_hdr32_rclav2", 14, 64, 36, A.GpuHDRx32PerturbedRCLAv2, None, 4),
     ("v14_hdr32_bla", 14, 64, 36, A.GpuHDRx32PerturbedBLA, None, 4),
 ]
+# seventh fixture file (tests/golden/ref_gpu_small7.npz): direct kernels at iteration_precision 4 / 8 / 16 -- P steps
+# per bailout test and `n_iterations -= P-1` (GPU_Render.cu:633-668, LowPrecisionKernels.cuh:317,707).  Iteration
+# limits are chosen NOT to be multiples of P so the shortened limit and the chunked overshoot both show.
+SMALL_CASES_7 = [
+    ("v0_gpu1x32_p4", 0, 96, 54, A.Gpu1x32, 1023, 4),
+    ("v0_gpu1x32_p8", 0, 96, 54, A.Gpu1x32, 1021, 4),
+    ("v0_gpu1x32_p16_u64", 0, 50, 37, A.Gpu1x32, 1000, 8),
+    ("v0_gpu1x64_p4_u64", 0, 50, 37, A.Gpu1x64, 301, 8),
+    ("v0_gpu1x64_p8", 0, 96, 54, A.Gpu1x64, 1023, 4),
+    ("v0_gpu1x64_p16", 0, 96, 54, A.Gpu1x64, 1030, 4),
+    ("v0_gpu2x32_p4", 0, 96, 54, A.Gpu2x32, 1023, 4),
+    ("v100_gpu2x32_p8_u64", 100, 50, 37, A.Gpu2x32, 20001, 8),
+    ("v0_gpu2x32_p16", 0, 96, 54, A.Gpu2x32, 1030, 4),
+    ("v0_gpuhdrx32_p4", 0, 96, 54, A.GpuHDRx32, 511, 4),
+    ("v100_gpuhdrx32_p8_u64", 100, 50, 37, A.GpuHDRx32, 5003, 8),
+    ("v0_gpuhdrx32_p16", 0, 96, 54, A.GpuHDRx32, 520, 4),
+    ("v0_gpu1x32_p16_tiny", 0, 16, 8, A.Gpu1x32, 17, 4),       # limit barely above P: one chunk at most
+]
+# iteration_precision of a case (default 1)
+CASE_PRECISION = {c[0]: int(c[0].split("_p")[1].split("_")[0]) for c in SMALL_CASES_7}
 # Gpu4x32 / Gpu4x64: the four-limb products are split exactly here (one FMA) while the reference build leaves a
 # Dekker split to the compiler's contraction (fs_qd.cuh); frames agree to >= 99.9 % of pixels, not bit for bit.
 NOT_BIT_EXACT = {"v0_gpu4x32": 0.999, "v0_gpu4x64": 0.999}
-ALL_SMALL_CASES = SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3 + SMALL_CASES_4 + SMALL_CASES_5 + SMALL_CASES_6
+ALL_SMALL_CASES = (SMALL_CASES + SMALL_CASES_2 + SMALL_CASES_3 + SMALL_CASES_4 + SMALL_CASES_5 + SMALL_CASES_6 +
+                   SMALL_CASES_7)
 CASE_SETS = {"1": SMALL_CASES, "2": SMALL_CASES_2, "3": SMALL_CASES_3, "4": SMALL_CASES_4, "5": SMALL_CASES_5,
-             "6": SMALL_CASES_6}
+             "6": SMALL_CASES_6, "7": SMALL_CASES_7}
 GOLDEN_FILES = {"1": "ref_gpu_small.npz", "2": "ref_gpu_small2.npz", "3": "ref_gpu_small3.npz",
-                "4": "ref_gpu_small4.npz", "5": "ref_gpu_small5.npz", "6": "ref_gpu_small6.npz"}
+                "4": "ref_gpu_small4.npz", "5": "ref_gpu_small5.npz", "6": "ref_gpu_small6.npz",
+                "7": "ref_gpu_small7.npz"}
 
 
 def golden_file_of(name):
@@ -136,7 +158,7 @@ def inputs_crc(coords, orbit, table):
     return crc
 
 
-def oracle_render(alg, w, h, coords, orbit, table, n, ib, **kw):
+def oracle_render(alg, w, h, coords, orbit, table, n, ib, precision=1, **kw):
     """CPU oracle for a case, or None when the oracle has no restatement of that variant."""
     import oracle_cpu
     from fractalshark_b200 import traits
@@ -149,7 +171,7 @@ def oracle_render(alg, w, h, coords, orbit, table, n, ib, **kw):
             return oracle_cpu.render_bla(alg, w, h, coords, orbit, table, n, iter_bytes=ib, **kw)[0]
         if fam == "scaled":
             return oracle_cpu.render_scaled(alg, w, h, coords, orbit, table, n, iter_bytes=ib, **kw)[0]
-        return oracle_cpu.render_direct(alg, w, h, coords, n, 1, iter_bytes=ib, threads=kw["threads"])[0]
+        return oracle_cpu.render_direct(alg, w, h, coords, n, precision, iter_bytes=ib, threads=kw["threads"])[0]
     except NotImplementedError:
         return None
 
@@ -201,11 +223,14 @@ def make_inputs(view_id, w, h, alg, n_iter, iter_bytes):
     return view, coords, orbit, la, n_iter
 
 
-def render(renderer_cls, w, h, alg, coords, orbit, la, n_iter, iter_bytes, want_colors=False, aa=1):
+def render(renderer_cls, w, h, alg, coords, orbit, la, n_iter, iter_bytes, want_colors=False, aa=1, precision=1,
+           shard=None):
     from fractalshark_b200 import traits
     r = renderer_cls()
     rc = r.InitializeMemory(w, h, aa, iter_bytes=iter_bytes)
     assert rc == 0, rc
+    if shard is not None:
+        assert r.SetShard(*shard) == 0
     fam = traits(alg).family
     if orbit is not None and fam == "lav2":
         rc = r.InitializePerturb(1, orbit, 0, None, la)
@@ -218,7 +243,7 @@ def render(renderer_cls, w, h, alg, coords, orbit, la, n_iter, iter_bytes, want_
     elif fam == "scaled":
         rc = r.RenderPerturbBLAScaled(alg, orbit, la, coords, n_iter)
     else:
-        rc = r.Render(alg, coords, n_iter, 1)
+        rc = r.Render(alg, coords, n_iter, precision)
     assert rc == 0, rc
     rc, iters, colors, red = r.RenderCurrent(n_iter, want_colors=want_colors)
     assert rc == 0, rc

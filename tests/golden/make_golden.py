@@ -29,7 +29,8 @@ def main(out_path, which="1"):
     out = {}
     for name, view_id, w, h, alg, n_iter, ib in cases.CASE_SETS[which]:
         _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
-        iters, _, red = cases.render(ref_renderer.RefGPURenderer, w, h, alg, coords, orbit, la, n, ib)
+        iters, _, red = cases.render(ref_renderer.RefGPURenderer, w, h, alg, coords, orbit, la, n, ib,
+                                     precision=cases.CASE_PRECISION.get(name, 1))
         out[name] = iters[:h, :w].copy()
         out[name + "__crc"] = np.array([inputs_crc(coords, orbit, la)], dtype=np.uint64)
         print(name, iters[:h, :w].shape, red, flush=True)

@@ -199,3 +199,11 @@ def at_growth(cre, cim, ce, rm, re_, zre, zim, passes):
                                          C.POINTER(C.c_int)]
     first = _lock.lockstep_at_growth(cre, cim, ce, rm, re_, zre, zim, passes, C.byref(stays))
     return int(first), bool(stays.value)
+
+
+def twice_product_identity_mismatches(count, seed=1):
+    """fma(a, b, RN(a*b)) == 2*RN(a*b) on `count` random binary32 and binary64 pairs (lockstep_check.cpp)."""
+    L = C.CDLL(LOCKSTEP_LIB)
+    L.lockstep_twice_product_identity.restype = C.c_uint64
+    L.lockstep_twice_product_identity.argtypes = [C.c_uint64, C.c_uint64]
+    return int(L.lockstep_twice_product_identity(count, seed))

@@ -30,7 +30,7 @@ def test_oracle_matches_reference_gpu_golden(golden, case):
     name, view_id, w, h, alg, n_iter, ib = case
     _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
     assert int(golden[name + "__crc"][0]) == cases.inputs_crc(coords, orbit, la), "input generator drifted from the fixture"
-    got = cases.oracle_render(alg, w, h, coords, orbit, la, n, ib)
+    got = cases.oracle_render(alg, w, h, coords, orbit, la, n, ib, precision=cases.CASE_PRECISION.get(name, 1))
     if got is None:
         pytest.skip("no CPU restatement of this variant: pinned by the fixture against the CUDA path only (-m gpu)")
     want = golden[name]
@@ -177,6 +177,12 @@ def test_scaled_plain_float_chunks_match_float_exponent_steps_in_lockstep(built,
     assert st["mismatches"] == 0, st
     np.testing.assert_array_equal(got, want)
     assert st["fast_steps"] > 4 * st["slow_steps"], st
+
+
+def test_twice_the_rounded_product_identity_behind_the_six_rounding_at_pass(built):
+    """fma(a, b, RN(a*b)) == 2*RN(a*b): what lets the AT pass drop the reference's seventh rounding (fs_at_fast.cuh).
+    40 M random binary32 + binary64 pairs, denormal / overflow / tie-heavy operand classes included."""
+    assert oracle_cpu.twice_product_identity_mismatches(20_000_000, seed=7) == 0
 
 
 @pytest.mark.parametrize("view_id,w,h,stride", [(14, 384, 216, 4), (5, 384, 216, 5), (19, 192, 108, 5), (1, 192, 108, 5)])

@@ -1,7 +1,8 @@
-"""Dev tool: render one configuration a few times (for ncu): python tests/gpu_one.py VIEW ALG [N_ITER] [W H] [--noref]"""
+"""Dev tool: render one configuration a few times (for ncu): python tools/gpu_one.py VIEW ALG [N_ITER] [W H] [--noref]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from gpu_probe import run
 from fractalshark_b200 import RenderAlgorithm as A
 args = [a for a in sys.argv[1:] if not a.startswith("--")]

@@ -2,6 +2,7 @@
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from fractalshark_b200 import RenderAlgorithm, Numeric, traits
 from fractalshark_b200.gpu_renderer import GPURenderer
