@@ -402,12 +402,19 @@ uint32_t upload_la(fs_renderer *r, int numeric, uint32_t iter_bytes, const fs_la
     return rc;
 }
 
-// persistent grid: one 256-thread CTA per resident slot
+// persistent grid: one 256-thread CTA per resident slot -- minus kDisplaySlots.  The render kernels never give an SM
+// slot back before their queue is empty, and one warp-tile can last as long as the frame (interior pixels at a
+// multi-million iteration limit), so a progressive RenderCurrent (high-priority display stream, called by the
+// reference's pool once a second while the frame renders: RenderThreadPool.cpp:915-959, 1923-1948) would otherwise
+// wait for the end of the render.  Two CTA slots (of 592 for the HDRx32 kernels: 0.3 % of the throughput) stay free
+// for it at all times; more are freed on request where tiles turn over quickly (TileQueue::yield_quota).
+constexpr int kDisplaySlots = 2;
 template <class K> int resident_ctas(fs_renderer *r, K kernel) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     if (r->ctas_per_sm_cap > 0 && per_sm > r->ctas_per_sm_cap) per_sm = r->ctas_per_sm_cap;
-    return per_sm * r->num_sms;
+    const int slots = per_sm * r->num_sms;
+    return slots > 8 * kDisplaySlots ? slots - kDisplaySlots : slots;
 }
 
 // Grid of the LAv2 kernels.  Full occupancy (4 CTAs/SM for HDRx32) is best while every warp gets many tiles; once a
@@ -416,12 +423,12 @@ template <class K> int resident_ctas(fs_renderer *r, K kernel) {
 // measured 1.035 vs 1.088 ms on that shard, 1.95 vs 1.88 ms on the 4-way shard (13.7 tiles per warp), 7.64 vs 7.30 ms
 // on the whole frame.  Below 8 tiles per warp the grid drops to 3/4 of the occupancy.
 template <class K> int lav2_grid(fs_renderer *r, K kernel) {
-    int per_sm = resident_ctas(r, kernel) / r->num_sms;
+    int per_sm = (resident_ctas(r, kernel) + kDisplaySlots) / r->num_sms;
     const uint64_t tiles_x = (r->width + 7) / 8;
     const uint64_t bands = ((r->height + 3) / 4 + r->shard_count - 1 - r->shard_index) / r->shard_count;
     const uint64_t warps = (uint64_t)per_sm * r->num_sms * 8;
-    if (r->ctas_per_sm_cap == 0 && per_sm >= 4 && tiles_x * bands < 8 * warps) per_sm = per_sm * 3 / 4;
-    return per_sm * r->num_sms;
+    if (r->ctas_per_sm_cap == 0 && per_sm >= 4 && tiles_x * bands < 8 * warps) return per_sm * 3 / 4 * r->num_sms;
+    return per_sm * r->num_sms - kDisplaySlots;
 }
 
 // CTAs a progressive RenderCurrent asks to leave a running persistent grid (of num_sms x 2..8 CTAs): enough slots for

@@ -427,7 +427,9 @@ def test_progressive_render_current_returns_during_a_running_render():
         assert filled.any() and not filled.all()                   # a partial frame
         np.testing.assert_array_equal(part[:h, :w][filled], want[:h, :w][filled])   # finished pixels are final
         assert 0 < red["Sum"] < want_red["Sum"]
-    assert partials[0][0] < 0.7 * t_done
+    # asked for a quarter of the way in, back well before the end -- even though every warp-tile of this workload
+    # (interior pixels first, each running to the iteration limit) outlasts the wait
+    assert partials[0][0] < 0.6 * t_done, (partials[0][0], t_done)
     # the render that lent its slots is not much slower (8 of ~600 CTAs)
     assert r.LastRenderMs() < 1.25 * full_ms
     r.close()
