@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <new>
 #include <vector>
 
@@ -108,6 +109,7 @@ struct fs_renderer {
     // run, so the device->host transfer of the frame overlaps the render instead of following it
     void *sink_host = nullptr, *sink_dev = nullptr;
     bool sink_registered = false, sink_filled = false;
+    int carveout_pct = -1;   // explicit shared-memory carve-out preference for every kernel (% of 228 KB), -1 = the driver's choice; FS_CARVEOUT
     int ctas_per_sm_cap = 0; // FS_CTAS_PER_SM: experiment switch, caps the persistent grid below full occupancy
     bool split_at = false;  // HDRx32 + AT: AT shortcut in its own launch ahead of the LA/perturbation launch (fs_lav2.cuh AtPhase);
                             // measured slower than the fused launch (View 14: 9.7 vs 8.5 ms), kept as an A/B switch
@@ -409,7 +411,17 @@ uint32_t upload_la(fs_renderer *r, int numeric, uint32_t iter_bytes, const fs_la
 // wait for the end of the render.  Two CTA slots (of 592 for the HDRx32 kernels: 0.3 % of the throughput) stay free
 // for it at all times; more are freed on request where tiles turn over quickly (TileQueue::yield_quota).
 constexpr int kDisplaySlots = 2;
+// Kernels of two streams share an SM only if they agree on its shared-memory carve-out (it cannot change while CTAs are
+// resident; measured with tools/concurrency_probe.cu: a launch whose carve-out differs waits until the SMs have drained,
+// i.e. until the render is over).  The driver sizes the carve-out from the launch's occupancy -- 1 KB is reserved per
+// resident CTA, so a <<<1, 1>>> launch (up to 32 CTAs per SM) asks for four times the carve-out of a 256-thread one.
+// Every kernel of this library is therefore launched with 256-thread CTAs and a few bytes of static shared memory at
+// most, which puts all of them in the same class; FS_CARVEOUT (a percentage) forces an explicit preference instead.
+template <class K> void same_carveout(fs_renderer *r, K kernel) {
+    if (r->carveout_pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, r->carveout_pct);
+}
 template <class K> int resident_ctas(fs_renderer *r, K kernel) {
+    same_carveout(r, kernel);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     if (r->ctas_per_sm_cap > 0 && per_sm > r->ctas_per_sm_cap) per_sm = r->ctas_per_sm_cap;
@@ -707,7 +719,12 @@ template <class Pixel> uint32_t launch_direct_ext_pods(fs_renderer *r, const voi
 }
 
 template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaStream_t stream) {
-    reduction_init_kernel<IterT><<<1, 1, 0, stream>>>(r->red_dev);
+    same_carveout(r, reduction_init_kernel<IterT>);
+    same_carveout(r, post_kernel<IterT, 1>);
+    same_carveout(r, post_kernel<IterT, 2>);
+    same_carveout(r, post_kernel<IterT, 3>);
+    same_carveout(r, post_kernel<IterT, 4>);
+    reduction_init_kernel<IterT><<<1, 256, 0, stream>>>(r->red_dev); // 256 threads: same carve-out class as the render kernels
     const int pitch = (int)(r->w_block * NB_THREADS_W);
     const int grid = r->num_sms * 8;
     const IterT *it = static_cast<const IterT *>(r->iter_buf);
@@ -721,6 +738,19 @@ template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaSt
 #undef FS_POST
     r->launches += 2;
     return cudaGetLastError();
+}
+
+template <class IterT> void preload_post_kernels_typed() {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, reduction_init_kernel<IterT>);
+    cudaFuncGetAttributes(&fa, post_kernel<IterT, 1>);
+    cudaFuncGetAttributes(&fa, post_kernel<IterT, 2>);
+    cudaFuncGetAttributes(&fa, post_kernel<IterT, 3>);
+    cudaFuncGetAttributes(&fa, post_kernel<IterT, 4>);
+}
+void preload_post_kernels(fs_renderer *r) {
+    if (r->iter_bytes == 8) preload_post_kernels_typed<uint64_t>();
+    else preload_post_kernels_typed<uint32_t>();
 }
 
 // FP32 issue-rate probe: 16 independent FFMA chains per thread, no memory traffic.
@@ -764,6 +794,7 @@ fs_renderer *fs_create(int32_t device) {
         // development switches (profiling under ncu without touching the caller): FS_SPLIT_AT=1, FS_SCALED_STEPS=0
         if (const char *e = getenv("FS_SPLIT_AT")) r->split_at = atoi(e) != 0;
         if (const char *e = getenv("FS_CTAS_PER_SM")) r->ctas_per_sm_cap = atoi(e);
+        if (const char *e = getenv("FS_CARVEOUT")) r->carveout_pct = atoi(e);
         if (const char *e = getenv("FS_SCALED_STEPS")) r->use_scaled = atoi(e) != 0;
     }
     return r;
@@ -871,6 +902,9 @@ uint32_t fs_initialize_memory(fs_renderer *r, uint32_t iter_bytes, uint32_t w, u
     fs_clear_memory(r);
     cudaEventRecord(r->ev_alloc, r->compute);
     cudaStreamWaitEvent(r->display, r->ev_alloc, 0);
+    // With lazy module loading a kernel's first launch loads it, and that waits for running kernels: the result
+    // kernels are loaded here so the first progressive RenderCurrent does not sit out the render it was meant to show.
+    preload_post_kernels(r);
     return 0;
 }
 

@@ -15,6 +15,7 @@
 #include <type_traits>
 #include "fs_perturb_loop.cuh"
 #include "fs_at_fast.cuh"
+#include "fs_la_fast.cuh"
 
 #ifndef FS_AT_PACKED
 #define FS_AT_PACKED 1
@@ -25,14 +26,24 @@
 #ifndef FS_AT_CHUNK
 #define FS_AT_CHUNK 16
 #endif
+#ifndef FS_LA_FAST
+// HDRx32: 1 = flattened LA walk with the select-free step of fs_la_fast.cuh, 0 (default) = the nested walk on the
+// reference-shaped operations.  Both are bit-exact (GPU parity suite; oracle/lockstep_check.cpp for the step).  Measured
+// on View 14, 3840x2160: 7.37 ms flattened vs 7.08 ms nested -- the step is ~137 SASS instructions either way (the
+// nested form's selects cost what the flattened form's guards and second scaling multiply cost), so the build keeps
+// the nested walk; the flattened one is the per-lane state machine a lane-level refill would start from.
+#define FS_LA_FAST 0
+#endif
 // resident CTAs per SM the compiler must allow for lav2_kernel; undefined = plain __launch_bounds__(256) (HDRx32: 60
 // registers, 4 CTAs; an explicit 1 lets ptxas take 70 registers = 3 CTAs: View 5 29.0 vs 27.7 ms).
 // Measured: 5 (48 registers, 32 B spilled) View 14 7.13 vs 7.29 ms but View 5 28.8 vs 27.7 ms and an 8-way shard 1.17
 // vs 1.08 ms; 6 (40 registers) worse everywhere.
 #ifdef FS_LAV2_MIN_CTAS
-#define FS_LAV2_BOUNDS __launch_bounds__(256, FS_LAV2_MIN_CTAS)
+#define FS_LAV2_BOUNDS(Num) __launch_bounds__(256, FS_LAV2_MIN_CTAS)
 #else
-#define FS_LAV2_BOUNDS __launch_bounds__(256)
+// HDRx32 is held to 64 registers (4 CTAs of 256 threads per SM; with the flattened LA walk, FS_LA_FAST, ptxas would
+// otherwise take 71 and lose a quarter of the resident warps); the other numeric types keep the compiler's own choice.
+#define FS_LAV2_BOUNDS(Num) __launch_bounds__(256, (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4) ? 4 : 0)
 #endif
 
 namespace fs {
@@ -345,8 +356,100 @@ FS_D void lav2_stages(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc
     }
 }
 
+// ---- LA stages of one pixel, float+exponent binary32 (HDRx32): the same walk as lav2_stages above, flattened into one
+// loop whose body is a single select-free step (fs_la_fast.cuh).  Why: profiled on View 14, the nested form executes
+// ~185 warp-instructions per LA step at 22.6 of 32 lanes -- the operand selects of the three aligned additions, the
+// zero/clamp special cases of every operation and the stage-transition code all diverge inside a warp.  Here a lane is
+// either between stages (a short divergent loop picks the next stage whose threshold admits dc) or takes exactly one step
+// per trip; a step the fast form refuses (exact zeros, exponent gaps in [120,127), non-finite values: rare) is redone
+// by the reference-shaped operations, which stay the definition of the result.
+// The reference-shaped LA step (Prepare GPU_LAInfoDeep.h:90-105, Evaluate :120-123, getZ LAstep.h:181-185) for the steps the
+// select-free form refuses.  Out of line: it runs for ~1 % of the steps and its live values must not cost the fast
+// loop registers (inlined, the Full kernel needs 76 registers = 3 CTAs per SM instead of 4).
+__device__ __noinline__ void la_step_as_written(HdrC<float> Ref, HdrC<float> ZCoeff, HdrC<float> CCoeff, Hdr<float> LAThreshold,
+                                                HdrC<float> nref, HdrC<float> dz, HdrC<float> dc, HdrC<float> &ndz,
+                                                HdrC<float> &z, bool &unusable, bool &rebase) {
+    using Num = NumHdr<float>;
+    HdrC<float> newdz = mul(dz, add(Num::c_mul2(Ref), dz));
+    reduce(newdz);
+    unusable = ge_pr(cheb(newdz), LAThreshold);
+    rebase = false;
+    if (!unusable) {
+        ndz = add(mul(newdz, ZCoeff), mul(dc, CCoeff));
+        z = add(nref, ndz);
+        Hdr<float> zn = cheb(z), dn = cheb(ndz);
+        reduce(zn);
+        reduce(dn);
+        rebase = lt_pr(zn, dn);
+    }
+}
+
+template <class IterT, bool Count>
+FS_D void lav2_stages_hdr32(const Lav2Args<NumHdr<float>, IterT> &A, const HdrC<float> dc, HdrC<float> &dz,
+                            IterT &RefIteration, IterT &iter, unsigned long long &steps) {
+    using Num = NumHdr<float>;
+    using Real = Hdr<float>;
+    using Cplx = HdrC<float>;
+    using LA = LaRec<Num, IterT>;
+    IterT stage = A.la_valid ? A.la_stage_count : 0;
+    IterT LAIndex = 0, MacroItCount = 0, j = 0;
+    bool need_stage = true;
+    for (;;) {
+        while (need_stage) {
+            if (stage == 0) return;
+            stage--;
+            const StageRec<IterT> sr = A.stages[stage];
+            LAIndex = sr.LAIndex;
+            // isLAStageInvalid  GPU_LAReference.h:241-255
+            if (ge_pr(cheb(dc), A.las[LAIndex].LAThresholdC)) continue;
+            MacroItCount = sr.MacroItCount;
+            j = RefIteration;
+            need_stage = false;
+            if (!(iter < A.n_iterations)) return;
+        }
+        // getLA  GPU_LAReference.h:271-303: the record is fetched whole with 128-bit loads
+        const LA *recp = A.las + (LAIndex + j);
+        const LA rec = ldg_rec(recp);
+        const IterT l = rec.StepLength;
+        bool unusable = true, rebase = false;
+        Cplx ndz = dz, z = dz;
+        if (iter + l <= A.n_iterations) {
+            const Cplx nref = recp[1].Ref;
+            lafast::StepOut o;
+            if (lafast::step(rec.Ref.re, rec.Ref.im, rec.Ref.e, rec.ZCoeff.re, rec.ZCoeff.im, rec.ZCoeff.e, rec.CCoeff.re,
+                             rec.CCoeff.im, rec.CCoeff.e, rec.LAThreshold.m, rec.LAThreshold.e, nref.re, nref.im, nref.e,
+                             dz.re, dz.im, dz.e, dc.re, dc.im, dc.e, o)) {
+                unusable = o.unusable;
+                rebase = o.rebase;
+                ndz.re = o.dz.re; ndz.im = o.dz.im; ndz.e = o.dz.e;
+                z.re = o.z.re; z.im = o.z.im; z.e = o.z.e;
+            } else {
+                // results come back through locals of this branch only: the loop's own variables stay in registers
+                Cplx s_ndz, s_z;
+                bool s_unusable, s_rebase;
+                la_step_as_written(rec.Ref, rec.ZCoeff, rec.CCoeff, rec.LAThreshold, nref, dz, dc, s_ndz, s_z, s_unusable, s_rebase);
+                unusable = s_unusable;
+                rebase = s_rebase;
+                if (!s_unusable) { ndz = s_ndz; z = s_z; }
+            }
+        }
+        if (unusable) {
+            RefIteration = rec.NextStageLAIndex;
+            need_stage = true;
+            continue;
+        }
+        iter += l;
+        if (Count) steps++;
+        j++;
+        const bool rb = rebase || j >= MacroItCount;
+        dz = rb ? z : ndz;
+        j = rb ? (IterT)0 : j;
+        if (!(iter < A.n_iterations)) return;
+    }
+}
+
 template <class Num, class IterT, Lav2Mode Mode, bool Count, AtPhase Phase = AtPhase::Fused>
-__global__ void FS_LAV2_BOUNDS lav2_kernel(const Lav2Args<Num, IterT> A) {
+__global__ void FS_LAV2_BOUNDS(Num) lav2_kernel(const Lav2Args<Num, IterT> A) {
     using Real = typename Num::Real;
     using Cplx = typename Num::Cplx;
 
@@ -399,7 +502,10 @@ __global__ void FS_LAV2_BOUNDS lav2_kernel(const Lav2Args<Num, IterT> A) {
                 } else {
                     lav2_at<Num, IterT, Count>(A, dc, dz, iter, steps_at);
                 }
-                lav2_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps_la);
+                if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4 && FS_LA_FAST)
+                    lav2_stages_hdr32<IterT, Count>(A, dc, dz, RefIteration, iter, steps_la);
+                else
+                    lav2_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps_la);
             }
         }
 

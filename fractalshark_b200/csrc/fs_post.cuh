@@ -17,7 +17,8 @@ namespace fs {
 struct Color16 { uint16_t r, g, b, a; };                 // GPU_Types.h:14-16
 struct Reduction { unsigned long long Min, Max, Sum; };   // GPU_Types.h:40-50
 
-template <class IterT> __global__ void reduction_init_kernel(Reduction *out) {
+template <class IterT> __global__ void __launch_bounds__(256) reduction_init_kernel(Reduction *out) {
+    if (threadIdx.x != 0) return;
     out->Min = (unsigned long long)(IterT)~(IterT)0;
     out->Max = 0;
     out->Sum = 0;

@@ -14,6 +14,7 @@
 
 #include "../fractalshark_b200/csrc/fs_scaled_loop.cuh"
 #include "../fractalshark_b200/csrc/fs_at_fast.cuh"
+#include "../fractalshark_b200/csrc/fs_la_fast.cuh"
 
 namespace {
 
@@ -126,6 +127,31 @@ template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, in
         if (bits(z.re) != bits(re) || bits(z.im) != bits(im) || z.exp != plan.E) { st.mismatches++; return; }
     }
 }
+
+// LA steps: the product's select-free step (fs_la_fast.cuh) evaluated on the inputs of every step the oracle attempts;
+// whatever it accepts must agree bit for bit (decision, new delta, z, rebase-by-norm), whatever it refuses is counted.
+struct LaStats {
+    uint64_t steps = 0, refused = 0, mismatches = 0, unusable = 0;
+};
+struct LaObserver {
+    LaStats &st;
+    template <class Rec>
+    void la_step(const Rec &r, const HC &next_ref, const HC &dz, const HC &dc, bool unusable, bool, const HC &ndz, const HC &z,
+                 bool by_norm) {
+        fs::lafast::StepOut o;
+        st.steps++;
+        if (unusable) st.unusable++;
+        const bool ok = fs::lafast::step(r.Ref.re, r.Ref.im, r.Ref.exp, r.ZCoeff.re, r.ZCoeff.im, r.ZCoeff.exp, r.CCoeff.re,
+                                         r.CCoeff.im, r.CCoeff.exp, r.LAThreshold.mantissa, r.LAThreshold.exp, next_ref.re,
+                                         next_ref.im, next_ref.exp, dz.re, dz.im, dz.exp, dc.re, dc.im, dc.exp, o);
+        if (!ok) { st.refused++; return; }
+        if (o.unusable != unusable) { st.mismatches++; return; }
+        if (unusable) return;
+        if (bits(o.dz.re) != bits(ndz.re) || bits(o.dz.im) != bits(ndz.im) || o.dz.e != ndz.exp || bits(o.z.re) != bits(z.re) ||
+            bits(o.z.im) != bits(z.im) || o.z.e != z.exp || o.rebase != by_norm)
+            st.mismatches++;
+    }
+};
 
 } // namespace
 
@@ -252,6 +278,39 @@ uint64_t lockstep_render_lav2(int mode, const void *orbit, uint64_t count, const
         stats[4] = total.entries_refused; stats[5] = total.mismatches; stats[6] = total.finished_fast;
     }
     return total.mismatches;
+}
+
+
+// LA-step lockstep over a pixel sub-grid (HDRx32, AT + LA prologue only).  out[0..3] = steps, refused, mismatches, unusable.
+void lockstep_la(const void *las, const void *stages, const void *at, uint64_t la_stage_count, int use_at, int is_valid, int w,
+                 int h, const void *dx, const void *dy, const void *cx, const void *cy, uint64_t n_iterations, int iter_bytes,
+                 int col_step, int row_step, uint64_t *out) {
+    LaStats st;
+    auto run = [&](auto it) {
+        using IterT = decltype(it);
+        Lav2Job<IterT> J{};
+        J.mode = 3;
+        J.orbit = nullptr;
+        J.orbit_count = 0;
+        J.las = (const LAInfoDeepF<IterT> *)las;
+        J.stages = (const LAStageInfo<IterT> *)stages;
+        J.at = (const ATInfoF<IterT> *)at;
+        J.la_stage_count = (IterT)la_stage_count;
+        J.use_at = use_at && at;
+        J.is_valid = is_valid && las;
+        J.width = w; J.height = h; J.pitch = w;
+        memcpy(&J.dx, dx, 8); memcpy(&J.dy, dy, 8); memcpy(&J.centerX, cx, 8); memcpy(&J.centerY, cy, 8);
+        J.n_iterations = (IterT)n_iterations;
+        LaObserver obs{st};
+        for (int y = 0; y < h; y += row_step)
+            for (int x = 0; x < w; x += col_step) {
+                uint64_t steps = 0;
+                PerturbState<IterT> S;
+                lav2_prologue(J, x, y, steps, S, &obs);
+            }
+    };
+    if (iter_bytes == 8) run(uint64_t{}); else run(uint32_t{});
+    out[0] = st.steps; out[1] = st.refused; out[2] = st.mismatches; out[3] = st.unusable;
 }
 
 } // extern "C"

@@ -207,3 +207,20 @@ def twice_product_identity_mismatches(count, seed=1):
     L.lockstep_twice_product_identity.restype = C.c_uint64
     L.lockstep_twice_product_identity.argtypes = [C.c_uint64, C.c_uint64]
     return int(L.lockstep_twice_product_identity(count, seed))
+
+
+def lockstep_la(w, h, coords, la, n_iter, iter_bytes=4, col_step=1, row_step=1):
+    """Runs the product's select-free LA step (fs_la_fast.cuh, host build) on the inputs of every LA step the oracle
+    attempts for the sampled pixels.  Returns {"steps", "refused", "mismatches", "unusable"}; mismatches must be 0."""
+    global _lock
+    if _lock is None:
+        _lock = C.CDLL(LOCKSTEP_LIB)
+    fn = _lock.lockstep_la
+    fn.restype = None
+    V, I, U64 = C.c_void_p, C.c_int, C.c_uint64
+    fn.argtypes = [V, V, V, U64, I, I, I, I, V, V, V, V, U64, I, I, I, V]
+    l = la.descriptor()
+    out = (C.c_uint64 * 4)()
+    fn(l.las, l.stages, l.at, l.la_stage_count, l.use_at, l.is_valid, w, h, _buf(coords["dx"]), _buf(coords["dy"]),
+       _buf(coords["center_x"]), _buf(coords["center_y"]), n_iter, iter_bytes, col_step, row_step, out)
+    return dict(zip(("steps", "refused", "mismatches", "unusable"), (int(v) for v in out)))

@@ -179,6 +179,17 @@ def test_scaled_plain_float_chunks_match_float_exponent_steps_in_lockstep(built,
     assert st["fast_steps"] > 4 * st["slow_steps"], st
 
 
+@pytest.mark.parametrize("view_id,w,h,stride", [(14, 384, 216, 4), (5, 384, 216, 4), (19, 192, 108, 3), (1, 192, 108, 3), (100, 192, 108, 3)])
+def test_select_free_la_step_matches_float_exponent_step_in_lockstep(built, view_id, w, h, stride):
+    """fs_la_fast.cuh (the LA step of the flattened walk, FS_LA_FAST) on the inputs of every LA step the oracle attempts:
+    whatever it accepts agrees bit for bit -- usable/unusable, new delta, z, rebase-by-norm; what it refuses (exact
+    zeros, exponent gaps in [120,127), non-finite values) is left to the reference-shaped step and stays a minority."""
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 4)
+    st = oracle_cpu.lockstep_la(w, h, coords, la, n, col_step=stride, row_step=stride)
+    assert st["mismatches"] == 0, st
+    assert st["steps"] > 10_000 and st["refused"] < st["steps"] // 4, st
+
+
 def test_twice_the_rounded_product_identity_behind_the_six_rounding_at_pass(built):
     """fma(a, b, RN(a*b)) == 2*RN(a*b): what lets the AT pass drop the reference's seventh rounding (fs_at_fast.cuh).
     40 M random binary32 + binary64 pairs, denormal / overflow / tie-heavy operand classes included."""
