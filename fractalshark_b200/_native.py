@@ -63,6 +63,7 @@ GPU_SYMBOLS = {
     "fs_get_height": (_U32, [_V]),
     "fs_set_shard": (_U32, [_V, _U32, _U32]),
     "fs_measure_fp32_issue_peak": (_U32, [_I32, C.POINTER(C.c_double)]),
+    "fs_measure_fp64_issue_peak": (_U32, [_I32, C.POINTER(C.c_double)]),
     "fs_last_render_ms": (_U32, [_V, C.POINTER(C.c_float)]),
     "fs_enable_step_counter": (_U32, [_V, _I32]),
     "fs_read_step_counter": (_U32, [_V, C.POINTER(_U64)]),

@@ -769,6 +769,22 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float *sink, int iters, 
     if (s == 12345.678f) *sink = s;
 }
 
+// FP64 issue-rate probe: the same shape with DFMA chains.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters, double seed) {
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = seed + (double)(threadIdx.x + k);
+    const double m = 0.999, c = 0.001;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) a[k] = __fma_rn(a[k], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += a[k];
+    if (s == 12345.678) *sink = s;
+}
+
 void CUDART_CB done_trampoline(void *p) {
     fs_renderer *r = static_cast<fs_renderer *>(p);
     if (r->cb) r->cb(r->cb_user);
@@ -1218,6 +1234,37 @@ uint32_t fs_measure_fp32_issue_peak(int32_t device, double *ffma_per_second) {
     cudaEventDestroy(e1);
     cudaFree(sink);
     *ffma_per_second = best;
+    return err;
+}
+
+uint32_t fs_measure_fp64_issue_peak(int32_t device, double *dfma_per_second) {
+    DeviceGuard g(device);
+    int sms = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err != cudaSuccess) return err;
+    double *sink = nullptr;
+    err = cudaMalloc(&sink, sizeof(double));
+    if (err != cudaSuccess) return err;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 11;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(sink, iters, 1.0 + rep);
+        cudaEventRecord(e1);
+        err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double n = (double)blocks * threads * (double)iters * 16.0;
+        if (rep > 0 && n / (ms * 1e-3) > best) best = n / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *dfma_per_second = best;
     return err;
 }
 

@@ -213,6 +213,14 @@ class GPURenderer:
             raise RuntimeError(GPURenderer.ConvertErrorToString(rc))
         return float(v.value)
 
+    @staticmethod
+    def MeasureFp64IssuePeak(device: int = 0) -> float:
+        v = C.c_double(0)
+        rc = N.gpu_lib().fs_measure_fp64_issue_peak(device, C.byref(v))
+        if rc:
+            raise RuntimeError(GPURenderer.ConvertErrorToString(rc))
+        return float(v.value)
+
     def LastRenderMs(self) -> float:
         ms = C.c_float(0)
         rc = self._lib.fs_last_render_ms(self._h, C.byref(ms))

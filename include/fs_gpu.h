@@ -173,6 +173,8 @@ uint32_t fs_set_shard(fs_renderer *r, uint32_t shard_count, uint32_t shard_index
 /* Measured FP32 issue peak of `device` (FFMA thread-instructions per second, micro-kernel with 16
  * independent chains per thread): the denominator of the roofline fraction reported by bench.py. */
 uint32_t fs_measure_fp32_issue_peak(int32_t device, double *ffma_per_second);
+/* Same probe with DFMA chains: the denominator for the FP64 kernels (Gpu1x64 direct, FP64 perturbation). */
+uint32_t fs_measure_fp64_issue_peak(int32_t device, double *dfma_per_second);
 /* Device time (CUDA events on the compute stream) of the most recent render kernel, in ms. Syncs. */
 uint32_t fs_last_render_ms(fs_renderer *r, float *ms);
 /* Count executed steps (perturbation + LA + AT) of subsequent renders into a device counter. */

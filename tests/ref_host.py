@@ -29,6 +29,8 @@ def lib():
         L.refhost_la_info.argtypes = [V, I, C.POINTER(U64)]
         L.refhost_la_copy.argtypes = [V, I, V, V, V]
         L.refhost_free.argtypes = [V, I]
+        L.refhost_cpu_lav2.restype = U64
+        L.refhost_cpu_lav2.argtypes = [V, I, I, I, V, V, V, V, U64, V, I, I, I]
         L.refhost_build_blas.restype = U64
         L.refhost_build_blas.argtypes = [V, I, C.POINTER(C.c_int32)]
         L.refhost_blas_level.restype = U64
@@ -68,4 +70,24 @@ class RefLaTable:
                 if n:
                     L.refhost_blas_level(h, iter_bytes, lv, a.ctypes.data)
                 self.blas_levels.append(a)
-        L.refhost_free(h, iter_bytes)
+        self._h, self._iter_bytes, self._orbit = h, iter_bytes, orbit   # the orbit's memory is borrowed by the handle
+
+    def cpu_lav2(self, w, h, coords, n_iterations, row_step=1, col_step=1, threads=0, want_iters=False):
+        """The reference's CPU renderer for HDRx32 + LAv2 (Fractal::CalcCpuPerturbationFractalLAV2<IterType, float,
+        Disable>, Fractal.cpp:2485-2691; loop restated in ref_host_harness.cpp on the reference's own types and compiled
+        methods) over a regular sub-grid of the w x h frame.  Returns (sum of iteration counts, iters or None)."""
+        out = None
+        if want_iters:
+            out = np.zeros((h, w), np.uint32 if self._iter_bytes == 4 else np.uint64)
+        buf = lambda b: C.cast(C.create_string_buffer(b, len(b)), C.c_void_p)
+        total = lib().refhost_cpu_lav2(self._h, self._iter_bytes, w, h, buf(coords["dx"]), buf(coords["dy"]),
+                                       buf(coords["center_x"]), buf(coords["center_y"]), n_iterations,
+                                       out.ctypes.data if out is not None else None, row_step, col_step, threads)
+        return int(total), out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().refhost_free(self._h, self._iter_bytes)
+            self._h = None
+
+    __del__ = close
