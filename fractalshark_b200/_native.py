@@ -52,7 +52,7 @@ GPU_SYMBOLS = {
     "fs_render_perturb_bla_scaled": (_U32, [_V, _U32, _I32, C.POINTER(FsOrbit), C.POINTER(FsOrbit), _V, _V, _V, _V,
                                             _V, _V, _U64, _I32]),
     "fs_render_current": (_U32, [_V, _U64, _V, _V, C.POINTER(FsReduction), _I32]),
-    "fs_render_current_shard": (_U32, [_V, _U64, _V, C.POINTER(FsReduction), _I32]),
+    "fs_render_current_shard": (_U32, [_V, _U64, _V, _V, C.POINTER(FsReduction), _I32]),
     "fs_set_result_sink": (_U32, [_V, _V, _U64]),
     "fs_sync_compute_stream": (_U32, [_V]),
     "fs_sync_display_stream": (_U32, [_V]),

@@ -61,6 +61,7 @@ static_assert(sizeof(WireAT<NumHdr2x32, uint32_t>) == 184 && sizeof(WireAT<NumHd
 struct DeviceBlob {
     void *ptr = nullptr;
     size_t bytes = 0;
+    bool host = false; // page-locked host memory read over PCIe: the reference's fallback when device memory runs out
 };
 
 struct OrbitDev {
@@ -110,6 +111,7 @@ struct fs_renderer {
     void *sink_host = nullptr, *sink_dev = nullptr;
     bool sink_registered = false, sink_filled = false;
     int carveout_pct = -1;   // explicit shared-memory carve-out preference for every kernel (% of 228 KB), -1 = the driver's choice; FS_CARVEOUT
+    bool force_host_tables = false; // FS_FORCE_HOST_TABLES: take the page-locked fallback of alloc_table (test hook)
     int ctas_per_sm_cap = 0; // FS_CTAS_PER_SM: experiment switch, caps the persistent grid below full occupancy
     bool split_at = false;  // HDRx32 + AT: AT shortcut in its own launch ahead of the LA/perturbation launch (fs_lav2.cuh AtPhase);
                             // measured slower than the fused launch (View 14: 9.7 vs 8.5 ms), kept as an A/B switch
@@ -137,9 +139,32 @@ struct DeviceGuard {
 };
 
 void free_blob(fs_renderer *r, DeviceBlob &b) {
-    if (b.ptr) cudaFreeAsync(b.ptr, r->compute);
+    if (b.ptr && b.host) {
+        cudaStreamSynchronize(r->compute); // cudaFreeHost is not stream-ordered
+        cudaFreeHost(b.ptr);
+    } else if (b.ptr) {
+        cudaFreeAsync(b.ptr, r->compute);
+    }
     b.ptr = nullptr;
     b.bytes = 0;
+    b.host = false;
+}
+
+// Table memory (orbit, LA records, LA stages): device memory, else page-locked host memory the kernels read through the
+// unified address space -- the reference's own fallback for orbits that do not fit (Perturb.cuh:50-61,
+// GPU_LAReference.h:90-113).  FS_FORCE_HOST_TABLES=1 takes the fallback unconditionally (test hook).
+cudaError_t alloc_table(fs_renderer *r, DeviceBlob &b, size_t bytes) {
+    b = DeviceBlob{};
+    cudaError_t err = r->force_host_tables ? cudaErrorMemoryAllocation : cudaMallocAsync(&b.ptr, bytes, r->compute);
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        b.ptr = nullptr;
+        err = cudaMallocHost(&b.ptr, bytes);
+        if (err != cudaSuccess) return err;
+        b.host = true;
+    }
+    b.bytes = bytes;
+    return cudaSuccess;
 }
 
 void reset_perturb(fs_renderer *r) {
@@ -242,7 +267,7 @@ uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, u
         if (e != cudaSuccess) return e;
         e = cudaMemcpyAsync(wire, src->elements, eb * src->compressed_count, cudaMemcpyDefault, r->compute);
         if (e != cudaSuccess) return e;
-        e = cudaMallocAsync(&dst.data.ptr, full_bytes + 64, r->compute);
+        e = alloc_table(r, dst.data, full_bytes + 64);
         if (e != cudaSuccess) return e;
         dst.data.bytes = full_bytes;
         e = cudaMemsetAsync(static_cast<char *>(dst.data.ptr) + full_bytes, 0, 64, r->compute);
@@ -284,7 +309,7 @@ uint32_t upload_orbit(fs_renderer *r, OrbitDev &dst, int numeric, int pextras, u
     const size_t bytes = eb * src->compressed_count;
     // one zeroed element of padding: the reference's FP64 BLA kernel can read one element past the end after an
     // escaping skip (BLAKernels.cuh:128-134, its own TODO); the value there does not reach the output
-    cudaError_t err = cudaMallocAsync(&dst.data.ptr, bytes + 64, r->compute);
+    cudaError_t err = alloc_table(r, dst.data, bytes + 64);
     if (err != cudaSuccess) return err;
     dst.data.bytes = bytes;
     err = cudaMemsetAsync(static_cast<char *>(dst.data.ptr) + bytes, 0, 64, r->compute);
@@ -336,9 +361,8 @@ template <class Num, class IterT> uint32_t upload_la_typed(fs_renderer *r, const
     using D = LaRec<Num, IterT>;
     LaDev &la = r->la;
     const size_t n = src->num_las;
-    cudaError_t err = cudaMallocAsync(&la.las.ptr, (n ? n : 1) * sizeof(D), r->compute);
+    cudaError_t err = alloc_table(r, la.las, (n ? n : 1) * sizeof(D));
     if (err != cudaSuccess) return err;
-    la.las.bytes = (n ? n : 1) * sizeof(D);
     if (n) {
         void *wire = nullptr;
         err = cudaMallocAsync(&wire, n * sizeof(W), r->compute);
@@ -350,9 +374,8 @@ template <class Num, class IterT> uint32_t upload_la_typed(fs_renderer *r, const
         cudaFreeAsync(wire, r->compute);
     }
     const size_t sbytes = (src->num_stages ? src->num_stages : 1) * sizeof(StageRec<IterT>);
-    err = cudaMallocAsync(&la.stages.ptr, sbytes, r->compute);
+    err = alloc_table(r, la.stages, sbytes);
     if (err != cudaSuccess) return err;
-    la.stages.bytes = sbytes;
     if (src->num_stages) {
         err = cudaMemcpyAsync(la.stages.ptr, src->stages, src->num_stages * sizeof(StageRec<IterT>), cudaMemcpyHostToDevice, r->compute);
         if (err != cudaSuccess) return err;
@@ -728,7 +751,7 @@ template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaSt
     const int pitch = (int)(r->w_block * NB_THREADS_W);
     const int grid = r->num_sms * 8;
     const IterT *it = static_cast<const IterT *>(r->iter_buf);
-#define FS_POST(AA) post_kernel<IterT, AA><<<grid, 256, 0, stream>>>(it, pitch, r->color_buf, r->pal_dev, r->pal_iters, r->aux_depth, (int)r->color_w, (int)r->color_h, (IterT)n_iter, r->red_dev)
+#define FS_POST(AA) post_kernel<IterT, AA><<<grid, 256, 0, stream>>>(it, pitch, r->color_buf, r->pal_dev, r->pal_iters, r->aux_depth, (int)r->color_w, (int)r->color_h, (IterT)n_iter, r->red_dev, (int)r->shard_count, (int)r->shard_index)
     switch (r->aa) {
     case 1: FS_POST(1); break;
     case 2: FS_POST(2); break;
@@ -811,6 +834,7 @@ fs_renderer *fs_create(int32_t device) {
         if (const char *e = getenv("FS_SPLIT_AT")) r->split_at = atoi(e) != 0;
         if (const char *e = getenv("FS_CTAS_PER_SM")) r->ctas_per_sm_cap = atoi(e);
         if (const char *e = getenv("FS_CARVEOUT")) r->carveout_pct = atoi(e);
+        if (const char *e = getenv("FS_FORCE_HOST_TABLES")) r->force_host_tables = atoi(e) != 0;
         if (const char *e = getenv("FS_SCALED_STEPS")) r->use_scaled = atoi(e) != 0;
     }
     return r;
@@ -1104,13 +1128,16 @@ uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buf
     return 0;
 }
 
-// Multi-GPU result path: only the 4-row bands this shard rendered leave the device (one strided 2-D copy), so N
-// ranks writing into one host frame (e.g. a registered shared-memory mapping) assemble it with no collective and
-// 1/N of the PCIe bytes each.  The reduction results cover this shard's rows (the others are zero on this device).
-uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *iter_buffer,
+// Multi-GPU result path: only the 4-row bands this shard rendered leave the device (one strided 2-D copy each for the
+// iteration cells and, when asked for, their colours), so N ranks writing into one host frame (e.g. a registered
+// shared-memory mapping) assemble it with no collective and 1/N of the PCIe bytes each.  Colours and Min/Max/Sum cover this
+// shard's cells only (post_kernel skips the others): the frame's reduction is min / max / sum over the shards'.
+uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *iter_buffer, fs_color16 *color_buffer,
                                  fs_reduction *reduction_results, int32_t progressive) {
     if (!r || !memory_initialized(r)) return 0;
-    if (r->shard_count <= 1) return fs_render_current(r, n_iterations, iter_buffer, nullptr, reduction_results, progressive);
+    if (r->shard_count <= 1) return fs_render_current(r, n_iterations, iter_buffer, color_buffer, reduction_results, progressive);
+    // an antialiasing cell must lie inside one 4-row band: 3x3 cells straddle bands, their colours would need other shards' rows
+    if (color_buffer && r->aa == 3) return FS_ERROR_UNSUPPORTED;
     DeviceGuard g(r->device);
     cudaStream_t stream = progressive ? r->display : r->compute;
     if (progressive) request_yield_if_rendering(r);
@@ -1125,6 +1152,29 @@ uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *it
         if (owned) {
             err = cudaMemcpy2DAsync((char *)iter_buffer + first, stride, (const char *)r->iter_buf + first, stride,
                                     4 * row_bytes, owned, cudaMemcpyDefault, stream);
+            if (err != cudaSuccess) return err;
+        }
+    }
+    if (color_buffer) {
+        // colour cells are stored un-padded (index oy * color_w + ox, AntialiasingKernel.cuh:3-71): the colour rows of one
+        // band, 4 / AA of them, are contiguous; band b of this shard sits at row (b * shard_count + shard_index) * 4 / AA
+        const size_t rows_per_band = 4 / r->aa;
+        const size_t band_bytes = rows_per_band * (size_t)r->color_w * sizeof(Color16);
+        const size_t total_bands = ((size_t)r->color_h + rows_per_band - 1) / rows_per_band;
+        const size_t full_rows_bands = (size_t)r->color_h / rows_per_band; // bands with all their rows inside the frame
+        size_t owned_full = 0;
+        if (full_rows_bands > r->shard_index) owned_full = (full_rows_bands - r->shard_index + r->shard_count - 1) / r->shard_count;
+        const size_t first = (size_t)r->shard_index * band_bytes, stride = (size_t)r->shard_count * band_bytes;
+        if (owned_full) {
+            err = cudaMemcpy2DAsync((char *)color_buffer + first, stride, (const char *)r->color_buf + first, stride, band_bytes,
+                                    owned_full, cudaMemcpyDefault, stream);
+            if (err != cudaSuccess) return err;
+        }
+        if (total_bands > full_rows_bands && (total_bands - 1) % r->shard_count == r->shard_index) {
+            // the frame's last band is cut short by the frame edge and belongs to this shard
+            const size_t off = (total_bands - 1) * band_bytes;
+            const size_t rest = ((size_t)r->color_h - full_rows_bands * rows_per_band) * (size_t)r->color_w * sizeof(Color16);
+            err = cudaMemcpyAsync((char *)color_buffer + off, (const char *)r->color_buf + off, rest, cudaMemcpyDefault, stream);
             if (err != cudaSuccess) return err;
         }
     }

@@ -28,12 +28,15 @@ template <class IterT, int AA>
 __global__ void __launch_bounds__(256) post_kernel(const IterT *__restrict__ iters, int pitch,
                                                    Color16 *__restrict__ colors, const Color16 *__restrict__ pal,
                                                    uint32_t pal_iters, uint32_t aux_depth, int color_w, int color_h,
-                                                   IterT n_iterations, Reduction *out) {
+                                                   IterT n_iterations, Reduction *out, int shard_count, int shard_index) {
     unsigned long long vmin = ~0ull, vmax = 0, vsum = 0;
     const size_t total = (size_t)color_w * (size_t)color_h;
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
         const int ox = (int)(o % (size_t)color_w);
         const int oy = (int)(o / (size_t)color_w);
+        // multi-GPU: a shard colours and reduces the cells of its own 4-row bands only (AA in {1,2,4} divides the band
+        // height, so a cell never straddles two bands; the host refuses AA 3 with more than one shard)
+        if (shard_count > 1 && ((oy * AA) >> 2) % shard_count != shard_index) continue;
         unsigned long long ar = 0, ag = 0, ab = 0;
 #pragma unroll
         for (int sx = 0; sx < AA; sx++) {

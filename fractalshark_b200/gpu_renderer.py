@@ -151,16 +151,21 @@ class GPURenderer:
             rc = self.SyncDisplayStream() if progressive else self.SyncComputeStream()
         return rc, iters, colors, {"Min": int(red.Min), "Max": int(red.Max), "Sum": int(red.Sum)}
 
-    def RenderCurrentShard(self, n_iterations: int, iters_out, progressive: bool = False):
+    def RenderCurrentShard(self, n_iterations: int, iters_out, progressive: bool = False, colors_out=None):
         """Multi-GPU form: copies only the 4-row bands this shard rendered (``SetShard``) into the same positions of
         ``iters_out`` -- a caller-owned whole-frame host array, typically one shared-memory frame every rank writes
-        into -- and leaves the other rows untouched.  Returns ``(status, reduction over this shard's rows)``."""
+        into -- and leaves the other rows untouched; ``colors_out`` (whole-frame colour array, shape of
+        ``RenderCurrent``'s) receives the Color16 cells of those bands the same way.
+        Returns ``(status, reduction over this shard's cells)``."""
         hp, wp = self.buffer_shape()
         dt = np.uint32 if self._iter_bytes == 4 else np.uint64
         assert iters_out.shape == (hp, wp) and iters_out.dtype == dt and iters_out.flags["C_CONTIGUOUS"]
+        if colors_out is not None:
+            assert colors_out.dtype == np.uint16 and colors_out.flags["C_CONTIGUOUS"]
         red = N.FsReduction()
-        rc = int(self._lib.fs_render_current_shard(self._h, n_iterations, iters_out.ctypes.data, C.byref(red),
-                                                   int(progressive)))
+        rc = int(self._lib.fs_render_current_shard(self._h, n_iterations, iters_out.ctypes.data,
+                                                   colors_out.ctypes.data if colors_out is not None else None,
+                                                   C.byref(red), int(progressive)))
         if rc == 0:
             rc = self.SyncDisplayStream() if progressive else self.SyncComputeStream()
         return rc, {"Min": int(red.Min), "Max": int(red.Max), "Sum": int(red.Sum)}

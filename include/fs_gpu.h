@@ -141,10 +141,13 @@ uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buf
                            fs_reduction *reduction_results, int32_t progressive);
 
 /* Sharded form of RenderCurrent (no reference counterpart: the reference drives one GPU, GPU_Render.h:123-129 is the
- * whole-frame call).  After fs_set_shard(n, i) it copies only the 4-row bands shard i rendered into the same
- * positions of iter_buffer (whole-frame layout as above), so n processes can fill one host frame without a
- * collective.  With one shard it is fs_render_current without a colour buffer. */
-uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *iter_buffer,
+ * whole-frame call).  After fs_set_shard(n, i) it copies only the 4-row bands shard i rendered -- iteration cells and,
+ * when color_buffer is given, the Color16 cells computed from them -- into the same positions of whole-frame host
+ * buffers (layouts as in fs_render_current), so n processes can fill one host frame without a collective.  Colours and
+ * the reduction cover this shard's cells only (frame reduction = min / max / sum of the shards').  Antialiasing 3 with
+ * n > 1 and a colour buffer is refused (FS_ERROR_UNSUPPORTED): 3x3 cells straddle the 4-row bands.  With one shard it
+ * is fs_render_current. */
+uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *iter_buffer, fs_color16 *color_buffer,
                                  fs_reduction *reduction_results, int32_t progressive);
 
 /* Result sink (no reference counterpart; the reference copies the frame after the render, GPU_Render.cu:1768-1788).

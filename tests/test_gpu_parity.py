@@ -381,6 +381,55 @@ def test_sharded_renders_of_every_kernel_family_merge_to_the_unsharded_frame(cas
     assert total == whole_red["Sum"]
 
 
+@pytest.mark.parametrize("aa,h_ss", [(1, 270), (2, 272), (4, 272), (2, 268)])
+def test_sharded_colour_frame_assembles_to_the_unsharded_one(aa, h_ss):
+    """RenderCurrentShard with a colour buffer: every shard colours the cells of its own 4-row bands and copies exactly
+    those (iterations and Color16) into whole-frame host buffers; three shards fill the frames the unsharded
+    RenderCurrent produces, and Min/Max/Sum combine to the frame's.  268 rows: the last band is cut by the frame edge."""
+    w, h, alg, n = 96 * aa, h_ss, A.Gpu1x64, 300
+    _, coords, _, _, _ = cases.make_inputs(0, w, h, alg, n, 4)
+    r = GPURenderer()
+    assert r.InitializeMemory(w, h, aa, iter_bytes=4) == 0
+    r.ClearMemory()
+    assert r.Render(alg, coords, n, 1) == 0
+    rc, want_it, want_col, want_red = r.RenderCurrent(n, want_colors=True)
+    assert rc == 0
+    it = np.full_like(want_it, 0xDEADBEEF)
+    col = np.zeros_like(want_col)
+    mins, maxs, sums = [], [], 0
+    for s in range(3):
+        assert r.SetShard(3, s) == 0
+        r.ClearMemory()
+        assert r.Render(alg, coords, n, 1) == 0
+        rc, red = r.RenderCurrentShard(n, it, colors_out=col)
+        assert rc == 0
+        mins.append(red["Min"]); maxs.append(red["Max"]); sums += red["Sum"]
+    np.testing.assert_array_equal(it[:h, :w], want_it[:h, :w])
+    n_cells = (h // aa) * (w // aa)
+    np.testing.assert_array_equal(col.reshape(-1, 4)[:n_cells], want_col.reshape(-1, 4)[:n_cells])
+    assert (min(mins), max(maxs), sums) == (want_red["Min"], want_red["Max"], want_red["Sum"])
+    r.close()
+
+
+def test_sharded_colours_with_antialiasing_3_are_refused():
+    """3x3 antialiasing cells straddle the 4-row bands the shards own: a colour buffer is refused, iterations still flow."""
+    w, h, alg, n = 96, 54, A.Gpu1x64, 100
+    _, coords, _, _, _ = cases.make_inputs(0, w, h, alg, n, 4)
+    r = GPURenderer()
+    assert r.InitializeMemory(w, h, 3, iter_bytes=4) == 0
+    assert r.SetShard(2, 1) == 0
+    r.ClearMemory()
+    assert r.Render(alg, coords, n, 1) == 0
+    hp, wp = r.buffer_shape()
+    it = np.zeros((hp, wp), np.uint32)
+    col = np.zeros((24, 32, 4), np.uint16)
+    rc, _ = r.RenderCurrentShard(n, it, colors_out=col)
+    assert rc == 10100
+    rc, _ = r.RenderCurrentShard(n, it)
+    assert rc == 0 and it.any()
+    r.close()
+
+
 def test_progressive_render_current_returns_during_a_running_render():
     """RenderCurrent(progressive=true) is called by the reference's pool once a second WHILE the render kernel runs
     (RenderThreadPool.cpp:915-959, 1923-1948): it must come back with the partial frame (finished pixels, zeros
@@ -433,6 +482,20 @@ def test_progressive_render_current_returns_during_a_running_render():
     # the render that lent its slots is not much slower (8 of ~600 CTAs)
     assert r.LastRenderMs() < 1.25 * full_ms
     r.close()
+
+
+def test_tables_in_page_locked_host_memory_render_the_same_frame(monkeypatch):
+    """The reference keeps orbit and LA tables in page-locked host memory when device memory runs out (Perturb.cuh:50-61,
+    GPU_LAReference.h:90-113); the same fallback here (forced through FS_FORCE_HOST_TABLES) gives the same frames."""
+    for name in ("v5_hdr32_lav2", "v5_hdr32_rclav2", "v5_hdr32_bla", "v100_f64_lav2"):
+        _, view_id, w, h, alg, n_iter, ib = next(c for c in cases.ALL_SMALL_CASES if c[0] == name)
+        _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, ib)
+        want, _, want_red = cases.render(GPURenderer, w, h, alg, coords, orbit, la, n, ib)
+        monkeypatch.setenv("FS_FORCE_HOST_TABLES", "1")
+        got, _, got_red = cases.render(GPURenderer, w, h, alg, coords, orbit, la, n, ib)
+        monkeypatch.delenv("FS_FORCE_HOST_TABLES")
+        np.testing.assert_array_equal(got, want)
+        assert got_red == want_red
 
 
 def test_native_library_is_the_one_loaded():
