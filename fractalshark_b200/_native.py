@@ -70,6 +70,8 @@ GPU_SYMBOLS = {
     "fs_read_step_counters": (_U32, [_V, C.POINTER(_U64)]),
     "fs_set_scaled_steps": (_U32, [_V, _I32]),
     "fs_set_split_at": (_U32, [_V, _I32]),
+    "fs_set_pool_kernel": (_U32, [_V, _I32]),
+    "fs_set_at_cycle_detection": (_U32, [_V, _I32]),
     "fs_device_iter_buffer": (_V, [_V]),
     "fs_kernel_launch_count": (_U64, [_V]),
 }

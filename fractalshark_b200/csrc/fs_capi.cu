@@ -21,6 +21,7 @@
 #include "fs_direct.cuh"
 #include "fs_direct_ext.cuh"
 #include "fs_lav2.cuh"
+#include "fs_lav2_pool.cuh"
 #include "fs_orbit_rc.cuh"
 #include "fs_post.cuh"
 #include "fs_scaled_kernel.cuh"
@@ -116,6 +117,8 @@ struct fs_renderer {
     bool split_at = false;  // HDRx32 + AT: AT shortcut in its own launch ahead of the LA/perturbation launch (fs_lav2.cuh AtPhase);
                             // measured slower than the fused launch (View 14: 9.7 vs 8.5 ms), kept as an A/B switch
     DeviceBlob at_state;    // float4 per iteration-buffer cell, allocated on first use
+    bool at_cycle = true;   // AT shortcut: cycle detection (fs_lav2.cuh CycleWatch); FS_AT_CYCLE=0 / fs_set_at_cycle_detection executes every pass
+    bool use_pool = false;  // HDRx32 LAv2: the lane-refill kernel of fs_lav2_pool.cuh (FS_LAV2_POOL=0 / fs_set_pool_kernel: one tile per warp)
     bool use_scaled = true; // HDRx32: scaled plain-float chunks (fs_scaled_loop.cuh); off = pure float+exponent loop
     OrbitDev orbit1, orbit2;
     OrbitDev bla_orbit;                  // RenderPerturbBLA uploads its orbit and table per call (GPU_Render.cu:1462-1483)
@@ -466,6 +469,16 @@ template <class K> int lav2_grid(fs_renderer *r, K kernel) {
     return per_sm * r->num_sms - kDisplaySlots;
 }
 
+// Grid of the lane-refill LAv2 kernel (fs_lav2_pool.cuh): full occupancy with its per-warp pools in shared memory.
+template <class K> int pool_grid(fs_renderer *r, K kernel, size_t smem) {
+    same_carveout(r, kernel);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (r->ctas_per_sm_cap > 0 && per_sm > r->ctas_per_sm_cap) per_sm = r->ctas_per_sm_cap;
+    const int slots = per_sm * r->num_sms;
+    return slots > 8 * kDisplaySlots ? slots - kDisplaySlots : slots;
+}
+
 // CTAs a progressive RenderCurrent asks to leave a running persistent grid (of num_sms x 2..8 CTAs): enough slots for
 // the post kernel to stream the frame in well under a millisecond, ~1 % of the render's throughput
 constexpr int kYieldCtas = 8;
@@ -527,6 +540,7 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
     A.centerY = load_pod<Real>(cy);
     A.n_iterations = (IterT)n_iter;
     A.sink = static_cast<IterT *>(r->sink_dev);
+    A.at_cycle = r->at_cycle ? 1 : 0;
     A.queue = render_queue(r);
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     const bool count = r->count_steps;
@@ -554,6 +568,24 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
             else { if (count) FS_LAUNCH_SPLIT(Lav2Mode::LAO, true) else FS_LAUNCH_SPLIT(Lav2Mode::LAO, false) }
 #undef FS_LAUNCH_SPLIT
             r->launches++;
+            return end_render(r);
+        }
+    }
+    // float+exponent binary32: the lane-refill kernel (fs_lav2_pool.cuh); pixel coordinates travel as 16 + 16 bits
+    if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4) {
+        if (r->use_pool && r->width < 65536u && r->height < 65536u) {
+            begin_render(r, true);
+            const size_t smem = pool::Layout<IterT>::kCtaBytes;
+#define FS_LAUNCH_POOL(MODE)                                                                                           \
+    if (count) { auto k = lav2_pool_kernel<IterT, MODE, true>; k<<<pool_grid(r, k, smem), 256, smem, r->compute>>>(A); } \
+    else { auto k = lav2_pool_kernel<IterT, MODE, false>; k<<<pool_grid(r, k, smem), 256, smem, r->compute>>>(A); }
+            switch (mode) {
+            case FS_LAV2_FULL: FS_LAUNCH_POOL(Lav2Mode::Full) break;
+            case FS_LAV2_PO: FS_LAUNCH_POOL(Lav2Mode::PO) break;
+            case FS_LAV2_LAO: FS_LAUNCH_POOL(Lav2Mode::LAO) break;
+            default: return FS_ERROR_UNSUPPORTED;
+            }
+#undef FS_LAUNCH_POOL
             return end_render(r);
         }
     }
@@ -836,6 +868,8 @@ fs_renderer *fs_create(int32_t device) {
         if (const char *e = getenv("FS_CARVEOUT")) r->carveout_pct = atoi(e);
         if (const char *e = getenv("FS_FORCE_HOST_TABLES")) r->force_host_tables = atoi(e) != 0;
         if (const char *e = getenv("FS_SCALED_STEPS")) r->use_scaled = atoi(e) != 0;
+        if (const char *e = getenv("FS_LAV2_POOL")) r->use_pool = atoi(e) != 0;
+        if (const char *e = getenv("FS_AT_CYCLE")) r->at_cycle = atoi(e) != 0;
     }
     return r;
 }
@@ -1349,6 +1383,31 @@ uint32_t fs_set_result_sink(fs_renderer *r, void *host_iter_buffer, uint64_t byt
 uint32_t fs_set_split_at(fs_renderer *r, int32_t enable) {
     if (!r) return FS_ERROR_UNSUPPORTED;
     r->split_at = enable != 0;
+    return 0;
+}
+
+#ifdef FS_POOL_DEBUG
+// development build only: read and clear the session counters of fs_lav2_pool.cuh
+uint32_t fs_debug_pool_counters(uint64_t *out16) {
+    unsigned long long v[16];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(v, pool::fs_pool_dbg, sizeof(v));
+    for (int i = 0; i < 16; i++) out16[i] = v[i];
+    memset(v, 0, sizeof(v));
+    cudaMemcpyToSymbol(pool::fs_pool_dbg, v, sizeof(v));
+    return 0;
+}
+#endif
+
+uint32_t fs_set_at_cycle_detection(fs_renderer *r, int32_t enable) {
+    if (!r) return FS_ERROR_UNSUPPORTED;
+    r->at_cycle = enable != 0;
+    return 0;
+}
+
+uint32_t fs_set_pool_kernel(fs_renderer *r, int32_t enable) {
+    if (!r) return FS_ERROR_UNSUPPORTED;
+    r->use_pool = enable != 0;
     return 0;
 }
 

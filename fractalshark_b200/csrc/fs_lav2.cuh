@@ -26,6 +26,10 @@
 #ifndef FS_AT_CHUNK
 #define FS_AT_CHUNK 16
 #endif
+#ifndef FS_AT_CYCLE
+// Cycle detection in the AT shortcut (1 = on): see lav2_at.
+#define FS_AT_CYCLE 1
+#endif
 #ifndef FS_LA_FAST
 // HDRx32: 1 = flattened LA walk with the select-free step of fs_la_fast.cuh, 0 (default) = the nested walk on the
 // reference-shaped operations.  Both are bit-exact (GPU parity suite; oracle/lockstep_check.cpp for the step).  Measured
@@ -93,6 +97,7 @@ template <class Num, class IterT> struct Lav2Args {
     TileQueue queue;
     unsigned long long *step_counter; // optional: executed perturbation/LA/AT steps (bench roofline)
     float4 *at_state;                 // HDRx32 two-launch form: per-pixel AT result {dz.re, dz.im, dz.e}; iter sits in `out`
+    int at_cycle;                     // 1: cycle detection in the AT shortcut (CycleWatch), 0: every pass is executed
     IterT *sink;                      // optional mapped host copy of `out` (fs_set_result_sink): finished pixels stream out over PCIe
 };
 
@@ -179,6 +184,40 @@ template <> struct OrbitIO<NumHdr2x32> {
 // ---- small vocabulary shims so the kernel reads the same for plain and HDR numbers ------------
 template <class Num> FS_D bool c_is_ge(typename Num::Real a, typename Num::Real b) { return ge_pr(a, b); }
 
+// ---- cycle detection in the AT shortcut -----------------------------------------------------------------------------
+// PerformAT (ATInfo.h:155-188) iterates z <- z*z + c until |z|^2 passes the escape radius or n / StepLength passes are
+// done.  For a pixel inside the set the second case is the rule, and the passes are a deterministic map F of two binary32
+// (binary64) numbers: in AT coordinates the pixel's orbit falls towards an attracting cycle and, in finite precision,
+// reaches an exactly periodic sequence of states after a few hundred passes (View 14: the interior pixels run 18,402
+// passes each in the reference).  Once the state after a chunk equals, bit for bit, a state saved at an earlier chunk
+// boundary P passes before, every later state is known: no pass of the cycle escaped (each was tested), so none ever
+// will, and  z after `at_max` passes = F^((at_max - i) mod P) (z).  The watch below saves a state at chunk counts 1, 2, 4,
+// 8 ... (Brent's schedule) and compares after every chunk; on a hit it advances the pass counter by the largest multiple
+// of P that fits and lets the loop finish the remainder (< P passes) the ordinary way.  Same z, same pass count, hence the
+// same iteration buffer as the reference, bit for bit; what changes is the number of executed passes.
+template <class M, class IterT> struct CycleWatch {
+    M sre, sim;
+    IterT at;       // pass count of the saved state
+    IterT next;     // chunk-boundary pass count at which the next state is saved
+    bool armed;
+    FS_D CycleWatch(M re, M im, IterT i) : sre(re), sim(im), at(i), next(i + (IterT)FS_AT_CHUNK), armed(true) {}
+    FS_D static bool same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
+    FS_D static bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+    FS_D void after_chunk(M re, M im, IterT &i, IterT at_max, IterT &skipped) {
+        if (!armed) return;
+        if (same_bits(re, sre) && same_bits(im, sim)) {
+            const IterT P = i - at;
+            skipped = ((at_max - i) / P) * P;
+            i += skipped;
+            armed = false;
+        } else if (i == next) {
+            sre = re; sim = im;
+            next = i + (i - at) * 2; // gaps of 1, 2, 4, 8 ... chunks (stops growing if it would wrap: i never gets there)
+            at = i;
+        }
+    }
+};
+
 // ---- AT shortcut of one pixel (LAKernel.cuh:66-89, ATInfo.h:128-188) -----------------------------------------------
 template <class Num, class IterT, bool Count>
 FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, typename Num::Cplx &dz, IterT &iter,
@@ -191,6 +230,7 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
         reduce(c);
         Cplx z = Num::c_zero();
         IterT i = 0;
+        IterT at_skipped = 0; // passes the cycle watch accounted for without executing them
         bool at_done = false;
         if constexpr (Num::kHdr && !Num::kDf) {
             // Fast form of the loop below for the float+exponent types (binary32 and binary64 mantissas): the
@@ -212,12 +252,14 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                 //  * otherwise the running maximum of |z|^2 over the chunk (an overflowed pass shows as +inf before
                 //    any NaN can form).
                 constexpr int kAtChunk = FS_AT_CHUNK;
+                const bool cycle_watch = FS_AT_CYCLE && A.at_cycle;
                 auto chunks = [&](auto lean_tag) {
                     constexpr bool kLean = decltype(lean_tag)::value;
                     if constexpr (sizeof(M) == 4 && FS_AT_PACKED) {
                         // (re, im) travel as one packed pair: squares in one FMUL2, the scale-and-add of c in one FFMA2
                         // imaginary part as fma(RN(re*im), 2s, c.im): fs_at_fast.cuh `advance` has the argument
                         const f32x2 s2 = f2_make(s, s + s), c2 = f2_make(c.re, c.im);
+                        CycleWatch<float, IterT> watch(re, im, i);
                         while (at_max - i >= (IterT)kAtChunk) { // i <= at_max always; `i + chunk` could wrap for u32 counts near 2^32
                             const float re0 = re, im0 = im;
                             float worst = 0.0f;
@@ -237,9 +279,11 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                                 break;
                             }
                             i += kAtChunk;
+                            if (cycle_watch) watch.after_chunk(re, im, i, at_max, at_skipped);
                         }
                     } else {
                         const M s_im = s + s;
+                        CycleWatch<M, IterT> watch(re, im, i);
                         while (at_max - i >= (IterT)kAtChunk) {
                             const M re0 = re, im0 = im;
                             M worst = M(0);
@@ -258,6 +302,7 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                                 break;
                             }
                             i += kAtChunk;
+                            if (cycle_watch) watch.after_chunk(re, im, i, at_max, at_skipped);
                         }
                     }
                 };
@@ -296,7 +341,7 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
             z = add(z2, c);
             }
         }
-        if (Count) steps_at += i;
+        if (Count) steps_at += i - at_skipped;
         dz = mul(z, A.at.InvZCoeff);
         reduce(dz);
         iter = i * A.at.StepLength;

@@ -260,6 +260,15 @@ class GPURenderer:
         """A/B switch: AT shortcut of the HDRx32 LAv2 path in its own launch (default) or fused (same results)."""
         return int(self._lib.fs_set_split_at(self._h, int(enable)))
 
+    def SetAtCycleDetection(self, enable: bool = True) -> int:
+        """A/B switch of the AT shortcut: skip whole periods once the passes repeat exactly (default) or execute every
+        pass like the reference (same results)."""
+        return int(self._lib.fs_set_at_cycle_detection(self._h, int(enable)))
+
+    def SetPoolKernel(self, enable: bool = True) -> int:
+        """A/B switch of the HDRx32 LAv2 path: lane-refill kernel (default) or one tile per warp (same results)."""
+        return int(self._lib.fs_set_pool_kernel(self._h, int(enable)))
+
     def DeviceIterBuffer(self) -> int:
         return int(self._lib.fs_device_iter_buffer(self._h) or 0)
 

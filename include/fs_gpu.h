@@ -193,6 +193,14 @@ uint32_t fs_set_scaled_steps(fs_renderer *r, int32_t enable);
 /* HDRx32 LAv2 with an AT block: 1 = the AT shortcut runs in its own launch ahead of the LA/perturbation launch;
  * 0 (default) = one fused launch as in the reference.  Results are identical; the fused form measured faster. */
 uint32_t fs_set_split_at(fs_renderer *r, int32_t enable);
+/* AT shortcut of the LAv2 kernels (float+exponent types): 1 (default) = a pixel whose AT passes have entered an exactly
+ * periodic sequence of states (interior pixels) skips whole periods instead of executing them; 0 = every pass of
+ * ATInfo::PerformAT is executed, as the reference does.  Results are identical bit for bit. */
+uint32_t fs_set_at_cycle_detection(fs_renderer *r, int32_t enable);
+/* HDRx32 LAv2: 1 (default) = the lane-refill kernel (every warp keeps pools of pixels waiting for the LA walk and for
+ * perturbation steps and refills idle lanes from them, fs_lav2_pool.cuh); 0 = one 8x4 tile per warp from start to
+ * finish.  Results are identical.  A/B switch for tests and profiling. */
+uint32_t fs_set_pool_kernel(fs_renderer *r, int32_t enable);
 /* Device pointer of the iteration buffer (for NCCL gather by the host plumbing). */
 void *fs_device_iter_buffer(fs_renderer *r);
 /* Number of kernels this renderer has launched so far. */
