@@ -76,6 +76,7 @@ struct OrbitDev {
 
 struct LaDev {
     DeviceBlob las, stages;
+    DeviceBlob las2, stages2; // HDRx32 / 32-bit counts: step-shaped records of fs_la_step2.cuh, derived on the device
     uint64_t num_las = 0, num_stages = 0, stage_count = 0;
     int use_at = 0, is_valid = 0;
     int numeric = -1;
@@ -118,6 +119,7 @@ struct fs_renderer {
                             // measured slower than the fused launch (View 14: 9.7 vs 8.5 ms), kept as an A/B switch
     DeviceBlob at_state;    // float4 per iteration-buffer cell, allocated on first use
     bool at_cycle = true;   // AT shortcut: cycle detection (fs_lav2.cuh CycleWatch); FS_AT_CYCLE=0 / fs_set_at_cycle_detection executes every pass
+    bool use_la2 = true;    // HDRx32 / 32-bit counts: LA walk on step-shaped records (fs_la_step2.cuh); FS_LA_STEP2=0: reference-shaped records
     bool use_pool = false;  // HDRx32 LAv2: the lane-refill kernel of fs_lav2_pool.cuh (FS_LAV2_POOL=0 / fs_set_pool_kernel: one tile per warp)
     bool use_scaled = true; // HDRx32: scaled plain-float chunks (fs_scaled_loop.cuh); off = pure float+exponent loop
     OrbitDev orbit1, orbit2;
@@ -187,6 +189,8 @@ void reset_perturb(fs_renderer *r) {
     r->orbit2 = OrbitDev{};
     free_blob(r, r->la.las);
     free_blob(r, r->la.stages);
+    free_blob(r, r->la.las2);
+    free_blob(r, r->la.stages2);
     r->la = LaDev{};
 }
 
@@ -359,6 +363,38 @@ __global__ void __launch_bounds__(256) la_repack_kernel(const WireLA<Num, IterT>
     }
 }
 
+// LaRec[] -> la2::Rec[] (fs_la_step2.cuh): 2*Ref's exponent, the next record's Ref, threshold beside the operands.
+// A record whose LAThreshold mantissa is not in [1, 2) (never produced by the reference's builder: thresholds are
+// reduced, LAInfoDeep.h:109-502) gets Ref = NaN, which makes la2::step refuse every step on it.
+__global__ void __launch_bounds__(256) la2_pack_kernel(const LaRec<NumHdr<float>, uint32_t> *las, la2::Rec *out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const LaRec<NumHdr<float>, uint32_t> a = las[i];
+        la2::Rec d;
+        const long long th_key = (long long)a.LAThreshold.e * (1ll << 23) + (long long)(__float_as_uint(a.LAThreshold.m) & 0x007fffffu);
+        d.ref_re = a.Ref.re; d.ref_im = a.Ref.im; d.ref_e2 = imax(a.Ref.e + 1, MIN_BIG); d.th_lo = (uint32_t)th_key;
+        d.zc_re = a.ZCoeff.re; d.zc_im = a.ZCoeff.im; d.zc_e = a.ZCoeff.e; d.th_hi = (int32_t)(th_key >> 32);
+        d.cc_re = a.CCoeff.re; d.cc_im = a.CCoeff.im; d.cc_e = a.CCoeff.e; d.step = a.StepLength;
+        d.nx_re = 0.0f; d.nx_im = 0.0f; d.nx_e = MIN_BIG; d.next = a.NextStageLAIndex;
+        if (i + 1 < n) {
+            const HdrC<float> nx = las[i + 1].Ref;
+            d.nx_re = nx.re; d.nx_im = nx.im; d.nx_e = nx.e;
+        } else {
+            d.ref_re = __uint_as_float(0x7fc00000u); // no following record to read: refuse
+        }
+        if (!(a.LAThreshold.m >= 1.0f && a.LAThreshold.m < 2.0f)) d.ref_re = __uint_as_float(0x7fc00000u);
+        out[i] = d;
+    }
+}
+__global__ void __launch_bounds__(256) la2_stage_kernel(const LaRec<NumHdr<float>, uint32_t> *las, uint64_t n_las,
+                                                        const StageRec<uint32_t> *stages, uint4 *out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const StageRec<uint32_t> s = stages[i];
+        Hdr<float> thc = hdr_zero<float>();
+        if (s.LAIndex < n_las) thc = las[s.LAIndex].LAThresholdC;
+        out[i] = make_uint4(s.LAIndex, s.MacroItCount, __float_as_uint(thc.m), (uint32_t)thc.e);
+    }
+}
+
 template <class Num, class IterT> uint32_t upload_la_typed(fs_renderer *r, const fs_la_reference *src) {
     using W = WireLA<Num, IterT>;
     using D = LaRec<Num, IterT>;
@@ -382,6 +418,19 @@ template <class Num, class IterT> uint32_t upload_la_typed(fs_renderer *r, const
     if (src->num_stages) {
         err = cudaMemcpyAsync(la.stages.ptr, src->stages, src->num_stages * sizeof(StageRec<IterT>), cudaMemcpyHostToDevice, r->compute);
         if (err != cudaSuccess) return err;
+    }
+    if constexpr (std::is_same<Num, NumHdr<float>>::value && sizeof(IterT) == 4) {
+        if (n && src->num_stages) {
+            err = alloc_table(r, la.las2, n * sizeof(la2::Rec));
+            if (err != cudaSuccess) return err;
+            err = alloc_table(r, la.stages2, src->num_stages * sizeof(uint4));
+            if (err != cudaSuccess) return err;
+            const unsigned int grid = (unsigned int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+            la2_pack_kernel<<<grid, 256, 0, r->compute>>>(static_cast<const D *>(la.las.ptr), static_cast<la2::Rec *>(la.las2.ptr), n);
+            la2_stage_kernel<<<(unsigned int)((src->num_stages + 255) / 256), 256, 0, r->compute>>>(
+                static_cast<const D *>(la.las.ptr), n, static_cast<const StageRec<IterT> *>(la.stages.ptr),
+                static_cast<uint4 *>(la.stages2.ptr), src->num_stages);
+        }
     }
     AtDev<Num, IterT> at;
     memset(&at, 0, sizeof(at));
@@ -419,6 +468,8 @@ template <class F> uint32_t dispatch_num_iter(int numeric, uint32_t iter_bytes, 
 uint32_t upload_la(fs_renderer *r, int numeric, uint32_t iter_bytes, const fs_la_reference *src) {
     free_blob(r, r->la.las);
     free_blob(r, r->la.stages);
+    free_blob(r, r->la.las2);
+    free_blob(r, r->la.stages2);
     r->la = LaDev{};
     const uint32_t rc = dispatch_num_iter(numeric, iter_bytes, [&](auto num, auto it) -> uint32_t {
         return upload_la_typed<decltype(num), decltype(it)>(r, src);
@@ -525,6 +576,8 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
         A.las = static_cast<const LaRec<Num, IterT> *>(r->la.las.ptr);
         A.stages = static_cast<const StageRec<IterT> *>(r->la.stages.ptr);
         memcpy(&A.at, r->la.at, sizeof(A.at));
+        A.las2 = r->use_la2 ? r->la.las2.ptr : nullptr;
+        A.stages2 = r->la.stages2.ptr;
         A.la_stage_count = (IterT)r->la.stage_count;
         A.la_valid = r->la.is_valid;
         A.use_at = r->la.use_at;
@@ -870,6 +923,7 @@ fs_renderer *fs_create(int32_t device) {
         if (const char *e = getenv("FS_SCALED_STEPS")) r->use_scaled = atoi(e) != 0;
         if (const char *e = getenv("FS_LAV2_POOL")) r->use_pool = atoi(e) != 0;
         if (const char *e = getenv("FS_AT_CYCLE")) r->at_cycle = atoi(e) != 0;
+        if (const char *e = getenv("FS_LA_STEP2")) r->use_la2 = atoi(e) != 0;
     }
     return r;
 }
@@ -1402,6 +1456,12 @@ uint32_t fs_debug_pool_counters(uint64_t *out16) {
 uint32_t fs_set_at_cycle_detection(fs_renderer *r, int32_t enable) {
     if (!r) return FS_ERROR_UNSUPPORTED;
     r->at_cycle = enable != 0;
+    return 0;
+}
+
+uint32_t fs_set_la_step2(fs_renderer *r, int32_t enable) {
+    if (!r) return FS_ERROR_UNSUPPORTED;
+    r->use_la2 = enable != 0;
     return 0;
 }
 

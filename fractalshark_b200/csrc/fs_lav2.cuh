@@ -16,6 +16,7 @@
 #include "fs_perturb_loop.cuh"
 #include "fs_at_fast.cuh"
 #include "fs_la_fast.cuh"
+#include "fs_la_step2.cuh"
 
 #ifndef FS_AT_PACKED
 #define FS_AT_PACKED 1
@@ -29,6 +30,17 @@
 #ifndef FS_AT_CYCLE
 // Cycle detection in the AT shortcut (1 = on): see lav2_at.
 #define FS_AT_CYCLE 1
+#endif
+#ifndef FS_LA_STEP2
+// HDRx32 with 32-bit iteration counts: 1 (default) = the LA walk on step-shaped records (fs_la_step2.cuh), 0 = the
+// generic walk below on reference-shaped records.  Both bit-exact (GPU parity suite).
+#define FS_LA_STEP2 1
+#endif
+#ifndef FS_LA2_EARLY_LOADS
+#define FS_LA2_EARLY_LOADS 1
+#endif
+#ifndef FS_LA2_PREFETCH
+#define FS_LA2_PREFETCH 0
 #endif
 #ifndef FS_LA_FAST
 // HDRx32: 1 = flattened LA walk with the select-free step of fs_la_fast.cuh, 0 (default) = the nested walk on the
@@ -97,6 +109,8 @@ template <class Num, class IterT> struct Lav2Args {
     TileQueue queue;
     unsigned long long *step_counter; // optional: executed perturbation/LA/AT steps (bench roofline)
     float4 *at_state;                 // HDRx32 two-launch form: per-pixel AT result {dz.re, dz.im, dz.e}; iter sits in `out`
+    const void *las2;                 // HDRx32 / 32-bit counts: la2::Rec[] (fs_la_step2.cuh), nullptr = not built
+    const void *stages2;              // ... and la2 stage records {LAIndex, MacroItCount, LAThresholdC.m, LAThresholdC.e}
     int at_cycle;                     // 1: cycle detection in the AT shortcut (CycleWatch), 0: every pass is executed
     IterT *sink;                      // optional mapped host copy of `out` (fs_set_result_sink): finished pixels stream out over PCIe
 };
@@ -493,6 +507,82 @@ FS_D void lav2_stages_hdr32(const Lav2Args<NumHdr<float>, IterT> &A, const HdrC<
     }
 }
 
+// ---- LA stages of one pixel, HDRx32 / 32-bit counts, on la2 records (fs_la_step2.cuh): the walk of lav2_stages above ----
+// The reference-shaped step for what la2::step refuses; reads the reference-layout record.  Out of line (rare).
+__device__ __noinline__ void la_step_refused(const LaRec<NumHdr<float>, uint32_t> *recp, HdrC<float> dz, HdrC<float> dc,
+                                             la2::Out &o) {
+    const LaRec<NumHdr<float>, uint32_t> rec = ldg_rec(recp);
+    HdrC<float> ndz = dz, z = dz;
+    bool unusable, rebase;
+    la_step_as_written(rec.Ref, rec.ZCoeff, rec.CCoeff, rec.LAThreshold, recp[1].Ref, dz, dc, ndz, z, unusable, rebase);
+    o.unusable = unusable;
+    o.rebase = rebase;
+    o.dre = ndz.re; o.dim = ndz.im; o.de = ndz.e;
+    o.zre = z.re; o.zim = z.im; o.ze = z.e;
+}
+
+template <bool Count>
+FS_D void lav2_stages_v2(const Lav2Args<NumHdr<float>, uint32_t> &A, const HdrC<float> dc, HdrC<float> &dz,
+                         uint32_t &RefIteration, uint32_t &iter, unsigned long long &steps) {
+    const uint4 *__restrict__ recs = reinterpret_cast<const uint4 *>(A.las2);
+    const uint4 *__restrict__ stages = reinterpret_cast<const uint4 *>(A.stages2);
+    const Hdr<float> dcn = cheb(dc);
+    uint32_t stage = A.la_valid ? A.la_stage_count : 0;
+    while (stage > 0) {
+        stage--;
+        const uint4 sr = __ldg(stages + stage); // {LAIndex, MacroItCount, LAThresholdC.m, LAThresholdC.e}
+        // isLAStageInvalid  GPU_LAReference.h:241-255
+        if (ge_pr(dcn, hdr_make<float>((int)sr.w, __uint_as_float(sr.z)))) continue;
+        const uint32_t LAIndex = sr.x, MacroItCount = sr.y;
+        uint32_t j = RefIteration;
+        while (iter < A.n_iterations) {
+            // getLA  GPU_LAReference.h:271-303
+            const uint4 *rp = recs + 4 * (size_t)(LAIndex + j);
+#if FS_LA2_EARLY_LOADS
+            // all four quarters are requested before anything is tested (the compiler otherwise sinks the second one
+            // below the first branch of the step and a trip pays two dependent load latencies)
+            uint4 q0, q1, q2, q3;
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(rp));
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(rp));
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w) : "l"(rp));
+            asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+48];" : "=r"(q3.x), "=r"(q3.y), "=r"(q3.z), "=r"(q3.w) : "l"(rp));
+#else
+            const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+#endif
+#if FS_LA2_PREFETCH
+            // the next trip reads the following record unless this one rebases or leaves the stage
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 4));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 6));
+#endif
+            const uint32_t l = q2.w;
+            la2::Out o;
+            o.unusable = true;
+            o.rebase = false;
+            if (iter + l <= A.n_iterations) {
+                if (!la2::step(q0, q1, q2, q3, dz.re, dz.im, dz.e, dc.re, dc.im, dc.e, o)) {
+                    // results come back through a local of this branch only: `o` stays in registers
+                    la2::Out slow;
+                    la_step_refused(A.las + (LAIndex + j), dz, dc, slow);
+                    o = slow;
+                }
+            }
+            if (o.unusable) {
+                RefIteration = q3.w;
+                break;
+            }
+            iter += l;
+            if (Count) steps++;
+            j++;
+            const bool rb = o.rebase || j >= MacroItCount;
+            dz.re = rb ? o.zre : o.dre;
+            dz.im = rb ? o.zim : o.dim;
+            dz.e = rb ? o.ze : o.de;
+            j = rb ? 0u : j;
+        }
+        if (iter >= A.n_iterations) break;
+    }
+}
+
 template <class Num, class IterT, Lav2Mode Mode, bool Count, AtPhase Phase = AtPhase::Fused>
 __global__ void FS_LAV2_BOUNDS(Num) lav2_kernel(const Lav2Args<Num, IterT> A) {
     using Real = typename Num::Real;
@@ -547,7 +637,10 @@ __global__ void FS_LAV2_BOUNDS(Num) lav2_kernel(const Lav2Args<Num, IterT> A) {
                 } else {
                     lav2_at<Num, IterT, Count>(A, dc, dz, iter, steps_at);
                 }
-                if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4 && FS_LA_FAST)
+                if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4 && sizeof(IterT) == 4 && FS_LA_STEP2) {
+                    if (A.las2 != nullptr) lav2_stages_v2<Count>(A, dc, dz, RefIteration, iter, steps_la);
+                    else lav2_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps_la);
+                } else if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4 && FS_LA_FAST)
                     lav2_stages_hdr32<IterT, Count>(A, dc, dz, RefIteration, iter, steps_la);
                 else
                     lav2_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, steps_la);

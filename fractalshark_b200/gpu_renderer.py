@@ -265,6 +265,10 @@ class GPURenderer:
         pass like the reference (same results)."""
         return int(self._lib.fs_set_at_cycle_detection(self._h, int(enable)))
 
+    def SetLaStep2(self, enable: bool = True) -> int:
+        """A/B switch of the HDRx32 / 32-bit LA walk: step-shaped records (default) or reference-shaped (same results)."""
+        return int(self._lib.fs_set_la_step2(self._h, int(enable)))
+
     def SetPoolKernel(self, enable: bool = True) -> int:
         """A/B switch of the HDRx32 LAv2 path: lane-refill kernel (default) or one tile per warp (same results)."""
         return int(self._lib.fs_set_pool_kernel(self._h, int(enable)))

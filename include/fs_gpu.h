@@ -197,9 +197,12 @@ uint32_t fs_set_split_at(fs_renderer *r, int32_t enable);
  * periodic sequence of states (interior pixels) skips whole periods instead of executing them; 0 = every pass of
  * ATInfo::PerformAT is executed, as the reference does.  Results are identical bit for bit. */
 uint32_t fs_set_at_cycle_detection(fs_renderer *r, int32_t enable);
-/* HDRx32 LAv2: 1 (default) = the lane-refill kernel (every warp keeps pools of pixels waiting for the LA walk and for
- * perturbation steps and refills idle lanes from them, fs_lav2_pool.cuh); 0 = one 8x4 tile per warp from start to
- * finish.  Results are identical.  A/B switch for tests and profiling. */
+/* HDRx32 LAv2 with 32-bit iteration counts: 1 (default) = the LA walk runs on step-shaped records derived on the device
+ * at upload (fs_la_step2.cuh); 0 = on the reference-shaped records.  Results are identical bit for bit. */
+uint32_t fs_set_la_step2(fs_renderer *r, int32_t enable);
+/* HDRx32 LAv2: 1 = the lane-refill kernel (every warp keeps pools of pixels waiting for the LA walk and for
+ * perturbation steps and refills idle lanes from them, fs_lav2_pool.cuh); 0 (default: measured faster) = one 8x4 tile
+ * per warp from start to finish.  Results are identical.  A/B switch for tests and profiling. */
 uint32_t fs_set_pool_kernel(fs_renderer *r, int32_t enable);
 /* Device pointer of the iteration buffer (for NCCL gather by the host plumbing). */
 void *fs_device_iter_buffer(fs_renderer *r);

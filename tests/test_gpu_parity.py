@@ -268,6 +268,80 @@ def test_split_and_fused_at_launches_agree():
         np.testing.assert_array_equal(outs[0], outs[1])
 
 
+def _render_lav2(view_id, w, h, alg, n_iter, iter_bytes, switches, count=False):
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, alg, n_iter, iter_bytes)
+    r = GPURenderer()
+    for name, value in switches.items():
+        assert getattr(r, name)(value) == 0
+    assert r.InitializeMemory(w, h, 1, iter_bytes=iter_bytes) == 0
+    assert r.InitializePerturb(1, orbit, 0, None, la) == 0
+    if count:
+        assert r.EnableStepCounter(True) == 0
+    r.ClearMemory()
+    assert r.RenderPerturbLAv2(alg, coords, n) == 0
+    rc, it, _, red = r.RenderCurrent(n)
+    assert rc == 0
+    steps = r.ReadStepCounters() if count else None
+    r.close()
+    return it.copy(), red, steps
+
+
+@pytest.mark.parametrize("view_id,w,h,alg,n_iter,iter_bytes", [
+    (14, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None, 4),   # interior pixels: 18,402 AT passes each in the reference
+    (14, 960, 540, A.GpuHDRx32PerturbedLAv2LAO, None, 8),
+    (14, 960, 540, A.GpuHDRx64PerturbedLAv2, None, 4),     # binary64 mantissa: the unpacked form of the loop
+    (5, 960, 540, A.GpuHDRx32PerturbedLAv2, None, 4),
+    (19, 960, 540, A.GpuHDRx32PerturbedLAv2, None, 4),
+    (100, 640, 360, A.GpuHDRx32PerturbedLAv2, None, 4),
+])
+def test_at_cycle_detection_skips_passes_not_results(view_id, w, h, alg, n_iter, iter_bytes):
+    """The AT shortcut with cycle detection (default) gives the frame of the loop that executes every pass of
+    ATInfo::PerformAT, and never executes more passes than it."""
+    on, red_on, st_on = _render_lav2(view_id, w, h, alg, n_iter, iter_bytes, {"SetAtCycleDetection": True}, count=True)
+    off, red_off, st_off = _render_lav2(view_id, w, h, alg, n_iter, iter_bytes, {"SetAtCycleDetection": False}, count=True)
+    np.testing.assert_array_equal(on, off)
+    assert red_on == red_off
+    assert st_on["at"] <= st_off["at"]                        # AT passes executed
+    assert st_on["la"] == st_off["la"]                        # identical walk afterwards
+    assert st_on["perturbation"] == st_off["perturbation"]
+    if view_id == 14 and alg == A.GpuHDRx32PerturbedLAv2:
+        assert st_on["at"] * 4 < st_off["at"], "View 14: the interior pixels should settle long before 18,402 passes"
+
+
+@pytest.mark.parametrize("view_id,w,h,alg,n_iter", [
+    (14, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None),
+    (5, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None),
+    (5, 1920, 1080, A.GpuHDRx32PerturbedLAv2LAO, None),
+    (19, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None),
+    (1, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None),
+    (100, 640, 360, A.GpuHDRx32PerturbedLAv2, None),
+    (101, 640, 360, A.GpuHDRx32PerturbedLAv2, None),
+])
+def test_step_shaped_la_records_equal_reference_shaped(view_id, w, h, alg, n_iter):
+    """A/B inside the library: the LA walk on la2 records (fs_la_step2.cuh, default) and on reference-shaped records
+    give the same iteration buffer and execute the same steps."""
+    a, _, st_a = _render_lav2(view_id, w, h, alg, n_iter, 4, {"SetLaStep2": True}, count=True)
+    b, _, st_b = _render_lav2(view_id, w, h, alg, n_iter, 4, {"SetLaStep2": False}, count=True)
+    np.testing.assert_array_equal(a, b)
+    assert st_a == st_b
+
+
+@pytest.mark.parametrize("view_id,w,h,alg,n_iter,iter_bytes", [
+    (14, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None, 4),
+    (5, 960, 540, A.GpuHDRx32PerturbedLAv2, None, 4),
+    (5, 960, 540, A.GpuHDRx32PerturbedLAv2PO, 20000, 4),
+    (5, 960, 540, A.GpuHDRx32PerturbedLAv2LAO, None, 8),
+    (19, 960, 540, A.GpuHDRx32PerturbedLAv2, None, 8),
+    (1, 100, 37, A.GpuHDRx32PerturbedLAv2, None, 4),       # ragged: partial tiles on both edges
+])
+def test_lane_refill_kernel_equals_tile_kernel(view_id, w, h, alg, n_iter, iter_bytes):
+    """A/B inside the library: the lane-refill kernel (fs_lav2_pool.cuh, off by default) gives the tile kernel's frame."""
+    a, red_a, _ = _render_lav2(view_id, w, h, alg, n_iter, iter_bytes, {"SetPoolKernel": True})
+    b, red_b, _ = _render_lav2(view_id, w, h, alg, n_iter, iter_bytes, {"SetPoolKernel": False})
+    np.testing.assert_array_equal(a, b)
+    assert red_a == red_b
+
+
 def test_error_behaviour_matches_reference():
     """Error codes and no-op-before-init behaviour (GPU_Render.cu:322-332, 626-628, 1007-1022)."""
     r = GPURenderer()

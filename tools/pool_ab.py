@@ -35,6 +35,8 @@ def run(view_id, alg, n_iter=None, iter_bytes=4, reps=3, shard=None):
         r = GPURenderer(0)
         if SWITCH == "pool":
             r.SetPoolKernel(bool(pool))
+        elif SWITCH == "la2":
+            r.SetLaStep2(bool(pool))
         else:
             r.SetAtCycleDetection(bool(pool))
         assert r.InitializeMemory(W, H, 1, iter_bytes=iter_bytes) == 0
