@@ -73,12 +73,14 @@ DEFAULT_CONFIGS = ["view14_hdr2x32_lav2", "view19_hdr32_lav2", "view5_hdr32_bla"
 # FP32-pipe thread-instructions the HDRx32 LAv2 kernel ISSUES per step (fs_lav2.cuh / fs_scaled_loop.cuh):
 #   AT pass   FMUL2 (2) + FMUL + FADD + FFMA2 (2) = 6, plus one FADD per 16-pass chunk for the escape test
 #   LA step   3 aligned complex additions (2 FFMA each) + 3 complex products (2 FMUL + 2 FFMA each) + Reduce (2 FMUL) + 2 scalings = 22
+#             (the select-free alignment of fs_la_step2.cuh scales both operands and its range guards add three FADDs: 30 issued;
+#             only the 22 are counted)
 #   perturbation step (scaled plain-float chunk)  2 FFMA + 4 FMUL + 4 FADD + 1 FMUL of the threshold test = 11
 EXECUTED_FP32 = {"at": 6.0 + 1.0 / 16.0, "la": 22.0, "perturbation": 11.0}
 # work per step of the reference formulation (AT pass: rr, ii, rr+ii, rr-ii, re*im, 3 FMA + compare)
 REFERENCE_CREDIT = {"at": 9.0, "la": 22.0, "perturbation": 20.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of lav2_kernel, one `ncu --set full` capture (bytes per launch)
-TRAFFIC = {"view14_hdr32_lav2": (5.47e6 + 0.15e6, "profiles/r2_lav2_view14_summary.md")}
+TRAFFIC = {"view14_hdr32_lav2": (7.67e6 + 3.07e6, "profiles/r2_lav2_view14_summary.md")}
 
 
 def _clock_sampler(stop, samples, gpu_index):
@@ -471,6 +473,20 @@ def main():
     r.EnableStepCounter(False)
     stop.set()
     sampler.join()
+    # the same frame with the AT cycle watch off (every pass of ATInfo::PerformAT executed, as the reference does and as
+    # round 1 of this library did): untimed for `value`, reported inside `roofline` -- it is the configuration the
+    # ">= 50 % of the FP32 issue peak" target of BASELINE.json was written against
+    all_passes = None
+    if lav2 and world == 1:
+        assert r.SetAtCycleDetection(False) == 0
+        step_resident()
+        ms_all = min(step_resident() for _ in range(3))
+        r.EnableStepCounter(True)
+        step_resident()
+        kinds_all = r.ReadStepCounters()
+        r.EnableStepCounter(False)
+        assert r.SetAtCycleDetection(True) == 0
+        all_passes = (ms_all, kinds_all)
 
     rc, iters, _, red = r.RenderCurrent(n_iter)
     assert rc == 0
@@ -633,6 +649,14 @@ def main():
     peaks = {"fp32": GPURenderer.MeasureFp32IssuePeak(local_rank), "fp64": GPURenderer.MeasureFp64IssuePeak(local_rank)}
     if rank == 0:
         roofline = roofline_of(wl, kinds, total_sum, ms_per_step, peaks, world)
+        if all_passes is not None:
+            ra = roofline_of(wl, all_passes[1], total_sum, all_passes[0], peaks, world)
+            roofline["every_at_pass_executed"] = {
+                "ms_per_step": all_passes[0], "value": total_sum / (all_passes[0] * 1e-3),
+                "executed_steps_by_kind": ra.get("executed_steps_by_kind"), "achieved": ra.get("achieved"), "frac": ra.get("frac"),
+                "reference_work_credit_frac": (ra.get("reference_work_credit") or {}).get("frac"),
+                "what": "same frame, same results, AT cycle watch off (fs_set_at_cycle_detection(0)): the kernel executes "
+                        "every AT pass the reference executes"}
         traffic = TRAFFIC.get(args.workload)
         roofline["traffic"] = traffic[0] if traffic else None
         roofline["traffic_source"] = traffic[1] if traffic else None
@@ -640,7 +664,10 @@ def main():
                             "thread-instructions (device step counters x the instructions this kernel issues per step) / kernel "
                             "time / FFMA issue rate measured live by fs_measure_fp32_issue_peak on this GPU (MEASURED_PEAKS.json "
                             "has only HBM/bf16 peaks); reference_work_credit = the same steps at the reference formulation's work "
-                            "per step.")
+                            "per step.  The default build skips the AT passes of pixels whose passes have entered an exact "
+                            "cycle (interior pixels: 97 % of the AT passes of this frame), so `frac` is over far fewer executed "
+                            "FP32 instructions than the reference formulation needs; `every_at_pass_executed` is the same "
+                            "frame with that shortcut off.")
 
         line = {"metric": metric_name(wl), "value": value, "unit": "pixel-iters/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

@@ -119,6 +119,8 @@ struct fs_renderer {
                             // measured slower than the fused launch (View 14: 9.7 vs 8.5 ms), kept as an A/B switch
     DeviceBlob at_state;    // float4 per iteration-buffer cell, allocated on first use
     bool at_cycle = true;   // AT shortcut: cycle detection (fs_lav2.cuh CycleWatch); FS_AT_CYCLE=0 / fs_set_at_cycle_detection executes every pass
+    int probe_passes = 0;    // small shards: AT passes the cost probe runs per tile corner (lav2_probe_kernel); 0 = no probe; FS_PROBE_PASSES
+    DeviceBlob tile_order;   // queue position -> tile ticket, plus two counters behind it
     bool use_la2 = true;    // HDRx32 / 32-bit counts: LA walk on step-shaped records (fs_la_step2.cuh); FS_LA_STEP2=0: reference-shaped records
     bool use_pool = false;  // HDRx32 LAv2: the lane-refill kernel of fs_lav2_pool.cuh (FS_LAV2_POOL=0 / fs_set_pool_kernel: one tile per warp)
     bool use_scaled = true; // HDRx32: scaled plain-float chunks (fs_scaled_loop.cuh); off = pure float+exponent loop
@@ -191,6 +193,7 @@ void reset_perturb(fs_renderer *r) {
     free_blob(r, r->la.stages);
     free_blob(r, r->la.las2);
     free_blob(r, r->la.stages2);
+    free_blob(r, r->tile_order);
     r->la = LaDev{};
 }
 
@@ -506,19 +509,10 @@ template <class K> int resident_ctas(fs_renderer *r, K kernel) {
     return slots > 8 * kDisplaySlots ? slots - kDisplaySlots : slots;
 }
 
-// Grid of the LAv2 kernels.  Full occupancy (4 CTAs/SM for HDRx32) is best while every warp gets many tiles; once a
-// shard is down to a handful of tiles per warp (View 14 at 8 GPUs: 32,400 tiles for 4,736 warps) the launch lasts as
-// long as its slowest warps, and those run faster with fewer co-resident warps competing for the FP32 pipe: 3 CTAs/SM
-// measured 1.035 vs 1.088 ms on that shard, 1.95 vs 1.88 ms on the 4-way shard (13.7 tiles per warp), 7.64 vs 7.30 ms
-// on the whole frame.  Below 8 tiles per warp the grid drops to 3/4 of the occupancy.
-template <class K> int lav2_grid(fs_renderer *r, K kernel) {
-    int per_sm = (resident_ctas(r, kernel) + kDisplaySlots) / r->num_sms;
-    const uint64_t tiles_x = (r->width + 7) / 8;
-    const uint64_t bands = ((r->height + 3) / 4 + r->shard_count - 1 - r->shard_index) / r->shard_count;
-    const uint64_t warps = (uint64_t)per_sm * r->num_sms * 8;
-    if (r->ctas_per_sm_cap == 0 && per_sm >= 4 && tiles_x * bands < 8 * warps) return per_sm * 3 / 4 * r->num_sms;
-    return per_sm * r->num_sms - kDisplaySlots;
-}
+// Grid of the LAv2 kernels: full occupancy.  (Round 1 cut the grid to 3/4 of the occupancy for shards with fewer than 8
+// tiles per resident warp; with the AT cycle watch and the la2 records the full grid is faster there too: View 14 8-way
+// shard 0.699 ms at 4 CTAs/SM, 0.719 at 3, 0.918 at 2; whole frame 4.23 / 4.97 / 6.68 ms.)
+template <class K> int lav2_grid(fs_renderer *r, K kernel) { return resident_ctas(r, kernel); }
 
 // Grid of the lane-refill LAv2 kernel (fs_lav2_pool.cuh): full occupancy with its per-warp pools in shared memory.
 template <class K> int pool_grid(fs_renderer *r, K kernel, size_t smem) {
@@ -643,6 +637,39 @@ uint32_t launch_lav2(fs_renderer *r, int mode, const void *dx, const void *dy, c
         }
     }
     begin_render(r, true);
+    // small shards of the float+exponent binary32 path: cost probe + expensive-tiles-first queue order (lav2_probe_kernel)
+    if constexpr (Num::kHdr && !Num::kDf && sizeof(typename Num::Mant) == 4) {
+        const uint64_t tiles_x = (r->width + 7) / 8;
+        const uint64_t bands = ((r->height + 3) / 4 + r->shard_count - 1 - r->shard_index) / r->shard_count;
+        const uint64_t n_tiles = tiles_x * bands;
+        const uint64_t warps = (uint64_t)resident_ctas(r, lav2_kernel<Num, IterT, Lav2Mode::Full, false>) * 8;
+        const uint64_t at_step = have_la && A.la_valid && A.use_at ? (uint64_t)A.at.StepLength : 0;
+        if (r->probe_passes > 0 && at_step > 0 && (mode == FS_LAV2_FULL || mode == FS_LAV2_LAO) && n_tiles < 16 * warps &&
+            n_tiles <= 64ull * 1024ull && n_iter / at_step > 4ull * (uint64_t)r->probe_passes) {
+            const size_t need = (2 * n_tiles + 2) * sizeof(unsigned int);
+            cudaError_t e = cudaSuccess;
+            if (r->tile_order.bytes < need) {
+                free_blob(r, r->tile_order);
+                e = cudaMallocAsync(&r->tile_order.ptr, need, r->compute);
+                if (e == cudaSuccess) r->tile_order.bytes = need;
+            }
+            if (e == cudaSuccess) {
+                unsigned int *order = static_cast<unsigned int *>(r->tile_order.ptr);
+                unsigned int *heads = order + 2 * n_tiles;
+                cudaMemsetAsync(heads, 0, 2 * sizeof(unsigned int), r->compute);
+                Lav2Args<Num, IterT> P = A;
+                P.n_iterations = (IterT)((uint64_t)r->probe_passes * at_step);
+                P.at_cycle = 1;
+                P.step_counter = nullptr;
+                auto kp = lav2_probe_kernel<IterT>;
+                same_carveout(r, kp);
+                kp<<<(unsigned int)((n_tiles * 4 + 255) / 256), 256, 0, r->compute>>>(P, order, heads);
+                lav2_order_kernel<<<1, 1024, 0, r->compute>>>(order, heads, (unsigned int)n_tiles);
+                r->launches += 2;
+                A.order = order;
+            }
+        }
+    }
 #define FS_LAUNCH_LAV2(MODE)                                                                                           \
     if (count) { auto k = lav2_kernel<Num, IterT, MODE, true>; k<<<lav2_grid(r, k), 256, 0, r->compute>>>(A); }         \
     else { auto k = lav2_kernel<Num, IterT, MODE, false>; k<<<lav2_grid(r, k), 256, 0, r->compute>>>(A); }
@@ -924,6 +951,7 @@ fs_renderer *fs_create(int32_t device) {
         if (const char *e = getenv("FS_LAV2_POOL")) r->use_pool = atoi(e) != 0;
         if (const char *e = getenv("FS_AT_CYCLE")) r->at_cycle = atoi(e) != 0;
         if (const char *e = getenv("FS_LA_STEP2")) r->use_la2 = atoi(e) != 0;
+        if (const char *e = getenv("FS_PROBE_PASSES")) r->probe_passes = atoi(e);
     }
     return r;
 }
@@ -1440,6 +1468,19 @@ uint32_t fs_set_split_at(fs_renderer *r, int32_t enable) {
     return 0;
 }
 
+#ifdef FS_TILE_TIMING
+// development build only: give the LAv2 kernels a buffer of 2 x n_tiles 64-bit words for per-tile {start ns, cycles}
+uint32_t fs_debug_tile_times(void *dev_buffer) {
+    unsigned long long *p = static_cast<unsigned long long *>(dev_buffer);
+    return cudaMemcpyToSymbol(fs::fs_tile_times, &p, sizeof(p));
+}
+uint32_t fs_debug_at_passes(void *dev_buffer) {
+    unsigned int *p = static_cast<unsigned int *>(dev_buffer);
+    unsigned int zero = 0;
+    cudaMemcpyToSymbol(fs::fs_at_passes_n, &zero, sizeof(zero));
+    return cudaMemcpyToSymbol(fs::fs_at_passes, &p, sizeof(p));
+}
+#endif
 #ifdef FS_POOL_DEBUG
 // development build only: read and clear the session counters of fs_lav2_pool.cuh
 uint32_t fs_debug_pool_counters(uint64_t *out16) {

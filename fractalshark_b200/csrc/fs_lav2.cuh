@@ -64,6 +64,14 @@
 
 namespace fs {
 
+#ifdef FS_TILE_TIMING
+// development build only: per-tile {start (globaltimer ns), duration (SM cycles)} of the last lav2_kernel launch, and
+// per-launch-thread executed AT passes (indexed by a running counter: order is irrelevant for the histogram)
+__device__ unsigned long long *fs_tile_times;
+__device__ unsigned int *fs_at_passes;
+__device__ unsigned int fs_at_passes_n;
+#endif
+
 enum class Lav2Mode : int { Full = 1, PO = 2, LAO = 3 }; // RenderAlgorithm.h:12-17
 
 // ---- device-side table records (our own layout; filled by the upload code in fs_capi.cu) ------
@@ -111,6 +119,7 @@ template <class Num, class IterT> struct Lav2Args {
     float4 *at_state;                 // HDRx32 two-launch form: per-pixel AT result {dz.re, dz.im, dz.e}; iter sits in `out`
     const void *las2;                 // HDRx32 / 32-bit counts: la2::Rec[] (fs_la_step2.cuh), nullptr = not built
     const void *stages2;              // ... and la2 stage records {LAIndex, MacroItCount, LAThresholdC.m, LAThresholdC.e}
+    const unsigned int *order;        // optional: queue position -> tile ticket (lav2_probe_kernel: expensive tiles first)
     int at_cycle;                     // 1: cycle detection in the AT shortcut (CycleWatch), 0: every pass is executed
     IterT *sink;                      // optional mapped host copy of `out` (fs_set_result_sink): finished pixels stream out over PCIe
 };
@@ -356,6 +365,13 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
             }
         }
         if (Count) steps_at += i - at_skipped;
+#ifdef FS_TILE_TIMING
+        if (fs_at_passes) {
+            const unsigned int k = atomicAdd(&fs_at_passes_n, 1u);
+            fs_at_passes[2 * (size_t)k] = (unsigned int)(i - at_skipped);
+            fs_at_passes[2 * (size_t)k + 1] = (unsigned int)i;
+        }
+#endif
         dz = mul(z, A.at.InvZCoeff);
         reduce(dz);
         iter = i * A.at.StepLength;
@@ -600,6 +616,16 @@ __global__ void FS_LAV2_BOUNDS(Num) lav2_kernel(const Lav2Args<Num, IterT> A) {
         unsigned int tile;
         if (!next_tile(A.queue, cursor, n_tiles, tile)) break;
 
+#ifdef FS_TILE_TIMING
+        const long long fs_t0 = clock64();
+        unsigned long long fs_g0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(fs_g0));
+#endif
+        if (A.order) {
+            // two lists filled by lav2_probe_kernel, each in ticket (centre-out) order: expensive tiles, then the rest
+            const unsigned int n_first = *(const volatile unsigned int *)(A.order + 2 * (size_t)n_tiles);
+            tile = tile < n_first ? __ldg(A.order + tile) : __ldg(A.order + n_tiles + (tile - n_first));
+        }
         int X, Y;
         tile_origin(tile, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Y);
         X += lane & 7;
@@ -659,6 +685,12 @@ __global__ void FS_LAV2_BOUNDS(Num) lav2_kernel(const Lav2Args<Num, IterT> A) {
             A.out[cell] = iter;
             if (A.sink) A.sink[cell] = iter; // 8 lanes per row: one 32-byte posted write
         }
+#ifdef FS_TILE_TIMING
+        if (lane == 0 && fs_tile_times) {
+            fs_tile_times[2 * (size_t)tile] = fs_g0;                                  // start, ns (global timer)
+            fs_tile_times[2 * (size_t)tile + 1] = (unsigned long long)(clock64() - fs_t0); // duration, SM cycles
+        }
+#endif
     }
 
     if (Count && A.step_counter) {
@@ -673,6 +705,81 @@ __global__ void FS_LAV2_BOUNDS(Num) lav2_kernel(const Lav2Args<Num, IterT> A) {
         if (lane == 0 && steps_at) atomicAdd(A.step_counter + 1, steps_at);
         if (lane == 0 && steps_la) atomicAdd(A.step_counter + 2, steps_la);
     }
+}
+
+// ---- cost probe for small shards --------------------------------------------------------------------------------------
+// Once a GPU's share of the frame is a handful of tiles per resident warp (8 GPUs on View 14: 6.9), the launch lasts as long
+// as its latest-finishing warp, and that is a warp that drew an expensive tile late: the interior pixels next to the set's
+// boundary, whose AT passes settle into a cycle only after thousands of passes or never (View 14: 0.5 % of the pixels
+// run more than 4,096 of the 18,402 passes; such a tile lasts 0.5 ms of a 0.7 ms launch wherever it starts).  This kernel
+// runs the first `A.n_iterations / StepLength` AT passes (the host passes a copy of the arguments with a small limit) of
+// the four corner pixels of every tile of the shard and writes the queue order: tiles with a corner that neither escaped
+// nor cycled within the limit first, the rest behind them.  Results do not depend on the order; the launch time does.
+template <class IterT>
+__global__ void __launch_bounds__(256) lav2_probe_kernel(const Lav2Args<NumHdr<float>, IterT> A, unsigned int *order,
+                                                         unsigned int *heads) {
+    using Num = NumHdr<float>;
+    const int tiles_x = (A.width + 7) >> 3;
+    const int tiles_y = (((A.height + 3) >> 2) - A.shard_index + A.shard_count - 1) / A.shard_count;
+    const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int ticket = t >> 2;
+    const int corner = (int)(t & 3u);
+    bool slow = false;
+    if (ticket < n_tiles) {
+        int X, Y;
+        tile_origin(ticket, tiles_x, tiles_y, A.shard_count, A.shard_index, X, Y);
+        X += (corner & 1) ? 7 : 0;
+        Y += (corner & 2) ? 3 : 0;
+        if (X < A.width && Y < A.height) {
+            const typename Num::Real dcX = Num::delta_x(A.dx, X, A.centerX);
+            const typename Num::Real dcY = Num::delta_y(A.dy, Y, A.centerY);
+            const typename Num::Cplx dc = Num::c_make(dcX, dcY);
+            typename Num::Cplx dz = Num::c_zero();
+            IterT iter = 0;
+            unsigned long long passes = 0;
+            lav2_at<Num, IterT, true>(A, dc, dz, iter, passes);
+            slow = passes >= (unsigned long long)(A.n_iterations / A.at.StepLength);
+        }
+    }
+    // the four corners of a tile sit in adjacent lanes
+    const unsigned int votes = __ballot_sync(0xffffffffu, slow);
+    const bool tile_slow = ((votes >> ((threadIdx.x & 31) & ~3)) & 0xfu) != 0u;
+    // flags live in the second list's space until lav2_order_kernel turns them into the two lists
+    if (corner == 0 && ticket < n_tiles) order[n_tiles + ticket] = tile_slow ? 1u : 0u;
+}
+
+// Stable partition of the tickets by the probe's flag (one CTA; a shard that is probed has a few ten thousand tiles):
+// order[0 .. n_first) = flagged tickets, order[n_tiles .. ) = the others, both ascending, i.e. still centre-out -- warps
+// that run side by side keep working on neighbouring tiles and find each other's LA records and orbit elements in L1.
+__global__ void __launch_bounds__(1024) lav2_order_kernel(unsigned int *order, unsigned int *heads, unsigned int n_tiles) {
+    __shared__ unsigned int sums[1024];
+    const unsigned int per = (n_tiles + 1023u) / 1024u;
+    const unsigned int lo = min(threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+    unsigned int mine = 0;
+    for (unsigned int k = lo; k < hi; k++) mine += order[n_tiles + k];
+    sums[threadIdx.x] = mine;
+    __syncthreads();
+    for (unsigned int o = 1; o < 1024u; o <<= 1) { // inclusive scan
+        const unsigned int v = threadIdx.x >= o ? sums[threadIdx.x - o] : 0u;
+        __syncthreads();
+        sums[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned int before = sums[threadIdx.x] - mine; // flagged tickets below `lo`
+    // the flags share the second list's space: every thread copies its flags out before anyone writes a slot
+    unsigned int local[64];
+    const bool fits = per <= 64u;
+    if (fits) for (unsigned int k = lo; k < hi; k++) local[k - lo] = order[n_tiles + k];
+    __syncthreads();
+    if (fits) {
+        for (unsigned int k = lo; k < hi; k++) {
+            if (local[k - lo]) order[before++] = k;
+            else order[n_tiles + (k - before)] = k;
+        }
+    }
+    if (threadIdx.x == 1023) heads[0] = fits ? sums[1023] : 0u;
+    if (!fits && threadIdx.x == 0) heads[1] = 1u; // caller never asks for more than 64 * 1024 tiles
 }
 
 } // namespace fs
