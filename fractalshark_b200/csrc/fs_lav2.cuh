@@ -241,6 +241,33 @@ template <class M, class IterT> struct CycleWatch {
     }
 };
 
+// The same watch for the general loop (any numeric type): the state is the whole complex number, exponent included.
+FS_D bool same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
+FS_D bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+FS_D bool same_bits(df32 a, df32 b) { return same_bits(a.head, b.head) && same_bits(a.tail, b.tail); }
+template <class M> FS_D bool same_state(Cx<M> a, Cx<M> b) { return same_bits(a.re, b.re) && same_bits(a.im, b.im); }
+template <class M> FS_D bool same_state(HdrC<M> a, HdrC<M> b) { return same_bits(a.re, b.re) && same_bits(a.im, b.im) && a.e == b.e; }
+template <class Cplx, class IterT> struct StateWatch {
+    Cplx saved;
+    IterT at, next;
+    bool armed;
+    FS_D StateWatch(Cplx z, IterT i) : saved(z), at(i), next(i + (IterT)FS_AT_CHUNK), armed(true) {}
+    // called with `i` = passes completed, a multiple of FS_AT_CHUNK
+    FS_D void after_chunk(Cplx z, IterT &i, IterT at_max, IterT &skipped) {
+        if (!armed) return;
+        if (same_state(z, saved)) {
+            const IterT P = i - at;
+            skipped = ((at_max - i) / P) * P;
+            i += skipped;
+            armed = false;
+        } else if (i == next) {
+            saved = z;
+            next = i + (i - at) * 2;
+            at = i;
+        }
+    }
+};
+
 // ---- AT shortcut of one pixel (LAKernel.cuh:66-89, ATInfo.h:128-188) -----------------------------------------------
 template <class Num, class IterT, bool Count>
 FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, typename Num::Cplx &dz, IterT &iter,
@@ -341,7 +368,14 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                 at_done = true;
             }
         }
+        StateWatch<Cplx, IterT> gwatch(z, i);
+        const bool gwatch_on = FS_AT_CYCLE && A.at_cycle && !at_done;
         for (; !at_done && i < at_max; i++) {
+            // every FS_AT_CHUNK passes: has the state been here before?  (see CycleWatch)
+            if (gwatch_on && i != 0 && (i % (IterT)FS_AT_CHUNK) == 0 && gwatch.armed) {
+                gwatch.after_chunk(z, i, at_max, at_skipped);
+                if (!(i < at_max)) break;
+            }
             if constexpr (Num::kDf) {
                 // 2x32: every operation is an explicit rounded sequence, evaluated as written (ATInfo.h:166-183)
                 Real nsq = norm2(z);

@@ -290,6 +290,9 @@ def _render_lav2(view_id, w, h, alg, n_iter, iter_bytes, switches, count=False):
     (14, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None, 4),   # interior pixels: 18,402 AT passes each in the reference
     (14, 960, 540, A.GpuHDRx32PerturbedLAv2LAO, None, 8),
     (14, 960, 540, A.GpuHDRx64PerturbedLAv2, None, 4),     # binary64 mantissa: the unpacked form of the loop
+    (14, 640, 360, A.GpuHDRx2x32PerturbedLAv2, None, 4),   # 2x32 mantissa: the watch on the general loop's whole state
+    (100, 640, 360, A.Gpu1x64PerturbedLAv2, None, 4),
+    (101, 640, 360, A.Gpu2x32PerturbedLAv2, None, 8),
     (5, 960, 540, A.GpuHDRx32PerturbedLAv2, None, 4),
     (19, 960, 540, A.GpuHDRx32PerturbedLAv2, None, 4),
     (100, 640, 360, A.GpuHDRx32PerturbedLAv2, None, 4),
@@ -304,7 +307,7 @@ def test_at_cycle_detection_skips_passes_not_results(view_id, w, h, alg, n_iter,
     assert st_on["at"] <= st_off["at"]                        # AT passes executed
     assert st_on["la"] == st_off["la"]                        # identical walk afterwards
     assert st_on["perturbation"] == st_off["perturbation"]
-    if view_id == 14 and alg == A.GpuHDRx32PerturbedLAv2:
+    if view_id == 14 and alg in (A.GpuHDRx32PerturbedLAv2, A.GpuHDRx2x32PerturbedLAv2):
         assert st_on["at"] * 4 < st_off["at"], "View 14: the interior pixels should settle long before 18,402 passes"
 
 

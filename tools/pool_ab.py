@@ -14,6 +14,7 @@ _orbits = {}
 
 
 def inputs(view_id, alg, n_iter, iter_bytes):
+    global W, H
     p = PRESETS[view_id]
     t = traits(alg)
     v = View(p.min_x, p.min_y, p.max_x, p.max_y, W, H)
@@ -65,6 +66,19 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         SWITCH = sys.argv[1]
     ok = True
+    if SWITCH == "cycle":
+        W, H = 1920, 1080
+        ok &= run(14, A.GpuHDRx2x32PerturbedLAv2)
+        ok &= run(14, A.GpuHDRx64PerturbedLAv2)
+        ok &= run(14, A.GpuHDRx32PerturbedLAv2)
+        ok &= run(19, A.GpuHDRx2x32PerturbedLAv2)
+        ok &= run(100, A.Gpu1x64PerturbedLAv2)
+        ok &= run(101, A.Gpu1x32PerturbedLAv2)
+        ok &= run(101, A.Gpu2x32PerturbedLAv2)
+        ok &= run(100, A.GpuHDRx64PerturbedLAv2)
+        ok &= run(5, A.GpuHDRx2x32PerturbedLAv2)
+        print("ALL IDENTICAL" if ok else "MISMATCH")
+        sys.exit(0 if ok else 1)
     ok &= run(14, A.GpuHDRx32PerturbedLAv2)
     ok &= run(5, A.GpuHDRx32PerturbedLAv2)
     ok &= run(19, A.GpuHDRx32PerturbedLAv2)
