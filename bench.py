@@ -51,6 +51,7 @@ WORKLOADS = {
     "view14_hdr32_lav2": dict(config=3, view=14, alg="GpuHDRx32PerturbedLAv2", w=3840, h=2160),
     "view14_hdr2x32_lav2": dict(config=3, view=14, alg="GpuHDRx2x32PerturbedLAv2", w=3840, h=2160),
     "view19_hdr32_lav2": dict(config=3, view=19, alg="GpuHDRx32PerturbedLAv2", w=3840, h=2160),
+    "view14_hdr32_bla": dict(config=3, view=14, alg="GpuHDRx32PerturbedBLA", w=3840, h=2160),
     # configs[2]: View 5, BLA and LAv2 (+ perturbation only, capped: every counted iteration is an executed step)
     "view5_hdr32_bla": dict(config=2, view=5, alg="GpuHDRx32PerturbedBLA", w=3840, h=2160),
     "view5_hdr32_lav2": dict(config=2, view=5, alg="GpuHDRx32PerturbedLAv2", w=3840, h=2160),
@@ -67,7 +68,7 @@ WORKLOADS = {
     "view30_standin_8k": dict(config=4, view=14, alg="GpuHDRx32PerturbedLAv2", w=7680, h=4320, n_iter=200_000_000),
 }
 HEADLINE = "view14_hdr32_lav2"
-DEFAULT_CONFIGS = ["view14_hdr2x32_lav2", "view19_hdr32_lav2", "view5_hdr32_bla", "view5_hdr32_lav2", "view5_hdr32_lav2_po",
+DEFAULT_CONFIGS = ["view14_hdr2x32_lav2", "view19_hdr32_lav2", "view14_hdr32_bla", "view5_hdr32_bla", "view5_hdr32_lav2", "view5_hdr32_lav2_po",
                    "view0_f32_direct", "view0_f64_direct", "interior_f32_direct", "interior_f64_direct", "view30_standin_8k"]
 
 # FP32-pipe thread-instructions the HDRx32 LAv2 kernel ISSUES per step (fs_lav2.cuh / fs_scaled_loop.cuh):

@@ -51,6 +51,7 @@ template <class Num, class IterT> struct BlaArgs {
     IterT n_iterations;
     TileQueue queue;
     unsigned long long *step_counter;
+    int cycle_watch; // 1: cycle detection at rebase events (RebaseWatch), 0: every period is executed
 };
 
 // device-side repack of one level: wire records -> heads + coefs
@@ -114,6 +115,8 @@ template <class M> FS_D void bla_get_value(const BlaCoef<NumPlain<M>> &b, M &dx,
     dx = fma_(-cy, b.By, t2);
 }
 
+// Cycle detection at rebase events: RebaseWatch (fs_types.cuh) on {dX, dY, the norm kept for the next table lookup}.
+// View 14, 2^31 - 2 iterations against a 116,695-element orbit: an interior pixel runs 18,402 periods in the reference.
 // ---- one pixel, float+exponent types: mandel_1xHDR_float_perturb_bla  BLAKernels.cuh:193-434 ----------------
 template <class Num, class IterT, bool Count>
 FS_D IterT bla_pixel_hdr(const BlaArgs<Num, IterT> &A, int X, int Y, unsigned long long &steps) {
@@ -123,8 +126,13 @@ FS_D IterT bla_pixel_hdr(const BlaArgs<Num, IterT> &A, int X, int Y, unsigned lo
     const Real cY = Num::delta_y(A.dy, Y, A.centerY);
     Real dX = Num::zero(), dY = Num::zero(), dn = Num::zero();
     const IterT count = A.orbit_count;
+    RebaseWatch<Real, IterT, 3> watch(A.cycle_watch != 0);
 
     while (iter < A.n_iterations) {
+        if (Ref == 0 && iter != 0 && watch.armed) {
+            const Real state[3] = {dX, dY, dn};
+            iter += watch.at_rebase(state, iter, A.n_iterations);
+        }
         Real zx, zy;
         OrbitIO<Num>::load(A.orbit, Ref, zx, zy);
         ++Ref;
@@ -180,8 +188,13 @@ FS_D IterT bla_pixel_plain(const BlaArgs<Num, IterT> &A, int X, int Y, unsigned 
     const Real cY = Num::delta_y(A.dy, Y, A.centerY);
     Real dX = 0, dY = 0, dn = 0;
     const IterT count = A.orbit_count;
+    RebaseWatch<Real, IterT, 3> watch(A.cycle_watch != 0);
 
     while (iter < A.n_iterations) {
+        if (Ref == 0 && iter != 0 && watch.armed) {
+            const Real state[3] = {dX, dY, dn};
+            iter += watch.at_rebase(state, iter, A.n_iterations);
+        }
         Real zx, zy;
         bool escaped = false;
         for (;;) {

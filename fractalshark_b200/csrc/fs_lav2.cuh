@@ -36,6 +36,11 @@
 // generic walk below on reference-shaped records.  Both bit-exact (GPU parity suite).
 #define FS_LA_STEP2 1
 #endif
+#ifndef FS_AT_WATCH_EVERY_PASS
+// 1: the cycle watch compares the state with the saved one after every pass (finds a period P as soon as P passes have
+// run since the save), 0: after every chunk of FS_AT_CHUNK passes (finds it once P * 16 / gcd(P, 16) have).
+#define FS_AT_WATCH_EVERY_PASS 0
+#endif
 #ifndef FS_LA2_EARLY_LOADS
 #define FS_LA2_EARLY_LOADS 1
 #endif
@@ -226,6 +231,26 @@ template <class M, class IterT> struct CycleWatch {
     FS_D CycleWatch(M re, M im, IterT i) : sre(re), sim(im), at(i), next(i + (IterT)FS_AT_CHUNK), armed(true) {}
     FS_D static bool same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
     FS_D static bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+    // `seen`: bit u set = the state after pass u + 1 of the chunk just finished (which ended at pass count i) equalled the
+    // saved state.  Any hit gives a period (a multiple of the true one): the lowest bit the shortest.
+    FS_D void after_chunk_seen(M re, M im, IterT &i, IterT at_max, IterT &skipped, unsigned int seen) {
+        if (!armed) return;
+        if (seen != 0u) {
+            const IterT hit = i - (IterT)FS_AT_CHUNK + (IterT)__ffs(seen); // pass count at the first hit
+            const IterT P = hit - at;
+            if (P != 0) {
+                skipped = ((at_max - i) / P) * P;
+                i += skipped;
+                armed = false;
+                return;
+            }
+        }
+        if (i == next) {
+            sre = re; sim = im;
+            next = i + (i - at) * 2;
+            at = i;
+        }
+    }
     FS_D void after_chunk(M re, M im, IterT &i, IterT at_max, IterT &skipped) {
         if (!armed) return;
         if (same_bits(re, sre) && same_bits(im, sim)) {
@@ -314,6 +339,9 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                             const float re0 = re, im0 = im;
                             float worst = 0.0f;
                             f32x2 z2 = f2_make(re, im);
+#if FS_AT_WATCH_EVERY_PASS
+                            unsigned int seen = 0u; // bit u: the state after pass u of this chunk equals the saved one
+#endif
 #pragma unroll
                             for (int u = 0; u < kAtChunk; u++) {
                                 float rr, ii;
@@ -322,6 +350,10 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                                 else if (u == kAtChunk - 1) worst = rr + ii;
                                 z2 = f2_fma(f2_make(rr - ii, re * im), s2, c2);
                                 f2_split(z2, re, im);
+#if FS_AT_WATCH_EVERY_PASS
+                                if (__float_as_uint(re) == __float_as_uint(watch.sre) && __float_as_uint(im) == __float_as_uint(watch.sim))
+                                    seen |= 1u << u;
+#endif
                             }
                             if (!(worst <= thr)) {
                                 re = re0;
@@ -329,7 +361,11 @@ FS_D void lav2_at(const Lav2Args<Num, IterT> &A, const typename Num::Cplx dc, ty
                                 break;
                             }
                             i += kAtChunk;
+#if FS_AT_WATCH_EVERY_PASS
+                            if (cycle_watch) watch.after_chunk_seen(re, im, i, at_max, at_skipped, seen);
+#else
                             if (cycle_watch) watch.after_chunk(re, im, i, at_max, at_skipped);
+#endif
                         }
                     } else {
                         const M s_im = s + s;

@@ -118,6 +118,51 @@ FS_HD double fma_(double a, double b, double c) {
 #endif
 }
 
+// bit-for-bit equality of numbers (cycle watches: a state that repeats exactly)
+FS_HD bool bits_equal(float a, float b) { return f2u(a) == f2u(b); }
+FS_HD bool bits_equal(double a, double b) { return d2u(a) == d2u(b); }
+FS_HD bool bits_equal(df32 a, df32 b) { return bits_equal(a.head, b.head) && bits_equal(a.tail, b.tail); }
+template <class M> FS_HD bool bits_equal(Hdr<M> a, Hdr<M> b) { return bits_equal(a.m, b.m) && a.e == b.e; }
+
+// Cycle watch of the perturbation loops, checked at rebase events (orbit index back to 0).  A pixel inside the set
+// iterates to the limit against a periodic reference orbit; at a rebase the delta (the orbit index being 0) is the whole
+// state of what follows except for the comparisons with the iteration limit, and towards an attracting cycle it settles,
+// in finite precision, into an exactly periodic sequence.  The watch compares the state at every rebase with one saved at
+// an earlier rebase (after 1, 2, 4, 8 ... events: Brent).  On a bit-for-bit match P iterations apart the periods that
+// follow repeat the one just executed -- in which nothing escaped and no step was cut short by the limit -- for as long
+// as a whole period fits below the limit: a step attempted at offset o with length l passed `iter + l < n` and o + l <= P,
+// so k = (n - iter - 1) / P further periods are identical.  The caller adds k * P to the iteration count and runs the
+// remainder (at most P iterations) the ordinary way: the reference's count, bit for bit, without the periods between.
+// Used by the BLA kernels (fs_bla.cuh; View 14: 3.1x).  Measured and not kept in the perturbation loop of the LAv2 kernels
+// (fs_perturb_loop.cuh): what is left for that loop on views 5 / 14 / 19 is not periodic at its rebase events, and the watch
+// cost 2 % there.
+template <class Real, class IterT, int N> struct RebaseWatch {
+    Real saved[N];
+    IterT at;
+    unsigned int events, next;
+    bool have, armed;
+    FS_HD RebaseWatch(bool on) : at(0), events(0), next(1), have(false), armed(on) {}
+    // s = the N numbers of the state; returns the iterations to skip (0 = none)
+    FS_HD IterT at_rebase(const Real (&s)[N], IterT iter, IterT n_iterations) {
+        if (!armed) return 0;
+        bool same = have;
+        for (int k = 0; k < N; k++) same = same && bits_equal(s[k], saved[k]);
+        if (same) {
+            armed = false;
+            const IterT P = iter - at;
+            return (P != 0 && n_iterations > iter) ? ((n_iterations - iter - 1) / P) * P : (IterT)0;
+        }
+        if (++events == next) {
+            for (int k = 0; k < N; k++) saved[k] = s[k];
+            at = iter;
+            next <<= 1;
+            have = true;
+            if (next == 0u) armed = false;
+        }
+        return 0;
+    }
+};
+
 // Tile order of the persistent work queue: centre-out in both directions (k = 0, 1, 2, 3 ... -> mid, mid+1, mid-1,
 // mid+2 ...).  Deep views are centred on the feature whose reference orbit they use, so the expensive tiles
 // (interior, long orbits) sit in the middle of the frame: handing them out first leaves the cheap border tiles for

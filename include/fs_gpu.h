@@ -193,9 +193,10 @@ uint32_t fs_set_scaled_steps(fs_renderer *r, int32_t enable);
 /* HDRx32 LAv2 with an AT block: 1 = the AT shortcut runs in its own launch ahead of the LA/perturbation launch;
  * 0 (default) = one fused launch as in the reference.  Results are identical; the fused form measured faster. */
 uint32_t fs_set_split_at(fs_renderer *r, int32_t enable);
-/* AT shortcut of the LAv2 kernels (float+exponent types): 1 (default) = a pixel whose AT passes have entered an exactly
- * periodic sequence of states (interior pixels) skips whole periods instead of executing them; 0 = every pass of
- * ATInfo::PerformAT is executed, as the reference does.  Results are identical bit for bit. */
+/* Cycle detection: 1 (default) = a pixel whose state has entered an exactly periodic sequence (interior pixels) skips
+ * whole periods instead of executing them -- in the AT shortcut of the LAv2 kernels (state after every 16 passes of
+ * ATInfo::PerformAT) and in the BLA kernels (state at rebase events); 0 = every pass / period is executed, as the
+ * reference does.  Results are identical bit for bit. */
 uint32_t fs_set_at_cycle_detection(fs_renderer *r, int32_t enable);
 /* HDRx32 LAv2 with 32-bit iteration counts: 1 (default) = the LA walk runs on step-shaped records derived on the device
  * at upload (fs_la_step2.cuh); 0 = on the reference-shaped records.  Results are identical bit for bit. */

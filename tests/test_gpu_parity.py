@@ -311,6 +311,37 @@ def test_at_cycle_detection_skips_passes_not_results(view_id, w, h, alg, n_iter,
         assert st_on["at"] * 4 < st_off["at"], "View 14: the interior pixels should settle long before 18,402 passes"
 
 
+@pytest.mark.parametrize("view_id,w,h,alg,iter_bytes", [
+    (14, 640, 360, A.GpuHDRx32PerturbedBLA, 4),    # interior pixels: 18,402 periods of the reference orbit each
+    (14, 320, 180, A.GpuHDRx64PerturbedBLA, 8),
+    (5, 960, 540, A.GpuHDRx32PerturbedBLA, 4),
+    (1, 960, 540, A.GpuHDRx32PerturbedBLA, 4),
+    (100, 640, 360, A.Gpu1x64PerturbedBLA, 4),
+])
+def test_bla_cycle_detection_skips_periods_not_results(view_id, w, h, alg, iter_bytes):
+    """The BLA kernels with cycle detection at rebase events (default) give the frame of the loop that executes every
+    period, and never execute more steps than it."""
+    _, coords, orbit, table, n = cases.make_inputs(view_id, w, h, alg, None, iter_bytes)
+    outs, steps = [], []
+    for on in (True, False):
+        r = GPURenderer()
+        assert r.SetAtCycleDetection(on) == 0
+        assert r.InitializeMemory(w, h, 1, iter_bytes=iter_bytes) == 0
+        assert r.EnableStepCounter(True) == 0
+        r.ClearMemory()
+        assert r.RenderPerturbBLA(alg, orbit, table, coords, n) == 0
+        rc, it, _, red = r.RenderCurrent(n)
+        assert rc == 0
+        outs.append((it.copy(), red))
+        steps.append(r.ReadStepCounter())
+        r.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]
+    assert steps[0] <= steps[1]
+    if view_id == 14:
+        assert steps[0] * 2 < steps[1], "View 14: interior pixels should settle long before 18,402 periods"
+
+
 @pytest.mark.parametrize("view_id,w,h,alg,n_iter", [
     (14, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None),
     (5, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None),

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from fractalshark_b200 import RenderAlgorithm, traits
 from fractalshark_b200.gpu_renderer import GPURenderer
-from fractalshark_b200.host_inputs import View, Orbit, LaTable
+from fractalshark_b200.host_inputs import View, Orbit, LaTable, BlaTable
 from fractalshark_b200.views import PRESETS
 
 W, H = 3840, 2160
@@ -18,10 +18,10 @@ def inputs(view_id, alg, n_iter, iter_bytes):
     p = PRESETS[view_id]
     t = traits(alg)
     v = View(p.min_x, p.min_y, p.max_x, p.max_y, W, H)
-    key = (view_id, n_iter, iter_bytes, int(t.numeric))
+    key = (view_id, n_iter, iter_bytes, int(t.numeric), t.family)
     if key not in _orbits:
         orbit = Orbit(v, t.numeric, n_iter, True)
-        _orbits[key] = (orbit, LaTable(orbit, iter_bytes))
+        _orbits[key] = (orbit, LaTable(orbit, iter_bytes) if t.family == "lav2" else BlaTable(orbit))
     return v.coords(t.numeric), *_orbits[key]
 
 
@@ -43,11 +43,13 @@ def run(view_id, alg, n_iter=None, iter_bytes=4, reps=3, shard=None):
         assert r.InitializeMemory(W, H, 1, iter_bytes=iter_bytes) == 0
         if shard:
             r.SetShard(*shard)
-        assert r.InitializePerturb(1, orbit, 0, None, la) == 0
+        fam = traits(alg).family
+        if fam == "lav2":
+            assert r.InitializePerturb(1, orbit, 0, None, la) == 0
         best = 1e30
         for _ in range(reps):
             r.ClearMemory()
-            rc = r.RenderPerturbLAv2(alg, coords, n_iter)
+            rc = r.RenderPerturbLAv2(alg, coords, n_iter) if fam == "lav2" else r.RenderPerturbBLA(alg, orbit, la, coords, n_iter)
             assert rc == 0, rc
             assert r.SyncComputeStream() == 0
             best = min(best, r.LastRenderMs())
@@ -66,8 +68,24 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         SWITCH = sys.argv[1]
     ok = True
+    if SWITCH == "bla":
+        SWITCH = "cycle"
+        W, H = 1920, 1080
+        ok &= run(14, A.GpuHDRx32PerturbedBLA, reps=2)
+        ok &= run(5, A.GpuHDRx32PerturbedBLA, reps=2)
+        ok &= run(1, A.GpuHDRx32PerturbedBLA, reps=2)
+        ok &= run(14, A.GpuHDRx64PerturbedBLA, reps=2)
+        ok &= run(100, A.Gpu1x64PerturbedBLA, reps=2)
+        ok &= run(5, A.GpuHDRx32PerturbedBLA, iter_bytes=8, reps=2)
+        print("ALL IDENTICAL" if ok else "MISMATCH")
+        sys.exit(0 if ok else 1)
     if SWITCH == "cycle":
         W, H = 1920, 1080
+        ok &= run(5, A.GpuHDRx32PerturbedLAv2)
+        ok &= run(19, A.GpuHDRx32PerturbedLAv2)
+        ok &= run(5, A.GpuHDRx32PerturbedLAv2PO, 50000)
+        ok &= run(1, A.GpuHDRx32PerturbedLAv2)
+        ok &= run(5, A.GpuHDRx32PerturbedLAv2, iter_bytes=8)
         ok &= run(14, A.GpuHDRx2x32PerturbedLAv2)
         ok &= run(14, A.GpuHDRx64PerturbedLAv2)
         ok &= run(14, A.GpuHDRx32PerturbedLAv2)
