@@ -178,7 +178,10 @@ template <class IterT, bool Count> struct PerturbLoop<NumHdr<float>, IterT, Coun
     using Real = Hdr<float>;
     // orbit_fast: the per-element table of fs_scaled_loop.cuh (built on upload); nullptr selects the pure
     // float+exponent loop.
-    static constexpr int kSlowBatch = 1;          // lanes that must be waiting before a float+exponent step is issued
+#ifndef FS_SLOW_BATCH
+#define FS_SLOW_BATCH 1
+#endif
+    static constexpr int kSlowBatch = FS_SLOW_BATCH; // lanes that must be waiting before a float+exponent step is issued
     // Warp-synchronous: all 32 lanes call this converged; `live` = the lane has a pixel to iterate.
     FS_D static void run(bool live, const void *orbit, const void *orbit_fast, IterT orbit_count, IterT n_iterations, Real dcX,
                          Real dcY, Real &dXio, Real &dYio, IterT &RefIteration, IterT &iter, unsigned long long &steps) {
