@@ -72,4 +72,61 @@ template <class M> FS_HD void advance_as_written(M &re, M &im, M s, M cre, M cim
 }
 
 } // namespace atfast
+
+// Passes per escape test of the chunked AT loop, and per comparison of the cycle watch (fs_lav2.cuh lav2_at).
+#ifndef FS_AT_CHUNK
+#define FS_AT_CHUNK 16
+#endif
+constexpr int kWatchChunk = FS_AT_CHUNK;
+FS_HD int first_bit(unsigned int m) { // 1-based index of the lowest set bit
+#ifdef __CUDA_ARCH__
+    return __ffs((int)m);
+#else
+    return __builtin_ffs((int)m);
+#endif
+}
+// Cycle watch of the chunked AT loop: see the comment ahead of lav2_at in fs_lav2.cuh.  FS_HD so that
+// oracle/lockstep_check.cpp runs the very same code against the loop that executes every pass.
+template <class M, class IterT> struct CycleWatch {
+    M sre, sim;
+    IterT at;       // pass count of the saved state
+    IterT next;     // chunk-boundary pass count at which the next state is saved
+    bool armed;
+    FS_HD CycleWatch(M re, M im, IterT i) : sre(re), sim(im), at(i), next(i + (IterT)kWatchChunk), armed(true) {}
+    // `seen`: bit u set = the state after pass u + 1 of the chunk just finished (which ended at pass count i) equalled the
+    // saved state.  Any hit gives a period (a multiple of the true one): the lowest bit the shortest.
+    FS_HD void after_chunk_seen(M re, M im, IterT &i, IterT at_max, IterT &skipped, unsigned int seen) {
+        if (!armed) return;
+        if (seen != 0u) {
+            const IterT hit = i - (IterT)kWatchChunk + (IterT)first_bit(seen); // pass count at the first hit
+            const IterT P = hit - at;
+            if (P != 0) {
+                skipped = ((at_max - i) / P) * P;
+                i += skipped;
+                armed = false;
+                return;
+            }
+        }
+        if (i == next) {
+            sre = re; sim = im;
+            next = i + (i - at) * 2;
+            at = i;
+        }
+    }
+    FS_HD void after_chunk(M re, M im, IterT &i, IterT at_max, IterT &skipped) {
+        if (!armed) return;
+        if (bits_equal(re, sre) && bits_equal(im, sim)) {
+            const IterT P = i - at;
+            skipped = ((at_max - i) / P) * P;
+            i += skipped;
+            armed = false;
+        } else if (i == next) {
+            sre = re; sim = im;
+            next = i + (i - at) * 2; // gaps of 1, 2, 4, 8 ... chunks (stops growing if it would wrap: i never gets there)
+            at = i;
+        }
+    }
+};
+
+
 } // namespace fs

@@ -372,19 +372,10 @@ __global__ void __launch_bounds__(256) la_repack_kernel(const WireLA<Num, IterT>
 __global__ void __launch_bounds__(256) la2_pack_kernel(const LaRec<NumHdr<float>, uint32_t> *las, la2::Rec *out, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const LaRec<NumHdr<float>, uint32_t> a = las[i];
-        la2::Rec d;
-        const long long th_key = (long long)a.LAThreshold.e * (1ll << 23) + (long long)(__float_as_uint(a.LAThreshold.m) & 0x007fffffu);
-        d.ref_re = a.Ref.re; d.ref_im = a.Ref.im; d.ref_e2 = imax(a.Ref.e + 1, MIN_BIG); d.th_lo = (uint32_t)th_key;
-        d.zc_re = a.ZCoeff.re; d.zc_im = a.ZCoeff.im; d.zc_e = a.ZCoeff.e; d.th_hi = (int32_t)(th_key >> 32);
-        d.cc_re = a.CCoeff.re; d.cc_im = a.CCoeff.im; d.cc_e = a.CCoeff.e; d.step = a.StepLength;
-        d.nx_re = 0.0f; d.nx_im = 0.0f; d.nx_e = MIN_BIG; d.next = a.NextStageLAIndex;
-        if (i + 1 < n) {
-            const HdrC<float> nx = las[i + 1].Ref;
-            d.nx_re = nx.re; d.nx_im = nx.im; d.nx_e = nx.e;
-        } else {
-            d.ref_re = __uint_as_float(0x7fc00000u); // no following record to read: refuse
-        }
-        if (!(a.LAThreshold.m >= 1.0f && a.LAThreshold.m < 2.0f)) d.ref_re = __uint_as_float(0x7fc00000u);
+        const bool has_next = i + 1 < n;
+        HdrC<float> next_ref = hc_zero<float>();
+        if (has_next) next_ref = las[i + 1].Ref;
+        const la2::Rec d = la2::pack(a.Ref, a.ZCoeff, a.CCoeff, a.LAThreshold, a.StepLength, a.NextStageLAIndex, has_next, next_ref);
         out[i] = d;
     }
 }

@@ -41,29 +41,64 @@ struct Out {
     bool unusable, rebase;
 };
 
-#ifdef __CUDACC__
-FS_D int field(int d) { return __viaddmin_s32_relu(d, 127, 127); } // clamp(127 + d, 0, 127): exponent field of 2^min(d, 0)
-FS_D float pow2f(int f) { return __int_as_float(f << 23); }
+// clamp(127 + d, 0, 127): exponent field of 2^min(d, 0)
+FS_HD int field(int d) {
+#ifdef __CUDA_ARCH__
+    return __viaddmin_s32_relu(d, 127, 127);
+#else
+    const int v = d < 0 ? d + 127 : 127;
+    return v < 0 ? 0 : v;
+#endif
+}
+FS_HD float pow2f(int f) { return u2f((uint32_t)f << 23); }
+FS_HD float abs_(float x) {
+#ifdef __CUDA_ARCH__
+    return fabsf(x);
+#else
+    return __builtin_fabsf(x);
+#endif
+}
+FS_HD float max_(float a, float b) { // operands are finite and non-negative wherever this is called
+#ifdef __CUDA_ARCH__
+    return fmaxf(a, b);
+#else
+    return a > b ? a : b;
+#endif
+}
 // finite, non-zero and within [2^-60, 2^60)
-FS_D bool sane(float s) { return (__float_as_uint(s) - ((uint32_t)(127 - 60) << 23)) < ((uint32_t)120 << 23); }
+FS_HD bool sane(float s) { return (f2u(s) - ((uint32_t)(127 - 60) << 23)) < ((uint32_t)120 << 23); }
+
+// The record of one reference-shaped LA entry (`next_ref`: Ref of the following entry; has_next = false for the last one).
+FS_HD Rec pack(HdrC<float> Ref, HdrC<float> ZCoeff, HdrC<float> CCoeff, Hdr<float> LAThreshold, uint32_t step_length,
+               uint32_t next_stage, bool has_next, HdrC<float> next_ref) {
+    Rec d;
+    const long long th_key = (long long)LAThreshold.e * (1ll << 23) + (long long)(f2u(LAThreshold.m) & 0x007fffffu);
+    d.ref_re = Ref.re; d.ref_im = Ref.im; d.ref_e2 = imax(Ref.e + 1, MIN_BIG); d.th_lo = (uint32_t)th_key;
+    d.zc_re = ZCoeff.re; d.zc_im = ZCoeff.im; d.zc_e = ZCoeff.e; d.th_hi = (int32_t)(th_key >> 32);
+    d.cc_re = CCoeff.re; d.cc_im = CCoeff.im; d.cc_e = CCoeff.e; d.step = step_length;
+    d.nx_re = next_ref.re; d.nx_im = next_ref.im; d.nx_e = next_ref.e; d.next = next_stage;
+    // refuse every step on a record without a follower or whose threshold is not a reduced positive number
+    if (!has_next || !(LAThreshold.m >= 1.0f && LAThreshold.m < 2.0f)) d.ref_re = u2f(0x7fc00000u);
+    return d;
+}
 
 // One step; false = refused (nothing may be used).
-FS_D bool step(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, float dr, float di, int de, float cr,
-               float ci, int ce, Out &o) {
-    const float rr = __uint_as_float(q0.x), ri = __uint_as_float(q0.y);
+FS_HD bool step(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, float dr, float di, int de, float cr,
+                float ci, int ce, Out &o) {
+    const float rr = u2f(q0.x), ri = u2f(q0.y);
     const int re2 = (int)q0.z;
     // Prepare: t = 2*Ref + dz
     const int d1 = re2 - de;
     const int fa1 = field(d1), fb1 = field(-d1);
     const float ma1 = pow2f(fa1), mb1 = pow2f(fb1);
-    const float tr = __fmaf_rn(dr, mb1, rr * ma1), ti = __fmaf_rn(di, mb1, ri * ma1);
-    const int te = max(re2, de);
+    const float tr = fma_(dr, mb1, rr * ma1), ti = fma_(di, mb1, ri * ma1);
+    const int te = imax(re2, de);
     bool gap = (uint32_t)(fa1 + fb1 - 128) < 7u;
     // w = dz * t, reduced
-    const float wr = __fmaf_rn(dr, tr, -(di * ti)), wi = __fmaf_rn(di, tr, dr * ti);
-    if (!sane(fabsf(wr) + fabsf(wi))) return false;
-    const uint32_t wb = __float_as_uint(fmaxf(fabsf(wr), fabsf(wi)));
-    const float sc = __uint_as_float(0x7f000000u - (wb & 0x7f800000u));
+    const float wr = fma_(dr, tr, -(di * ti)), wi = fma_(di, tr, dr * ti);
+    if (!sane(abs_(wr) + abs_(wi))) return false;
+    const uint32_t wb = f2u(max_(abs_(wr), abs_(wi)));
+    const float sc = u2f(0x7f000000u - (wb & 0x7f800000u));
     const float nr = wr * sc, ni = wi * sc;
     // cheb(newdz) >= LAThreshold on (exponent, mantissa) pairs of reduced positive numbers = one signed 64-bit comparison
     // of exponent * 2^23 + mantissa field; the record carries the threshold in that form (th_key).  wb already holds the
@@ -75,33 +110,32 @@ FS_D bool step(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, f
     o.unusable = wkey >= tkey;
     if (o.unusable) return !gap;
     // Evaluate: dz' = newdz*ZCoeff + dc*CCoeff
-    const float zr = __uint_as_float(q1.x), zi = __uint_as_float(q1.y);
-    const float ccr = __uint_as_float(q2.x), cci = __uint_as_float(q2.y);
-    const float pr = __fmaf_rn(nr, zr, -(ni * zi)), pi = __fmaf_rn(ni, zr, nr * zi);
-    const float qr = __fmaf_rn(cr, ccr, -(ci * cci)), qi = __fmaf_rn(ci, ccr, cr * cci);
+    const float zr = u2f(q1.x), zi = u2f(q1.y);
+    const float ccr = u2f(q2.x), cci = u2f(q2.y);
+    const float pr = fma_(nr, zr, -(ni * zi)), pi = fma_(ni, zr, nr * zi);
+    const float qr = fma_(cr, ccr, -(ci * cci)), qi = fma_(ci, ccr, cr * cci);
     const int pe = nwe + (int)q1.z, qe = ce + (int)q2.z;
     const int d2 = pe - qe;
     const int fa2 = field(d2), fb2 = field(-d2);
     const float ma2 = pow2f(fa2), mb2 = pow2f(fb2);
-    o.dre = __fmaf_rn(qr, mb2, pr * ma2);
-    o.dim = __fmaf_rn(qi, mb2, pi * ma2);
-    o.de = max(pe, qe);
+    o.dre = fma_(qr, mb2, pr * ma2);
+    o.dim = fma_(qi, mb2, pi * ma2);
+    o.de = imax(pe, qe);
     gap = gap || (uint32_t)(fa2 + fb2 - 128) < 7u;
     // getZ: z = Ref' + dz'
     const int ne = (int)q3.z;
     const int d3 = ne - o.de;
     const int fa3 = field(d3), fb3 = field(-d3);
     const float ma3 = pow2f(fa3), mb3 = pow2f(fb3);
-    o.zre = __fmaf_rn(o.dre, mb3, __uint_as_float(q3.x) * ma3);
-    o.zim = __fmaf_rn(o.dim, mb3, __uint_as_float(q3.y) * ma3);
-    o.ze = max(ne, o.de);
+    o.zre = fma_(o.dre, mb3, u2f(q3.x) * ma3);
+    o.zim = fma_(o.dim, mb3, u2f(q3.y) * ma3);
+    o.ze = imax(ne, o.de);
     gap = gap || (uint32_t)(fa3 + fb3 - 128) < 7u;
-    if (gap || !sane(fabsf(o.zre) + fabsf(o.zim)) || !sane(fabsf(o.dre) + fabsf(o.dim))) return false;
+    if (gap || !sane(abs_(o.zre) + abs_(o.zim)) || !sane(abs_(o.dre) + abs_(o.dim))) return false;
     // cheb(z) < cheb(dz'): z.e - dz'.e = max(d3, 0), and mb3 = 2^-max(d3, 0) (0 once the gap is >= 127: then |z| >> |dz'|)
-    o.rebase = fmaxf(fabsf(o.zre), fabsf(o.zim)) < fmaxf(fabsf(o.dre), fabsf(o.dim)) * mb3;
+    o.rebase = max_(abs_(o.zre), abs_(o.zim)) < max_(abs_(o.dre), abs_(o.dim)) * mb3;
     return true;
 }
-#endif
 
 } // namespace la2
 } // namespace fs

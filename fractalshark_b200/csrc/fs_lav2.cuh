@@ -223,48 +223,7 @@ template <class Num> FS_D bool c_is_ge(typename Num::Real a, typename Num::Real 
 // 8 ... (Brent's schedule) and compares after every chunk; on a hit it advances the pass counter by the largest multiple
 // of P that fits and lets the loop finish the remainder (< P passes) the ordinary way.  Same z, same pass count, hence the
 // same iteration buffer as the reference, bit for bit; what changes is the number of executed passes.
-template <class M, class IterT> struct CycleWatch {
-    M sre, sim;
-    IterT at;       // pass count of the saved state
-    IterT next;     // chunk-boundary pass count at which the next state is saved
-    bool armed;
-    FS_D CycleWatch(M re, M im, IterT i) : sre(re), sim(im), at(i), next(i + (IterT)FS_AT_CHUNK), armed(true) {}
-    FS_D static bool same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
-    FS_D static bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
-    // `seen`: bit u set = the state after pass u + 1 of the chunk just finished (which ended at pass count i) equalled the
-    // saved state.  Any hit gives a period (a multiple of the true one): the lowest bit the shortest.
-    FS_D void after_chunk_seen(M re, M im, IterT &i, IterT at_max, IterT &skipped, unsigned int seen) {
-        if (!armed) return;
-        if (seen != 0u) {
-            const IterT hit = i - (IterT)FS_AT_CHUNK + (IterT)__ffs(seen); // pass count at the first hit
-            const IterT P = hit - at;
-            if (P != 0) {
-                skipped = ((at_max - i) / P) * P;
-                i += skipped;
-                armed = false;
-                return;
-            }
-        }
-        if (i == next) {
-            sre = re; sim = im;
-            next = i + (i - at) * 2;
-            at = i;
-        }
-    }
-    FS_D void after_chunk(M re, M im, IterT &i, IterT at_max, IterT &skipped) {
-        if (!armed) return;
-        if (same_bits(re, sre) && same_bits(im, sim)) {
-            const IterT P = i - at;
-            skipped = ((at_max - i) / P) * P;
-            i += skipped;
-            armed = false;
-        } else if (i == next) {
-            sre = re; sim = im;
-            next = i + (i - at) * 2; // gaps of 1, 2, 4, 8 ... chunks (stops growing if it would wrap: i never gets there)
-            at = i;
-        }
-    }
-};
+// (CycleWatch itself lives in fs_at_fast.cuh so that oracle/lockstep_check.cpp can run it on the CPU.)
 
 // The same watch for the general loop (any numeric type): the state is the whole complex number, exponent included.
 FS_D bool same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }

@@ -11,10 +11,13 @@
 #include "oracle_cpu.cpp"
 
 #include <mutex>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../fractalshark_b200/csrc/fs_scaled_loop.cuh"
 #include "../fractalshark_b200/csrc/fs_at_fast.cuh"
 #include "../fractalshark_b200/csrc/fs_la_fast.cuh"
+#include "../fractalshark_b200/csrc/fs_la_step2.cuh"
 
 namespace {
 
@@ -132,7 +135,30 @@ template <class IterT> void lockstep_at_pixel(const Lav2Job<IterT> &J, int X, in
 // whatever it accepts must agree bit for bit (decision, new delta, z, rebase-by-norm), whatever it refuses is counted.
 struct LaStats {
     uint64_t steps = 0, refused = 0, mismatches = 0, unusable = 0;
+    uint64_t refused2 = 0, mismatches2 = 0; // the same for the step on step-shaped records (fs_la_step2.cuh)
 };
+// la2::step on the record la2::pack builds from a reference-shaped entry, against what the oracle computed for that step
+template <class Rec>
+int la2_check(const Rec &r, const HC &next_ref, const HC &dz, const HC &dc, bool unusable, const HC &ndz, const HC &z, bool by_norm) {
+    const fs::la2::Rec rec = fs::la2::pack(fs::HdrC<float>{r.Ref.re, r.Ref.im, r.Ref.exp}, fs::HdrC<float>{r.ZCoeff.re, r.ZCoeff.im, r.ZCoeff.exp},
+                                           fs::HdrC<float>{r.CCoeff.re, r.CCoeff.im, r.CCoeff.exp},
+                                           fs::Hdr<float>{r.LAThreshold.mantissa, r.LAThreshold.exp}, (uint32_t)r.StepLength,
+                                           (uint32_t)r.NextStageLAIndex, true, fs::HdrC<float>{next_ref.re, next_ref.im, next_ref.exp});
+    uint4 q[4];
+    memcpy(q, &rec, sizeof(rec));
+    fs::la2::Out o;
+    if (!fs::la2::step(q[0], q[1], q[2], q[3], dz.re, dz.im, dz.exp, dc.re, dc.im, dc.exp, o)) return 1; // refused
+    if (o.unusable != unusable) return 2;
+    if (unusable) return 0;
+    // bit for bit, except the SIGN of an exact zero: where the reference's addition drops an operand (gap >= 120) it
+    // returns the other one untouched (HDRFloatComplex.h:219-247), the product adds `dropped * 0` to it, which turns a -0
+    // component into +0.  No operation of the path can tell the two apart (no division, IEEE comparisons, |x| in the norms).
+    auto same = [](float a, float b) { return bits(a) == bits(b) || (a == 0.0f && b == 0.0f); };
+    if (!same(o.dre, ndz.re) || !same(o.dim, ndz.im) || o.de != ndz.exp || !same(o.zre, z.re) || !same(o.zim, z.im) ||
+        o.ze != z.exp || o.rebase != by_norm)
+        return 2;
+    return 0;
+}
 struct LaObserver {
     LaStats &st;
     template <class Rec>
@@ -141,6 +167,11 @@ struct LaObserver {
         fs::lafast::StepOut o;
         st.steps++;
         if (unusable) st.unusable++;
+        {
+            const int rc2 = la2_check(r, next_ref, dz, dc, unusable, ndz, z, by_norm);
+            if (rc2 == 1) st.refused2++;
+            if (rc2 == 2) st.mismatches2++;
+        }
         const bool ok = fs::lafast::step(r.Ref.re, r.Ref.im, r.Ref.exp, r.ZCoeff.re, r.ZCoeff.im, r.ZCoeff.exp, r.CCoeff.re,
                                          r.CCoeff.im, r.CCoeff.exp, r.LAThreshold.mantissa, r.LAThreshold.exp, next_ref.re,
                                          next_ref.im, next_ref.exp, dz.re, dz.im, dz.exp, dc.re, dc.im, dc.exp, o);
@@ -238,6 +269,73 @@ uint64_t lockstep_at(const void *at, int use_at, int is_valid, int w, int h, con
     return st.mismatches;
 }
 
+// The cycle watch of the chunked AT loop (fs_at_fast.cuh CycleWatch, the code the kernel runs) against the loop that
+// executes every pass: for every sampled pixel that takes the AT shortcut with an accepted plan, both must end with the same
+// pass count and the same (re, im), bit for bit.  The chunk structure is the kernel's: 16 passes per escape test, a chunk
+// with an escaped pass is replayed pass by pass, the watch is consulted after every clean chunk.
+// stats[5]: pixels compared, pixels whose cycle was found, passes executed with the watch, passes executed without, mismatches
+uint64_t lockstep_at_cycle(const void *at, int use_at, int is_valid, int w, int h, const void *dx, const void *dy,
+                           const void *cenx, const void *ceny, uint64_t n_iter, int col_step, int row_step, uint64_t *stats) {
+    using IterT = uint32_t;
+    Lav2Job<IterT> J;
+    memset((void *)&J, 0, sizeof(J));
+    J.at = (const ATInfoF<IterT> *)at;
+    J.use_at = use_at && at;
+    J.is_valid = is_valid;
+    memcpy(&J.dx, dx, 8); memcpy(&J.dy, dy, 8); memcpy(&J.centerX, cenx, 8); memcpy(&J.centerY, ceny, 8);
+    uint64_t pixels = 0, found = 0, with = 0, without = 0, mism = 0;
+    if (!(J.is_valid && J.use_at)) { stats[0] = stats[1] = stats[2] = stats[3] = stats[4] = 0; return 0; }
+    const ATInfoF<IterT> &AT = *J.at;
+    const IterT at_max = (IterT)(n_iter / AT.StepLength);
+    constexpr int K = fs::kWatchChunk;
+    for (int y = 0; y < h; y += (row_step < 1 ? 1 : row_step))
+        for (int x = 0; x < w; x += (col_step < 1 ? 1 : col_step)) {
+            const HF DeltaReal = sub(mul(J.dx, hf_from_number((float)x)), J.centerX);
+            const HF negdy{-J.dy.mantissa, J.dy.exp};
+            const HF DeltaImaginary = sub(mul(negdy, hf_from_number((float)y)), J.centerY);
+            const HC d0 = hc_from(DeltaReal, DeltaImaginary);
+            if (cmpPR(cheb(d0), AT.ThresholdC) > 0) continue;
+            HC c = add(mul(d0, AT.CCoeff), AT.RefC);
+            Reduce(c);
+            const fs::atfast::Plan<float> plan = fs::atfast::plan<float>(fs::HdrC<float>{c.re, c.im, c.exp},
+                                                                        fs::Hdr<float>{AT.SqrEscapeRadius.mantissa, AT.SqrEscapeRadius.exp}, at_max > 0);
+            if (!plan.ok) continue;
+            pixels++;
+            // every pass
+            float re0 = 0.0f, im0 = 0.0f;
+            IterT i0 = 0;
+            for (; i0 < at_max; i0++) {
+                if (fs::atfast::escaped(fs::atfast::norm(re0, im0), plan.thr)) break;
+                fs::atfast::advance(re0, im0, plan.s, c.re, c.im);
+            }
+            without += i0;
+            // chunked, with the watch
+            float re = 0.0f, im = 0.0f;
+            IterT i = 0, skipped = 0;
+            fs::CycleWatch<float, IterT> watch(re, im, i);
+            while (at_max - i >= (IterT)K) {
+                const float sre = re, sim = im;
+                bool esc = false;
+                for (int u = 0; u < K; u++) {
+                    if (fs::atfast::escaped(fs::atfast::norm(re, im), plan.thr)) { esc = true; break; }
+                    fs::atfast::advance(re, im, plan.s, c.re, c.im);
+                }
+                if (esc) { re = sre; im = sim; break; }
+                i += (IterT)K;
+                watch.after_chunk(re, im, i, at_max, skipped);
+            }
+            for (; i < at_max; i++) {
+                if (fs::atfast::escaped(fs::atfast::norm(re, im), plan.thr)) break;
+                fs::atfast::advance(re, im, plan.s, c.re, c.im);
+            }
+            with += i - skipped;
+            if (!watch.armed) found++;
+            if (i != i0 || bits(re) != bits(re0) || bits(im) != bits(im0)) mism++;
+        }
+    stats[0] = pixels; stats[1] = found; stats[2] = with; stats[3] = without; stats[4] = mism;
+    return mism;
+}
+
 // Returns the number of lockstep mismatches (0 = every committed chunk matched the oracle by value).
 // stats[7]: fast steps, slow steps, chunks committed, chunks rejected, entries refused, mismatches, pixels finished in a chunk
 uint64_t lockstep_render_lav2(int mode, const void *orbit, uint64_t count, const void *las, const void *stages,
@@ -311,6 +409,97 @@ void lockstep_la(const void *las, const void *stages, const void *at, uint64_t l
     };
     if (iter_bytes == 8) run(uint64_t{}); else run(uint32_t{});
     out[0] = st.steps; out[1] = st.refused; out[2] = st.mismatches; out[3] = st.unusable;
+    out[4] = st.refused2; out[5] = st.mismatches2;
+}
+
+// The LA step on step-shaped records (fs_la_step2.cuh) against the reference-shaped operations on synthetic inputs aimed
+// at its guards: exponent gaps of the three aligned additions spread over [-140, 140] (the reference drops an operand at
+// |gap| >= 120, the select-free form at 127), exact zeros in every operand, mantissas far from [1, 2) (un-reduced deltas,
+// near-total cancellation in dz * (2 Ref + dz) and in the sums), thresholds one ulp either side of cheb(newdz), records
+// whose threshold is not reduced.  Whatever la2::step accepts must agree bit for bit with the oracle's step.
+// out[0..3] = cases, accepted, refused, mismatches.
+void lockstep_la2_fuzz(uint64_t count, uint64_t seed, uint64_t *out) {
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+    auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    auto pick_mant = [&]() -> float {
+        const uint64_t r = next();
+        const unsigned kind = (unsigned)(r & 15u);
+        float m;
+        const uint32_t frac = (uint32_t)(r >> 20) & 0x007fffffu;
+        if (kind == 0) m = 0.0f;                                                         // exact zero
+        else if (kind == 1) m = fbits(((uint32_t)(127 - 1 - (unsigned)((r >> 8) & 63u)) << 23) | frac); // tiny: down to 2^-64
+        else if (kind == 2) m = fbits(((uint32_t)(127 + 1 + (unsigned)((r >> 8) & 7u)) << 23) | frac);  // un-reduced, up to 2^8
+        else if (kind == 3) m = fbits(0x3f800000u | ((r >> 50) & 1u ? 0x007fffffu : 0u));               // 1.0 or 2 - ulp
+        else m = fbits(0x3f800000u | frac);                                                             // reduced [1, 2)
+        return (r >> 63) ? -m : m;
+    };
+    uint64_t accepted = 0, refused = 0, mismatches = 0;
+    for (uint64_t n = 0; n < count; n++) {
+        LAInfoDeepF<uint32_t> r{};
+        const int base = (int)(next() % 4001) - 2000;
+        auto gap = [&]() -> int { const uint64_t q = next(); return (q & 7u) == 0 ? (int)((q >> 8) % 281) - 140 : (int)((q >> 8) % 61) - 30; };
+        HC dz{pick_mant(), pick_mant(), base};
+        r.Ref = HC{pick_mant(), pick_mant(), base + gap()};
+        r.ZCoeff = HC{pick_mant(), pick_mant(), (int)(next() % 2001) - 1000};
+        r.CCoeff = HC{pick_mant(), pick_mant(), (int)(next() % 2001) - 1000};
+        // dc chosen so that dc * CCoeff lands within `gap` of newdz * ZCoeff (exponents: ~2 base + ZCoeff.e)
+        HC dc{pick_mant(), pick_mant(), 2 * base + r.ZCoeff.exp - r.CCoeff.exp + gap()};
+        HC next_ref{pick_mant(), pick_mant(), 2 * base + r.ZCoeff.exp + gap()};
+        r.StepLength = 1;
+        r.NextStageLAIndex = 0;
+        // the oracle's step (oracle_cpu.cpp lav2_prologue, LAKernel.cuh:91-127)
+        HC newdz = mul(dz, add(mul(r.Ref, HF{1.0f, 1}), dz));
+        Reduce(newdz);
+        HF cn = cheb(newdz);
+        // threshold: mostly around cheb(newdz) (equal, one ulp below / above, an exponent apart), sometimes anything
+        const uint64_t q = next();
+        HF th = cn;
+        switch ((unsigned)(q & 7u)) {
+        case 0: break;
+        case 1: th.mantissa = fbits(bits(th.mantissa) + 1u); break;
+        case 2: th.mantissa = fbits(bits(th.mantissa) - 1u); break;
+        case 3: th.exp += 1; break;
+        case 4: th.exp -= 1; break;
+        case 5: th = HF{pick_mant(), cn.exp}; break; // possibly not reduced / zero / negative: the record must be refused
+        default: th = HF{fbits(0x3f800000u | ((uint32_t)(q >> 20) & 0x007fffffu)), cn.exp + (int)((q >> 8) % 5) - 2}; break;
+        }
+        if (!(th.mantissa >= 1.0f && th.mantissa < 2.0f) && (q & 7u) != 5) th.mantissa = 1.0f;
+        r.LAThreshold = th;
+        const bool unusable = cmpPR(cn, r.LAThreshold) >= 0;
+        HC ndz = dz, z = dz;
+        bool by_norm = false;
+        if (!unusable) {
+            ndz = add(mul(newdz, r.ZCoeff), mul(dc, r.CCoeff));
+            z = add(next_ref, ndz);
+            HF n0 = cheb(z), nN = cheb(ndz);
+            Reduce(n0);
+            Reduce(nN);
+            by_norm = cmpPR(n0, nN) < 0;
+        }
+        const int rc = la2_check(r, next_ref, dz, dc, unusable, ndz, z, by_norm);
+        if (rc == 0) accepted++;
+        else if (rc == 1) refused++;
+        else {
+            if (getenv("FS_FUZZ_VERBOSE") && mismatches < 12) {
+                fprintf(stderr, "mismatch: dz=(%a,%a,%d) Ref=(%a,%a,%d) ZC=(%a,%a,%d) CC=(%a,%a,%d) dc=(%a,%a,%d) nref=(%a,%a,%d) th=(%a,%d)\n",
+                        dz.re, dz.im, dz.exp, r.Ref.re, r.Ref.im, r.Ref.exp, r.ZCoeff.re, r.ZCoeff.im, r.ZCoeff.exp, r.CCoeff.re, r.CCoeff.im,
+                        r.CCoeff.exp, dc.re, dc.im, dc.exp, next_ref.re, next_ref.im, next_ref.exp, th.mantissa, th.exp);
+                fprintf(stderr, "   oracle: newdz=(%a,%a,%d) unusable=%d ndz=(%a,%a,%d) z=(%a,%a,%d) by_norm=%d\n", newdz.re, newdz.im, newdz.exp,
+                        (int)unusable, ndz.re, ndz.im, ndz.exp, z.re, z.im, z.exp, (int)by_norm);
+                const fs::la2::Rec rec = fs::la2::pack(fs::HdrC<float>{r.Ref.re, r.Ref.im, r.Ref.exp}, fs::HdrC<float>{r.ZCoeff.re, r.ZCoeff.im, r.ZCoeff.exp},
+                                                       fs::HdrC<float>{r.CCoeff.re, r.CCoeff.im, r.CCoeff.exp}, fs::Hdr<float>{th.mantissa, th.exp}, 1, 0, true,
+                                                       fs::HdrC<float>{next_ref.re, next_ref.im, next_ref.exp});
+                uint4 qq[4];
+                memcpy(qq, &rec, sizeof(rec));
+                fs::la2::Out o;
+                const bool ok = fs::la2::step(qq[0], qq[1], qq[2], qq[3], dz.re, dz.im, dz.exp, dc.re, dc.im, dc.exp, o);
+                fprintf(stderr, "   la2:    ok=%d unusable=%d ndz=(%a,%a,%d) z=(%a,%a,%d) rebase=%d\n", (int)ok, (int)o.unusable, o.dre, o.dim, o.de,
+                        o.zre, o.zim, o.ze, (int)o.rebase);
+            }
+            mismatches++;
+        }
+    }
+    out[0] = count; out[1] = accepted; out[2] = refused; out[3] = mismatches;
 }
 
 } // extern "C"

@@ -175,6 +175,23 @@ def lockstep_at(w, h, coords, la, n_iter, max_passes=20000, col_step=1, row_step
     return dict(zip(("pixels", "refused", "passes", "mismatches", "escaped", "mono"), (int(v) for v in stats)))
 
 
+def lockstep_at_cycle(w, h, coords, la, n_iter, col_step=1, row_step=1):
+    """The cycle watch of the chunked AT loop (fs_at_fast.cuh CycleWatch, host build) against the loop that executes every
+    pass, for every sampled pixel: same pass count and same z, bit for bit (mismatches must be 0)."""
+    global _lock
+    if _lock is None:
+        _lock = C.CDLL(LOCKSTEP_LIB)
+    fn = _lock.lockstep_at_cycle
+    fn.restype = C.c_uint64
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    l = la.descriptor()
+    stats = (C.c_uint64 * 5)()
+    fn(l.at, l.use_at, l.is_valid, w, h, _buf(coords["dx"]), _buf(coords["dy"]), _buf(coords["center_x"]),
+       _buf(coords["center_y"]), n_iter, col_step, row_step, stats)
+    return dict(zip(("pixels", "cycles_found", "passes_with_watch", "passes_without", "mismatches"), (int(v) for v in stats)))
+
+
 def at_plan(cre, cim, ce, rm, re_):
     """(ok, mono, E, thr) of the plan the kernel's AT shortcut makes for c = (cre, cim) x 2^ce, R = rm x 2^re_."""
     global _lock
@@ -220,7 +237,23 @@ def lockstep_la(w, h, coords, la, n_iter, iter_bytes=4, col_step=1, row_step=1):
     V, I, U64 = C.c_void_p, C.c_int, C.c_uint64
     fn.argtypes = [V, V, V, U64, I, I, I, I, V, V, V, V, U64, I, I, I, V]
     l = la.descriptor()
-    out = (C.c_uint64 * 4)()
+    out = (C.c_uint64 * 6)()
     fn(l.las, l.stages, l.at, l.la_stage_count, l.use_at, l.is_valid, w, h, _buf(coords["dx"]), _buf(coords["dy"]),
        _buf(coords["center_x"]), _buf(coords["center_y"]), n_iter, iter_bytes, col_step, row_step, out)
-    return dict(zip(("steps", "refused", "mismatches", "unusable"), (int(v) for v in out)))
+    # refused2 / mismatches2: the same inputs through the step on step-shaped records (fs_la_step2.cuh)
+    return dict(zip(("steps", "refused", "mismatches", "unusable", "refused2", "mismatches2"), (int(v) for v in out)))
+
+
+def lockstep_la2_fuzz(count, seed=1):
+    """la2::step (fs_la_step2.cuh, host build) against the oracle's reference-shaped LA step on synthetic inputs aimed at
+    its guards (exponent gaps around 120..127, exact zeros, un-reduced mantissas, thresholds one ulp off).
+    Returns {"cases", "accepted", "refused", "mismatches"}; mismatches must be 0."""
+    global _lock
+    if _lock is None:
+        _lock = C.CDLL(LOCKSTEP_LIB)
+    fn = _lock.lockstep_la2_fuzz
+    fn.restype = None
+    fn.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    out = (C.c_uint64 * 4)()
+    fn(count, seed, out)
+    return dict(zip(("cases", "accepted", "refused", "mismatches"), (int(v) for v in out)))

@@ -188,6 +188,35 @@ def test_select_free_la_step_matches_float_exponent_step_in_lockstep(built, view
     st = oracle_cpu.lockstep_la(w, h, coords, la, n, col_step=stride, row_step=stride)
     assert st["mismatches"] == 0, st
     assert st["steps"] > 10_000 and st["refused"] < st["steps"] // 4, st
+    # the same steps through the step on step-shaped records (fs_la_step2.cuh: la2::pack + la2::step, the default LA walk
+    # of the HDRx32 / 32-bit kernel)
+    assert st["mismatches2"] == 0, st
+    assert st["refused2"] < st["steps"] // 4, st
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_step_shaped_la_step_on_inputs_aimed_at_its_guards(built, seed):
+    """la2::step against the oracle's reference-shaped LA step on synthetic inputs: exponent gaps of the three aligned
+    additions across [-140, 140] (the reference drops an operand at 120, the select-free form at 127), exact zeros,
+    un-reduced and nearly cancelled mantissas, thresholds one ulp either side of cheb(newdz), un-reduced thresholds.
+    Whatever it accepts agrees bit for bit (up to the sign of an exact zero, see oracle/lockstep_check.cpp); it accepts most."""
+    st = oracle_cpu.lockstep_la2_fuzz(2_000_000, seed)
+    assert st["mismatches"] == 0, st
+    assert st["accepted"] > st["cases"] * 3 // 4, st
+
+
+@pytest.mark.parametrize("view_id,w,h,stride", [(14, 384, 216, 3), (5, 192, 108, 5), (19, 192, 108, 5)])
+def test_at_cycle_watch_ends_where_the_full_loop_ends(built, view_id, w, h, stride):
+    """CycleWatch (the code lav2_at runs, host build) against the AT loop that executes every pass: same number of passes
+    accounted for and the same z, bit for bit, for every sampled pixel; on View 14 the interior pixels (18,402 passes each
+    without the watch) must be found periodic and the executed passes must collapse."""
+    _, coords, orbit, la, n = cases.make_inputs(view_id, w, h, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 4)
+    st = oracle_cpu.lockstep_at_cycle(w, h, coords, la, n, col_step=stride, row_step=stride)
+    assert st["mismatches"] == 0, st
+    assert st["passes_with_watch"] <= st["passes_without"], st
+    if view_id == 14:
+        assert st["pixels"] > 1000 and st["cycles_found"] > 100, st
+        assert st["passes_with_watch"] * 10 < st["passes_without"], st
 
 
 def test_twice_the_rounded_product_identity_behind_the_six_rounding_at_pass(built):
