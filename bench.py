@@ -730,11 +730,17 @@ def main():
         if not args.no_cpu_baseline and lav2:
             import oracle_cpu
             threads = oracle_cpu.hardware_threads()
-            port_v, port_dt, port_sample = cpu_port_sample(wl, threads, 6 if spec.get("view") == 5 else 2)
-            cb = {"value": port_v, "unit": "pixel-iters/s", "cores": threads, "kind": "port", "sample": port_sample,
-                  "what": "oracle/oracle_cpu.cpp: CPU port of the GPU algorithm"}
             try:
-                ref = ReferenceCpu(wl)
+                port_v, port_dt, port_sample = cpu_port_sample(wl, threads, 6 if spec.get("view") == 5 else 2)
+                cb = {"value": port_v, "unit": "pixel-iters/s", "cores": threads, "kind": "port", "sample": port_sample,
+                      "what": "oracle/oracle_cpu.cpp: CPU port of the GPU algorithm"}
+            except NotImplementedError as e:  # numeric types the CPU port does not restate (2x32, HDRx64 ...)
+                port_v, port_sample = None, None
+                cb = {"value": None, "unit": "pixel-iters/s", "cores": threads, "kind": "port", "unavailable": str(e)[:200]}
+            try:
+                ref = ReferenceCpu(wl) if spec["alg"].startswith("GpuHDRx32") else None
+                if ref is None:
+                    raise RuntimeError("the reference CPU arm built here is the HDRFloat<float> LAv2 loop")
                 if ref.ok:
                     stride = ref.sized_stride(15.0)
                     v, dt, sample = ref.sample(stride)

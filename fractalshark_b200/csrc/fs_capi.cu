@@ -845,7 +845,7 @@ template <class Pixel> uint32_t launch_direct_ext_pods(fs_renderer *r, const voi
                : launch_direct_ext<Pixel, uint32_t>(r, load_pod<Cd>(cx), load_pod<Cd>(cy), load_pod<Cd>(dx), load_pod<Cd>(dy), n_iter);
 }
 
-template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaStream_t stream) {
+template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaStream_t stream, bool colors = true) {
     same_carveout(r, reduction_init_kernel<IterT>);
     same_carveout(r, post_kernel<IterT, 1>);
     same_carveout(r, post_kernel<IterT, 2>);
@@ -855,7 +855,10 @@ template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaSt
     const int pitch = (int)(r->w_block * NB_THREADS_W);
     const int grid = r->num_sms * 8;
     const IterT *it = static_cast<const IterT *>(r->iter_buf);
-#define FS_POST(AA) post_kernel<IterT, AA><<<grid, 256, 0, stream>>>(it, pitch, r->color_buf, r->pal_dev, r->pal_iters, r->aux_depth, (int)r->color_w, (int)r->color_h, (IterT)n_iter, r->red_dev, (int)r->shard_count, (int)r->shard_index)
+#define FS_POST_ARGS (it, pitch, r->color_buf, r->pal_dev, r->pal_iters, r->aux_depth, (int)r->color_w, (int)r->color_h, (IterT)n_iter, r->red_dev, (int)r->shard_count, (int)r->shard_index)
+#define FS_POST(AA)                                                                                                    \
+    if (colors) post_kernel<IterT, AA, true><<<grid, 256, 0, stream>>> FS_POST_ARGS;                                    \
+    else { same_carveout(r, post_kernel<IterT, AA, false>); post_kernel<IterT, AA, false><<<grid, 256, 0, stream>>> FS_POST_ARGS; }
     switch (r->aa) {
     case 1: FS_POST(1); break;
     case 2: FS_POST(2); break;
@@ -863,6 +866,7 @@ template <class IterT> uint32_t run_post(fs_renderer *r, uint64_t n_iter, cudaSt
     default: FS_POST(4); break;
     }
 #undef FS_POST
+#undef FS_POST_ARGS
     r->launches += 2;
     return cudaGetLastError();
 }
@@ -874,6 +878,10 @@ template <class IterT> void preload_post_kernels_typed() {
     cudaFuncGetAttributes(&fa, post_kernel<IterT, 2>);
     cudaFuncGetAttributes(&fa, post_kernel<IterT, 3>);
     cudaFuncGetAttributes(&fa, post_kernel<IterT, 4>);
+    cudaFuncGetAttributes(&fa, post_kernel<IterT, 1, false>);
+    cudaFuncGetAttributes(&fa, post_kernel<IterT, 2, false>);
+    cudaFuncGetAttributes(&fa, post_kernel<IterT, 3, false>);
+    cudaFuncGetAttributes(&fa, post_kernel<IterT, 4, false>);
 }
 void preload_post_kernels(fs_renderer *r) {
     if (r->iter_bytes == 8) preload_post_kernels_typed<uint64_t>();
@@ -1218,7 +1226,9 @@ uint32_t fs_render_current(fs_renderer *r, uint64_t n_iterations, void *iter_buf
     DeviceGuard g(r->device);
     cudaStream_t stream = progressive ? r->display : r->compute;
     if (progressive) request_yield_if_rendering(r);
-    uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream) : run_post<uint32_t>(r, n_iterations, stream);
+    // no colour buffer asked for: the reduction alone (the colour buffer on the device is then stale until a call that asks)
+    const bool colors = color_buffer != nullptr;
+    uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream, colors) : run_post<uint32_t>(r, n_iterations, stream, colors);
     if (rc) return rc;
     cudaError_t err = cudaSuccess;
     if (iter_buffer && !(r->sink_filled && iter_buffer == r->sink_host)) { // a filled sink already holds the frame
@@ -1249,7 +1259,8 @@ uint32_t fs_render_current_shard(fs_renderer *r, uint64_t n_iterations, void *it
     DeviceGuard g(r->device);
     cudaStream_t stream = progressive ? r->display : r->compute;
     if (progressive) request_yield_if_rendering(r);
-    uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream) : run_post<uint32_t>(r, n_iterations, stream);
+    const bool colors = color_buffer != nullptr;
+    uint32_t rc = r->iter_bytes == 8 ? run_post<uint64_t>(r, n_iterations, stream, colors) : run_post<uint32_t>(r, n_iterations, stream, colors);
     if (rc) return rc;
     cudaError_t err = cudaSuccess;
     if (iter_buffer && !(r->sink_filled && iter_buffer == r->sink_host)) {
