@@ -646,6 +646,23 @@ def main():
         e2e = {"value": total_sum / e2e_s, "unit": "pixel-iters/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": hp * wp * 4 + 24,
                "ms_per_step": e2e_s * 1e3, "host_frame": "pinned; copied after the render"}
 
+    # ---- time to the first frame of a new reference orbit: orbit + table (host, untimed above), upload, frame --------------
+    first_frame = None
+    if lav2:
+        ups = []
+        for _ in range(5):
+            gen += 1
+            torch.cuda.synchronize()
+            t0 = time.time()
+            assert r.InitializePerturb(gen, orbit_pinned, 0, None, la_pinned) == 0
+            assert r.SyncComputeStream() == 0
+            ups.append((time.time() - t0) * 1e3)
+        first_frame = {"orbit_s": gen_times["orbit_s"], "table_s": gen_times["table_s"], "upload_ms": min(ups),
+                       "frame_ms": ms_per_step,
+                       "what": "reference orbit (in-tree single-threaded GMP loop) and LA table (in-tree builder, byte-identical to "
+                               "the reference's) on the host, InitializePerturb from page-locked memory incl. the device-side "
+                               "repacks, one frame"}
+
     # ---- roofline -----------------------------------------------------------------------------------------------
     peaks = {"fp32": GPURenderer.MeasureFp32IssuePeak(local_rank), "fp64": GPURenderer.MeasureFp64IssuePeak(local_rank)}
     if rank == 0:
@@ -688,6 +705,8 @@ def main():
                 "sum_pixel_iters": total_sum}
         if e2e_as_is is not None:
             line["e2e_as_is"] = e2e_as_is
+        if first_frame is not None:
+            line["time_to_first_frame"] = first_frame
         if gather_ms is not None:
             line["gather_ms"] = gather_ms
             line["input_broadcast_ms"] = bcast_ms
