@@ -13,6 +13,10 @@
 #pragma once
 #include "fs_lav2.cuh"
 
+#ifndef FS_BLA_FAST
+#define FS_BLA_FAST 1
+#endif
+
 namespace fs {
 
 // reference wire record BLA<T> (BLA.h:7-14); natural alignment reproduces 44 / 88 / 48 / 24 bytes
@@ -52,6 +56,7 @@ template <class Num, class IterT> struct BlaArgs {
     TileQueue queue;
     unsigned long long *step_counter;
     int cycle_watch; // 1: cycle detection at rebase events (RebaseWatch), 0: every period is executed
+    int fast;        // HDRx32: 1 = select-free loop (bla_pixel_hdr32), 0 = reference-shaped operations (bla_pixel_hdr)
 };
 
 // device-side repack of one level: wire records -> heads + coefs
@@ -179,6 +184,157 @@ FS_D IterT bla_pixel_hdr(const BlaArgs<Num, IterT> &A, int X, int Y, unsigned lo
     return iter;
 }
 
+// ---- one pixel, float+exponent binary32, select-free ------------------------------------------------------------------
+// The same loop as bla_pixel_hdr with the float+exponent sums evaluated like the LAv2 kernel's perturbation step
+// (fs_perturb_loop.cuh hdr32fast): alignment scales BOTH operands -- one multiplier is exactly 1 -- so there are no operand
+// selects, Reduce() is bit surgery, and the reference's per-operation special cases are not evaluated per operation:
+//   * exact zeros (add/sub reset the exponent of a zero result, Reduce is a no-op on zero: HDRFloat.h:414-456, 974-1065):
+//     one product of the step's mantissas is tested;
+//   * operator+/- drop the smaller operand at an exponent gap >= 120 (HDRFloat.h:974-1000), the select-free form at 127:
+//     a gap in [120, 127) is read off the two multiplier fields (their sum is 128..134 exactly there);
+//   and a step or skip that meets either is recomputed by the reference-shaped operations of bla_pixel_hdr.  (The
+//   perturbation product custom_perturb2 uses the 127 rule itself, HDRFloat.h:725-794, and z = Z' + d' has a reduced,
+//   non-zero Z' as its large operand wherever the gap is that wide, so only the sums of getValue need the gap test.)
+// Profile of the reference-shaped loop on View 5 (profiles/r1_other_kernels_summary.md): ALU pipe 85 % busy with exactly
+// those selects and compares, FMA pipe 20 %.
+namespace blafast {
+using hdr32fast::align;
+using hdr32fast::reduce_nz;
+using hdr32fast::reduce_pos;
+
+// (a.m, a.e) + (b.m, b.e) like hdr32fast::align, also reporting an exponent gap in [120, 127)
+FS_D float align_g(float am, int ae, float bm, int be, int &E, bool &gap) {
+    const int fa = __viaddmin_s32_relu(ae - be, 127, 127);
+    const int fb = __viaddmin_s32_relu(be - ae, 127, 127);
+    gap = gap || (unsigned)(fa + fb - 128) < 7u;
+    E = max(ae, be);
+    return __fmaf_rn(bm, __int_as_float(fb << 23), am * __int_as_float(fa << 23));
+}
+} // namespace blafast
+
+template <class IterT, bool Count>
+FS_D IterT bla_pixel_hdr32(const BlaArgs<NumHdr<float>, IterT> &A, int X, int Y, unsigned long long &steps) {
+    using namespace blafast;
+    using Num = NumHdr<float>;
+    using Real = Hdr<float>;
+    const uint4 *__restrict__ orb = reinterpret_cast<const uint4 *>(A.orbit);
+    IterT iter = 0, Ref = 0;
+    const Real cX = Num::delta_x(A.dx, X, A.centerX);
+    const Real cY = Num::delta_y(A.dy, Y, A.centerY);
+    Real dX = Num::zero(), dY = Num::zero(), dn = Num::zero();
+    const IterT count = A.orbit_count;
+    RebaseWatch<Real, IterT, 3> watch(A.cycle_watch != 0);
+
+    while (iter < A.n_iterations) {
+        if (Ref == 0 && iter != 0 && watch.armed) {
+            const Real state[3] = {dX, dY, dn};
+            iter += watch.at_rebase(state, iter, A.n_iterations);
+        }
+        // ---- one perturbation step (BLAKernels.cuh:300-360), as hdr32fast::step evaluates it ----
+        const uint4 z = __ldg(orb + Ref);
+        ++Ref;
+        const uint4 zn = __ldg(orb + Ref);
+        Real nX, nY, tX, tY, n2, d2;
+        {
+            const float zxm = __uint_as_float(z.x), zym = __uint_as_float(z.w);
+            int s2e, s1e;
+            const float s2m = align(zxm, (int)z.y + 1, dX.m, dX.e, s2e); // 2Zx + dx
+            const float s1m = align(zym, (int)z.z + 1, dY.m, dY.e, s1e); // 2Zy + dy
+            const float pXa = dX.m * s2m, pXb = dY.m * s1m;
+            int eX, eY;
+            const float sumX = align(pXa, dX.e + s2e, -pXb, dY.e + s1e, eX);
+            nX.m = align(sumX, eX, cX.m, cX.e, nX.e);
+            const float pYa = dX.m * s1m, pYb = dY.m * s2m;
+            const float sumY = align(pYa, dX.e + s1e, pYb, dY.e + s2e, eY);
+            nY.m = align(sumY, eY, cY.m, cY.e, nY.e);
+            const float nz_guard = nX.m * nY.m;
+            reduce_nz(nX.m, nX.e);
+            reduce_nz(nY.m, nY.e);
+            tX.m = align(__uint_as_float(zn.x), (int)zn.y, nX.m, nX.e, tX.e);
+            tY.m = align(__uint_as_float(zn.w), (int)zn.z, nY.m, nY.e, tY.e);
+            const float sqx = tX.m * tX.m, sqy = tY.m * tY.m;
+            n2.m = align(sqx, tX.e + tX.e, sqy, tY.e + tY.e, n2.e);
+            reduce_pos(n2.m, n2.e);
+            const float sdx = nX.m * nX.m, sdy = nY.m * nY.m;
+            d2.m = align(sdx, nX.e + nX.e, sdy, nY.e + nY.e, d2.e);
+            reduce_pos(d2.m, d2.e);
+            // one test for every exact-zero special case of the reference
+            if (((pXa * pXb) * (sqx * sqy)) * nz_guard == 0.0f) {
+                Real zx{zxm, (int)z.y}, zy{zym, (int)z.z};
+                nX = dX; nY = dY;
+                Num::perturb(nX, nY, zx, zy, cX, cY);
+                tX = add(Real{__uint_as_float(zn.x), (int)zn.y}, nX);
+                tY = add(Real{__uint_as_float(zn.w), (int)zn.z}, nY);
+                n2 = reduced(add(mul(tX, tX), mul(tY, tY)));
+                d2 = reduced(add(mul(nX, nX), mul(nY, nY)));
+            }
+        }
+        if (Count) steps++;
+        if (!(lt_bailout(n2) && iter < A.n_iterations)) break;
+        if (lt_pr(n2, d2) || Ref >= count - 1) {
+            dX = tX; dY = tY; dn = n2; Ref = 0;
+        } else {
+            dX = nX; dY = nY; dn = d2;
+        }
+        ++iter;
+        // ---- BLA skips (BLAKernels.cuh:362-430) ----
+        for (;;) {
+            BlaCoef<Num> b;
+            int l;
+            if (!bla_lookup<Num, IterT>(A, Ref, dn, b, l)) break;
+            const bool res1 = Ref + (IterT)l >= count;
+            const bool res2 = iter + (IterT)l >= A.n_iterations;
+            const bool res3 = Ref + (IterT)l < count - 1;
+            if (res1 || res2) break;
+            iter += (IterT)l;
+            Ref += (IterT)l;
+            {
+                // getValue  BLA.cuh:21-38:  nx = ((Ax dx - Ay dy) + Bx cx) - By cy ;  ny = ((Ax dy + Ay dx) + Bx cy) + By cx
+                bool gap = false;
+                const float p1 = b.Ax.m * dX.m, p2 = b.Ay.m * dY.m, p3 = b.Bx.m * cX.m, p4 = b.By.m * cY.m;
+                const float q1 = b.Ax.m * dY.m, q2 = b.Ay.m * dX.m, q3 = b.Bx.m * cY.m, q4 = b.By.m * cX.m;
+                const int eAx = b.Ax.e + dX.e, eAy = b.Ay.e + dY.e, eBx = b.Bx.e + cX.e, eBy = b.By.e + cY.e;
+                const int fAx = b.Ax.e + dY.e, fAy = b.Ay.e + dX.e, fBx = b.Bx.e + cY.e, fBy = b.By.e + cX.e;
+                int e1, e2, e3, g1, g2, g3;
+                const float s1 = align_g(p1, eAx, -p2, eAy, e1, gap);
+                const float s2 = align_g(s1, e1, p3, eBx, e2, gap);
+                const float s3 = align_g(s2, e2, -p4, eBy, e3, gap);
+                const float t1 = align_g(q1, fAx, q2, fAy, g1, gap);
+                const float t2 = align_g(t1, g1, q3, fBx, g2, gap);
+                const float t3 = align_g(t2, g2, q4, fBy, g3, gap);
+                // zero anywhere (products or sums), or a gap the reference treats differently: the reference-shaped form
+                const float zero_guard = (((p1 * p2) * (p3 * p4)) * ((q1 * q2) * (q3 * q4))) * (((s1 * s2) * s3) * ((t1 * t2) * t3));
+                if (gap || zero_guard == 0.0f || !(zero_guard == zero_guard)) {
+                    bla_get_value(b, dX, dY, cX, cY);
+                } else {
+                    dX.m = s3; dX.e = e3;
+                    dY.m = t3; dY.e = g3;
+                }
+            }
+            if (Count) steps++;
+            if (res3) {
+                const float sdx = dX.m * dX.m, sdy = dY.m * dY.m;
+                if (sdx * sdy == 0.0f) {
+                    dn = reduced(add(mul(dX, dX), mul(dY, dY)));
+                } else {
+                    dn.m = align(sdx, dX.e + dX.e, sdy, dY.e + dY.e, dn.e);
+                    reduce_pos(dn.m, dn.e);
+                }
+                continue;
+            }
+            // landed on the last orbit element: rebase (BLAKernels.cuh:395-426); reference-shaped (once per period)
+            Real zx, zy;
+            OrbitIO<Num>::load(A.orbit, Ref, zx, zy);
+            dX = add(zx, dX);
+            dY = add(zy, dY);
+            dn = reduced(add(mul(zx, zx), mul(zy, zy)));
+            Ref = 0;
+            break;
+        }
+    }
+    return iter;
+}
+
 // ---- one pixel, plain FP64: mandel_1x_double_perturb_bla  BLAKernels.cuh:17-168 ------------------------------
 template <class Num, class IterT, bool Count>
 FS_D IterT bla_pixel_plain(const BlaArgs<Num, IterT> &A, int X, int Y, unsigned long long &steps) {
@@ -254,7 +410,9 @@ __global__ void __launch_bounds__(256) bla_kernel(const BlaArgs<Num, IterT> A) {
         Y += lane >> 3;
         if (X < A.width && Y < A.height) {
             IterT iter;
-            if constexpr (Num::kHdr) iter = bla_pixel_hdr<Num, IterT, Count>(A, X, Y, steps);
+            if constexpr (Num::kHdr && sizeof(typename Num::Mant) == 4 && FS_BLA_FAST) {
+                iter = A.fast ? bla_pixel_hdr32<IterT, Count>(A, X, Y, steps) : bla_pixel_hdr<Num, IterT, Count>(A, X, Y, steps);
+            } else if constexpr (Num::kHdr) iter = bla_pixel_hdr<Num, IterT, Count>(A, X, Y, steps);
             else iter = bla_pixel_plain<Num, IterT, Count>(A, X, Y, steps);
             A.out[(size_t)Y * A.pitch + X] = iter;
         }

@@ -732,6 +732,7 @@ uint32_t launch_bla(fs_renderer *r, const fs_blas *blas, const void *dx, const v
     A.queue = render_queue(r);
     A.step_counter = r->count_steps ? r->step_counter : nullptr;
     A.cycle_watch = r->at_cycle ? 1 : 0;
+    A.fast = r->use_la2 ? 1 : 0; // the A/B switch of the select-free forms (fs_set_la_step2) covers this loop too
     begin_render(r);
     if (r->count_steps) { auto k = bla_kernel<Num, IterT, true>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }
     else { auto k = bla_kernel<Num, IterT, false>; k<<<resident_ctas(r, k), 256, 0, r->compute>>>(A); }

@@ -198,8 +198,10 @@ uint32_t fs_set_split_at(fs_renderer *r, int32_t enable);
  * ATInfo::PerformAT) and in the BLA kernels (state at rebase events); 0 = every pass / period is executed, as the
  * reference does.  Results are identical bit for bit. */
 uint32_t fs_set_at_cycle_detection(fs_renderer *r, int32_t enable);
-/* HDRx32 LAv2 with 32-bit iteration counts: 1 (default) = the LA walk runs on step-shaped records derived on the device
- * at upload (fs_la_step2.cuh); 0 = on the reference-shaped records.  Results are identical bit for bit. */
+/* Select-free forms of the HDRx32 kernels: 1 (default) = the LAv2 LA walk (32-bit iteration counts) runs on step-shaped
+ * records derived on the device at upload (fs_la_step2.cuh) and the BLA loop evaluates its float+exponent sums without
+ * operand selects (fs_bla.cuh bla_pixel_hdr32); 0 = the reference-shaped records / operators.  Results are identical bit
+ * for bit. */
 uint32_t fs_set_la_step2(fs_renderer *r, int32_t enable);
 /* HDRx32 LAv2: 1 = the lane-refill kernel (every warp keeps pools of pixels waiting for the LA walk and for
  * perturbation steps and refills idle lanes from them, fs_lav2_pool.cuh); 0 (default: measured faster) = one 8x4 tile

@@ -342,6 +342,31 @@ def test_bla_cycle_detection_skips_periods_not_results(view_id, w, h, alg, iter_
         assert steps[0] * 2 < steps[1], "View 14: interior pixels should settle long before 18,402 periods"
 
 
+@pytest.mark.parametrize("view_id,w,h,n_iter,iter_bytes", [
+    (5, 1920, 1080, None, 4), (14, 640, 360, None, 4), (1, 960, 540, None, 8), (19, 640, 360, 3000000, 4), (100, 640, 360, None, 4),
+])
+def test_select_free_bla_loop_equals_reference_shaped(view_id, w, h, n_iter, iter_bytes):
+    """A/B inside the library: the select-free HDRx32 BLA loop (bla_pixel_hdr32, default) and the loop on the
+    reference-shaped float+exponent operators give the same iteration buffer and execute the same steps."""
+    alg = A.GpuHDRx32PerturbedBLA
+    _, coords, orbit, table, n = cases.make_inputs(view_id, w, h, alg, n_iter, iter_bytes)
+    outs, steps = [], []
+    for fast in (True, False):
+        r = GPURenderer()
+        assert r.SetLaStep2(fast) == 0   # the switch of the select-free forms
+        assert r.InitializeMemory(w, h, 1, iter_bytes=iter_bytes) == 0
+        assert r.EnableStepCounter(True) == 0
+        r.ClearMemory()
+        assert r.RenderPerturbBLA(alg, orbit, table, coords, n) == 0
+        rc, it, _, red = r.RenderCurrent(n)
+        assert rc == 0
+        outs.append((it.copy(), red))
+        steps.append(r.ReadStepCounter())
+        r.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1] and steps[0] == steps[1]
+
+
 @pytest.mark.parametrize("view_id,w,h,alg,n_iter", [
     (14, 3840, 2160, A.GpuHDRx32PerturbedLAv2, None),
     (5, 1920, 1080, A.GpuHDRx32PerturbedLAv2, None),

@@ -68,6 +68,18 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         SWITCH = sys.argv[1]
     ok = True
+    if SWITCH == "blafast":
+        SWITCH = "la2"
+        ok &= run(5, A.GpuHDRx32PerturbedBLA, reps=2)
+        W, H = 1920, 1080
+        _orbits.clear()
+        ok &= run(14, A.GpuHDRx32PerturbedBLA, reps=2)
+        ok &= run(1, A.GpuHDRx32PerturbedBLA, reps=2)
+        ok &= run(19, A.GpuHDRx32PerturbedBLA, 3000000, reps=2)
+        ok &= run(100, A.GpuHDRx32PerturbedBLA, reps=2)
+        ok &= run(5, A.GpuHDRx32PerturbedBLA, iter_bytes=8, reps=2)
+        print("ALL IDENTICAL" if ok else "MISMATCH")
+        sys.exit(0 if ok else 1)
     if SWITCH == "bla":
         SWITCH = "cycle"
         W, H = 1920, 1080
