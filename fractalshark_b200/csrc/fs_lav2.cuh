@@ -42,7 +42,10 @@
 #define FS_AT_WATCH_EVERY_PASS 0
 #endif
 #ifndef FS_LA2_EARLY_LOADS
-#define FS_LA2_EARLY_LOADS 1
+#define FS_LA2_EARLY_LOADS 0
+#endif
+#ifndef FS_LA2_LDG256
+#define FS_LA2_LDG256 1
 #endif
 #ifndef FS_LA2_PREFETCH
 #define FS_LA2_PREFETCH 0
@@ -591,6 +594,14 @@ FS_D void lav2_stages_v2(const Lav2Args<NumHdr<float>, uint32_t> &A, const HdrC<
             asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(rp));
             asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w) : "l"(rp));
             asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+48];" : "=r"(q3.x), "=r"(q3.y), "=r"(q3.z), "=r"(q3.w) : "l"(rp));
+#elif FS_LA2_LDG256
+            // two 256-bit loads (sm_100 LDG.256): half the L1 wavefronts of four 128-bit ones when the lanes of the warp are
+            // on different records
+            uint4 q0, q1, q2, q3;
+            asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(rp));
+            asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];"
+                : "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w), "=r"(q3.x), "=r"(q3.y), "=r"(q3.z), "=r"(q3.w) : "l"(rp));
 #else
             const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
 #endif
