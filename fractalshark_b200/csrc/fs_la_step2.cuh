@@ -98,7 +98,8 @@ FS_HD bool step(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, 
     const float wr = fma_(dr, tr, -(di * ti)), wi = fma_(di, tr, dr * ti);
     if (!sane(abs_(wr) + abs_(wi))) return false;
     const uint32_t wb = f2u(max_(abs_(wr), abs_(wi)));
-    const float sc = u2f(0x7f000000u - (wb & 0x7f800000u)); // 2^-k: Reduce() of w
+    const float sc = u2f(0x7f000000u - (wb & 0x7f800000u));
+    const float nr = wr * sc, ni = wi * sc;
     // cheb(newdz) >= LAThreshold on (exponent, mantissa) pairs of reduced positive numbers = one signed 64-bit comparison
     // of exponent * 2^23 + mantissa field; the record carries the threshold in that form (th_key).  wb already holds the
     // larger part's own exponent field, so adding it to (de + te - 127) * 2^23 forms the key and the reduced exponent.
@@ -111,9 +112,9 @@ FS_HD bool step(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, 
     // Evaluate: dz' = newdz*ZCoeff + dc*CCoeff
     const float zr = u2f(q1.x), zi = u2f(q1.y);
     const float ccr = u2f(q2.x), cci = u2f(q2.y);
-    // newdz * ZCoeff with newdz = w * 2^-k: the power of two moves out of the product (every rounding is scale-invariant
-    // while the operands stay normal, which `sane` has established), so the product does not wait for the Reduce
-    const float pr = fma_(wr, zr, -(wi * zi)) * sc, pi = fma_(wi, zr, wr * zi) * sc;
+    // (newdz * ZCoeff is formed from the REDUCED newdz, as the reference does: moving 2^-k out of the product is not exact
+    // when the smaller component of an un-reduced w sits in the denormal range -- found by tests/…guards[3])
+    const float pr = fma_(nr, zr, -(ni * zi)), pi = fma_(ni, zr, nr * zi);
     const float qr = fma_(cr, ccr, -(ci * cci)), qi = fma_(ci, ccr, cr * cci);
     const int pe = nwe + (int)q1.z, qe = ce + (int)q2.z;
     const int d2 = pe - qe;

@@ -427,7 +427,7 @@ void lockstep_la2_fuzz(uint64_t count, uint64_t seed, uint64_t *out) {
         float m;
         const uint32_t frac = (uint32_t)(r >> 20) & 0x007fffffu;
         if (kind == 0) m = 0.0f;                                                         // exact zero
-        else if (kind == 1) m = fbits(((uint32_t)(127 - 1 - (unsigned)((r >> 8) & 63u)) << 23) | frac); // tiny: down to 2^-64
+        else if (kind == 1) m = fbits(((uint32_t)(127 - 1 - (unsigned)((r >> 8) % 126u)) << 23) | frac); // tiny: down to 2^-126
         else if (kind == 2) m = fbits(((uint32_t)(127 + 1 + (unsigned)((r >> 8) & 7u)) << 23) | frac);  // un-reduced, up to 2^8
         else if (kind == 3) m = fbits(0x3f800000u | ((r >> 50) & 1u ? 0x007fffffu : 0u));               // 1.0 or 2 - ulp
         else m = fbits(0x3f800000u | frac);                                                             // reduced [1, 2)
