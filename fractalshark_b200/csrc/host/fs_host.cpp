@@ -18,6 +18,13 @@
 #include <vector>
 
 #include <memory>
+#include <atomic>
+#include <chrono>
+#include <stdio.h>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include "../fs_types.cuh"
 #include "fs_gmp_min.h"
@@ -79,6 +86,9 @@ template <class M> struct HostHdr {
     static constexpr bool kHdr = true;
     static Real r_int(int v) { return h_from_int<M>(v); }
     static Real r_scale(Real a, float s) { return h_mul_scalar<M>(a, (M)s); }
+    using Scale = Real; // r_scale's factor as the HDRFloat it is converted to (HDRFloat.h:853-868), made once
+    static Scale r_scale_pre(float s) { return h_from_mant<M>((M)s); }
+    static Real r_scale_by(Real a, Scale s) { return mul(a, s); }
     static Real r_mul(Real a, Real b) { return mul(a, b); }
     static Real r_div(Real a, Real b) { return div(a, b); }
     static Real r_min(Real a, Real b) { return h_min_pr(a, b); }
@@ -114,6 +124,9 @@ template <class M> struct HostPlain {
     static constexpr bool kHdr = false;
     static Real r_int(int v) { return (M)v; }
     static Real r_scale(Real a, float s) { return a * (M)s; }
+    using Scale = M;
+    static Scale r_scale_pre(float s) { return (M)s; }
+    static Real r_scale_by(Real a, Scale s) { return a * s; }
     static Real r_mul(Real a, Real b) { return a * b; }
     static Real r_div(Real a, Real b) { return a / b; }
     static Real r_min(Real a, Real b) { return std::min(a, b); }
@@ -366,6 +379,78 @@ template <class N> void compute_orbit(const fsh_view *v, fsh_orbit *o, uint64_t 
 // --------------------------------------------------------------------------------------------
 // LA table construction (single-thread routine of the reference)
 // --------------------------------------------------------------------------------------------
+// A small persistent pool for the record-parallel phase of the table builders: threads are created once per process
+// (FS_HOST_THREADS, default min(hardware threads, 16)), a job is a function of an index range, the caller works too.
+class HostPool {
+  public:
+    static HostPool &get() { static HostPool p; return p; }
+    size_t threads() const { return workers.size() + 1; }
+    void run(size_t n, const std::function<void(size_t, size_t)> &fn) {
+        if (n == 0) return;
+        if (workers.empty() || n < 512) { fn(0, n); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = &fn;
+            total = n;
+            grain = std::max<size_t>(64, n / (threads() * 8));
+            next.store(0);
+            pending = workers.size();
+            generation++;
+        }
+        wake.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu);
+        done.wait(lk, [&] { return pending == 0; });
+        job = nullptr;
+    }
+
+  private:
+    HostPool() {
+        size_t want = std::thread::hardware_concurrency();
+        if (const char *e = getenv("FS_HOST_THREADS")) want = (size_t)atoi(e);
+        want = std::min<size_t>(std::max<size_t>(want, 1), 16);
+        for (size_t t = 1; t < want; t++) workers.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+            generation++;
+        }
+        wake.notify_all();
+        for (auto &t : workers) t.join();
+    }
+    void work() {
+        for (;;) {
+            const size_t lo = next.fetch_add(grain);
+            if (lo >= total) break;
+            (*job)(lo, std::min(total, lo + grain));
+        }
+    }
+    void loop() {
+        size_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                wake.wait(lk, [&] { return generation != seen; });
+                seen = generation;
+                if (stop) return;
+            }
+            work();
+            std::lock_guard<std::mutex> lk(mu);
+            if (--pending == 0) done.notify_one();
+        }
+    }
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable wake, done;
+    const std::function<void(size_t, size_t)> *job = nullptr;
+    std::atomic<size_t> next{0};
+    size_t total = 0, grain = 1, pending = 0, generation = 0;
+    bool stop = false;
+};
+template <class F> void parallel_for(size_t n, F &&fn) { HostPool::get().run(n, std::function<void(size_t, size_t)>(fn)); }
+
 template <class N, class IterT> struct LaBuilder {
     using Real = typename N::Real;
     using Cplx = typename N::Cplx;
@@ -467,6 +552,79 @@ template <class N, class IterT> struct LaBuilder {
     }
     LA la_comp(const LA &a, const LA &b) const { LA r = la_blank(); la_comp(a, r, b); return r; }
 
+    // ---- two-phase construction -------------------------------------------------------------------------------------
+    // Which orbit elements (stage 0) or previous-stage records (higher stages) end up in which record is decided by the
+    // MinMag chain alone: Step / Composite report "period detected" from min(|z|, MinMag) and DetectPeriod from |z| and
+    // MinMag (LAInfoDeep.h:135-157, 185-259, 294-381) -- ZCoeff, CCoeff and the thresholds never steer the walk.  So a
+    // stage runs in two phases: phase 1 walks CreateLAFromOrbit / CreateNewLAStage exactly as written, carrying only
+    // {Ref, MinMag} and noting for every record pushed where it starts and how many elements it absorbs (a run of
+    // consecutive indices); phase 2 builds each record from its note -- the same Step / Composite calls on the same
+    // operands in the same order, hence the same bytes (tests/test_table_construction.py compares them with the
+    // reference's own builder) -- on all host threads at once, the records being independent of each other.
+    struct Note { uint32_t kind; IterT first, count; }; // kind 0: LAInfoDeep(orbit[first]); 1: copy of previous-stage record
+                                                        // `first`; 2: LAInfoDeep(0); 3: already complete
+    // what phase 1 carries for the record under construction (the walk's `LA`), and what it leaves behind for phase 2
+    struct LAx { Real MinMag; Note n; IterT StepLength, NextStageLAIndex; };
+    std::vector<Note> notes; // notes of the records of the stage under construction
+    std::vector<Real> chebs; // Chebyshev norm of every orbit element: all that phase 1 of stage 0 reads
+    size_t stage_begin = 0;  // index of that stage's first record in `las`
+    typename N::Scale thr_stage0, thr_detect; // the two period-detection factors, converted once
+
+    LAx x_new_zero() const { return LAx{N::r_int(4), Note{2, 0, 0}, 0, 0}; } // LAInfoDeep(z): MinMag = 4 (LAInfoDeep.h:109-133)
+    LAx x_new_at(IterT i) const { return LAx{N::r_int(4), Note{0, i, 0}, 0, 0}; }
+    LAx x_copy_prev(IterT prev_idx, IterT j) const { return LAx{las[prev_idx + j].MinMag, Note{1, j, 0}, 0, 0}; }
+    // Step  LAInfoDeep.h:185-259, the MinMag part: one more orbit element (always a.n.first + a.n.count + 1)
+    bool x_step(const LAx &a, LAx &out, IterT i) const {
+        out.n = Note{a.n.kind, a.n.first, a.n.count + 1};
+        out.MinMag = N::r_min(chebs[i], a.MinMag);
+        return N::r_cmp(out.MinMag, N::r_scale_by(a.MinMag, thr_stage0)) < 0;
+    }
+    LAx x_step(const LAx &a, IterT i) const { LAx r = a; x_step(a, r, i); return r; }
+    bool x_detect(const LAx &a, Real cheb_z) const { // DetectPeriod  LAInfoDeep.h:135-157 (method 1)
+        return N::r_cmp(cheb_z, N::r_scale_by(a.MinMag, thr_detect)) < 0;
+    }
+    // Composite  LAInfoDeep.h:294-381, the MinMag part: one more previous-stage record, consecutive as well
+    bool x_comp(const LAx &a, LAx &out, const LA &b) const {
+        out.n = Note{a.n.kind, a.n.first, a.n.count + 1};
+        const Real temp = N::r_min(N::c_cheb(b.Ref), a.MinMag);
+        out.MinMag = N::r_min(temp, b.MinMag);
+        return N::r_cmp(temp, N::r_scale_by(a.MinMag, thr_detect)) < 0;
+    }
+    LAx x_comp(const LAx &a, const LA &b) const { LAx r = a; x_comp(a, r, b); return r; }
+    void x_push(const LAx &a) {
+        LA l = la_blank();
+        l.StepLength = a.StepLength; l.NextStageLAIndex = a.NextStageLAIndex;
+        las.push_back(l);
+        notes.push_back(a.n);
+    }
+    void x_push_done(const LA &a) { las.push_back(a); notes.push_back(Note{3, 0, 0}); }
+    void x_pop() { las.pop_back(); notes.pop_back(); }
+    // phase 2 of the stage whose records are las[stage_begin ...]; prev_idx = first record of the previous stage
+    void fill_stage(IterT prev_idx) {
+        const size_t n = notes.size();
+        auto job = [&](size_t lo, size_t hi) {
+            for (size_t k = lo; k < hi; k++) {
+                const Note nt = notes[k];
+                if (nt.kind == 3) continue;
+                LA &dst = las[stage_begin + k];
+                LA l;
+                if (nt.kind == 1) l = las[(size_t)prev_idx + nt.first];
+                else l = la_new(nt.kind == 2 ? N::c_zero() : orbit_at(nt.first));
+                for (IterT c = 1; c <= nt.count; c++) {
+                    LA nl = la_blank();
+                    if (nt.kind == 1) la_comp(l, nl, las[(size_t)prev_idx + nt.first + c]);
+                    else la_step(l, nl, orbit_at((nt.kind == 2 ? (IterT)0 : nt.first) + c));
+                    l = nl;
+                }
+                l.StepLength = dst.StepLength;
+                l.NextStageLAIndex = dst.NextStageLAIndex;
+                dst = l;
+            }
+        };
+        parallel_for(n, job);
+        notes.clear();
+    }
+
     IterT nth_root_period(double maxRef, double ratio) const {
         const double nth = round(log2(maxRef) / periodDivisor);
         return (IterT)round(pow(ratio, 1.0 / nth));
@@ -474,32 +632,48 @@ template <class N, class IterT> struct LaBuilder {
 
     // CreateLAFromOrbit  LAReference.cpp:28-207
     bool stage0(IterT maxRef) {
+        notes.clear();
+        stage_begin = las.size();
+        las.reserve((size_t)maxRef + 4); // the walk holds references into `las` across push_back
+        thr_stage0 = N::r_scale_pre(P.stage0_thr2);
+        thr_detect = N::r_scale_pre(P.thr2);
+        chebs.resize((size_t)maxRef + 1);
+        parallel_for(chebs.size(), [&](size_t lo, size_t hi) { for (size_t k = lo; k < hi; k++) chebs[k] = N::c_cheb(orbit_at(k)); });
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool ok = stage0_walk(maxRef);
+        const auto t1 = std::chrono::steady_clock::now();
+        fill_stage(0);
+        if (getenv("FS_LA_TIMING")) fprintf(stderr, "stage 0: walk %.3f ms, fill %.3f ms, %zu records\n", std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), las.size() - stage_begin);
+        return ok;
+    }
+    bool stage0_walk(IterT maxRef) {
         is_valid = false;
         stages.assign(MaxLAStages, WireStage<IterT>{0, 0});
         use_at = false;
         stage_count = 0;
         stages[0].LAIndex = 0;
         IterT Period = 0;
-        LA la = la_step(la_new(N::c_zero()), orbit_at(1));
+        // isZCoeffZero() of the first step needs the coefficient itself
+        if (N::c_is_zero(la_step(la_new(N::c_zero()), orbit_at(1)).ZCoeff)) return false;
+        LAx la = x_step(x_new_zero(), 1);
         IterT nextIdx = 0;
-        if (N::c_is_zero(la.ZCoeff)) return false;
         IterT i;
         for (i = 2; i < maxRef; i++) {
-            LA nl = la_blank();
-            if (!la_step(la, nl, orbit_at(i))) { la = nl; continue; }
+            LAx nl;
+            if (!x_step(la, nl, i)) { la = nl; continue; }
             Period = i;
             la.StepLength = Period; la.NextStageLAIndex = nextIdx;
-            las.push_back(la);
+            x_push(la);
             nextIdx = i;
-            if (i + 1 < maxRef) { la = la_step(la_new(orbit_at(i)), orbit_at(i + 1)); i += 2; }
-            else { la = la_new(orbit_at(i)); i += 1; }
+            if (i + 1 < maxRef) { la = x_step(x_new_at(i), i + 1); i += 2; }
+            else { la = x_new_at(i); i += 1; }
             break;
         }
         stage_count = 1;
         IterT PeriodBegin = Period, PeriodEnd = PeriodBegin + Period;
         if (Period == 0) {
             if (maxRef > (IterT)lowBound) {
-                la = la_step(la_new(orbit_at(0)), orbit_at(1));
+                la = x_step(x_new_at(0), 1);
                 nextIdx = 0;
                 i = 2;
                 Period = nth_root_period((double)maxRef, (double)maxRef);
@@ -507,14 +681,14 @@ template <class N, class IterT> struct LaBuilder {
                 PeriodEnd = Period;
             } else {
                 la.StepLength = maxRef; la.NextStageLAIndex = nextIdx;
-                las.push_back(la);
-                las.push_back(la_new(orbit_at(maxRef)));
+                x_push(la);
+                x_push_done(la_new(orbit_at(maxRef)));
                 stages[0].MacroItCount = 1;
                 return false;
             }
         } else if (Period > (IterT)lowBound) {
-            las.pop_back();
-            la = la_step(la_new(orbit_at(0)), orbit_at(1));
+            x_pop();
+            la = x_step(x_new_at(0), 1);
             nextIdx = 0;
             i = 2;
             Period = nth_root_period((double)maxRef, (double)maxRef);
@@ -522,63 +696,75 @@ template <class N, class IterT> struct LaBuilder {
             PeriodEnd = Period;
         }
         for (; i < maxRef; i++) {
-            LA nl = la_blank();
-            const bool det = la_step(la, nl, orbit_at(i));
+            LAx nl;
+            const bool det = x_step(la, nl, i);
             if (!det && i < PeriodEnd) { la = nl; continue; }
             la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
-            las.push_back(la);
+            x_push(la);
             nextIdx = i;
             PeriodBegin = i;
             PeriodEnd = PeriodBegin + Period;
             const IterT ip1 = i + 1;
-            const bool detected = la_detect(nl, orbit_at(ip1));
+            const bool detected = x_detect(nl, chebs[ip1]);
             if (detected || ip1 >= maxRef) {
-                la = la_new(orbit_at(i));
+                la = x_new_at(i);
             } else {
-                la = la_step(la_new(orbit_at(i)), orbit_at(ip1));
+                la = x_step(x_new_at(i), ip1);
                 i++;
             }
         }
         la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
-        las.push_back(la);
+        x_push(la);
         stages[0].MacroItCount = (IterT)las.size();
         LA la2 = la_new(orbit_at(maxRef));
         la2.StepLength = 0; la2.NextStageLAIndex = 0;
-        las.push_back(la2);
+        x_push_done(la2);
         return true;
     }
 
     // CreateNewLAStage  LAReference.cpp:774-968
     bool next_stage(IterT maxRef) {
+        if (stage_count >= (IterT)MaxLAStages) return false;
+        notes.clear();
+        stage_begin = las.size();
+        las.reserve(las.size() + (size_t)stages[stage_count - 1].MacroItCount + 4); // references into `las` stay valid
+        const IterT prev_idx = stages[stage_count - 1].LAIndex;
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool ok = next_stage_walk(maxRef);
+        const auto t1 = std::chrono::steady_clock::now();
+        fill_stage(prev_idx);
+        if (getenv("FS_LA_TIMING")) fprintf(stderr, "stage %d: walk %.3f ms, fill %.3f ms, %zu records\n", (int)stage_count - 1, std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), las.size() - stage_begin);
+        return ok;
+    }
+    bool next_stage_walk(IterT maxRef) {
         const IterT PrevStage = stage_count - 1, CurrentStage = stage_count;
-        if (CurrentStage >= (IterT)MaxLAStages) return false;
         const IterT PrevIdx = stages[PrevStage].LAIndex;
         const IterT PrevCount = stages[PrevStage].MacroItCount;
         const LA PrevLA = las[PrevIdx];
         const LA PrevLAp1 = las[PrevIdx + 1];
         IterT Period = 0;
         stages[CurrentStage].LAIndex = (IterT)las.size();
-        LA la = la_comp(PrevLA, PrevLAp1);
+        LAx la = x_comp(x_copy_prev(PrevIdx, 0), PrevLAp1);
         IterT nextIdx = 0;
         IterT i = PrevLA.StepLength + PrevLAp1.StepLength;
         IterT j;
         for (j = 2; j < PrevCount; j++) {
-            LA nl = la_blank();
-            const LA Pj = las[PrevIdx + j];
-            const bool det = la_comp(la, nl, Pj);
+            LAx nl;
+            const LA &Pj = las[PrevIdx + j];
+            const bool det = x_comp(la, nl, Pj);
             if (det) {
                 if (N::r_is_zero(Pj.LAThreshold)) break;
                 Period = i;
                 la.StepLength = Period; la.NextStageLAIndex = nextIdx;
-                las.push_back(la);
+                x_push(la);
                 nextIdx = j;
-                const LA Pjp1 = las[PrevIdx + j + 1];
-                if (la_detect(nl, Pjp1.Ref) || j + 1 >= PrevCount) {
-                    la = Pj;
+                const LA &Pjp1 = las[PrevIdx + j + 1];
+                if (x_detect(nl, N::c_cheb(Pjp1.Ref)) || j + 1 >= PrevCount) {
+                    la = x_copy_prev(PrevIdx, j);
                     i += Pj.StepLength;
                     j++;
                 } else {
-                    la = la_comp(Pj, Pjp1);
+                    la = x_comp(x_copy_prev(PrevIdx, j), Pjp1);
                     i += Pj.StepLength + Pjp1.StepLength;
                     j += 2;
                 }
@@ -591,7 +777,7 @@ template <class N, class IterT> struct LaBuilder {
         IterT PeriodBegin = Period, PeriodEnd = PeriodBegin + Period;
         if (Period == 0) {
             if (maxRef > PrevLA.StepLength * (IterT)lowBound) {
-                la = la_comp(PrevLA, PrevLAp1);
+                la = x_comp(x_copy_prev(PrevIdx, 0), PrevLAp1);
                 i = PrevLA.StepLength + PrevLAp1.StepLength;
                 nextIdx = 0;
                 j = 2;
@@ -601,16 +787,16 @@ template <class N, class IterT> struct LaBuilder {
                 PeriodEnd = Period;
             } else {
                 la.StepLength = maxRef; la.NextStageLAIndex = nextIdx;
-                las.push_back(la);
+                x_push(la);
                 LA la2 = la_new(orbit_at(maxRef));
                 la2.StepLength = 0; la2.NextStageLAIndex = 0;
-                las.push_back(la2);
+                x_push_done(la2);
                 stages[CurrentStage].MacroItCount = 1;
                 return false;
             }
         } else if (Period > PrevLA.StepLength * (IterT)lowBound) {
-            las.pop_back();
-            la = la_comp(PrevLA, PrevLAp1);
+            x_pop();
+            la = x_comp(x_copy_prev(PrevIdx, 0), PrevLAp1);
             i = PrevLA.StepLength + PrevLAp1.StepLength;
             nextIdx = 0;
             j = 2;
@@ -620,20 +806,20 @@ template <class N, class IterT> struct LaBuilder {
             PeriodEnd = Period;
         }
         for (; j < PrevCount; j++) {
-            LA nl = la_blank();
-            const LA Pj = las[PrevIdx + j];
-            const bool det = la_comp(la, nl, Pj);
+            LAx nl;
+            const LA &Pj = las[PrevIdx + j];
+            const bool det = x_comp(la, nl, Pj);
             if (det || i >= PeriodEnd) {
                 la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
-                las.push_back(la);
+                x_push(la);
                 nextIdx = j;
                 PeriodBegin = i;
                 PeriodEnd = PeriodBegin + Period;
-                const LA Pjp1 = las[PrevIdx + j + 1];
-                if (la_detect(nl, Pjp1.Ref) || j + 1 >= PrevCount) {
-                    la = Pj;
+                const LA &Pjp1 = las[PrevIdx + j + 1];
+                if (x_detect(nl, N::c_cheb(Pjp1.Ref)) || j + 1 >= PrevCount) {
+                    la = x_copy_prev(PrevIdx, j);
                 } else {
-                    la = la_comp(Pj, Pjp1);
+                    la = x_comp(x_copy_prev(PrevIdx, j), Pjp1);
                     i += las[PrevIdx + j].StepLength;
                     j++;
                 }
@@ -643,11 +829,11 @@ template <class N, class IterT> struct LaBuilder {
             i += las[PrevIdx + j].StepLength;
         }
         la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
-        las.push_back(la);
+        x_push(la);
         stages[CurrentStage].MacroItCount = (IterT)las.size() - stages[CurrentStage].LAIndex;
         LA la2 = la_new(orbit_at(maxRef));
         la2.StepLength = 0; la2.NextStageLAIndex = 0;
-        las.push_back(la2);
+        x_push_done(la2);
         return true;
     }
 
