@@ -1239,16 +1239,19 @@ template <class N> struct BlaBuilder {
         if (lm2 < 0) lm2 = 0;
         if (kFirst >= per_level.size()) return;
         for (size_t l = kFirst; l < B.size(); l++) B[l].resize(per_level[l]);
-        for (size_t i = 1; i < per_level[kFirst] + 1; i++) B[kFirst][i - 1] = l_step(kFirst, i);
+        // every record of a level depends on the level below only: record-parallel on the host pool (same calls, same bytes)
+        parallel_for(per_level[kFirst], [&](size_t lo, size_t hi) { for (size_t i = lo + 1; i < hi + 1; i++) B[kFirst][i - 1] = l_step(kFirst, i); });
         // Merge  BLAS.cpp:160-210
         size_t src = kFirst;
         const size_t max_level = per_level.size() - 1;
         for (size_t n_src = per_level[src]; src < max_level && n_src > 1; src++) {
             const size_t n_dst = per_level[src + 1];
-            for (size_t i = 0; i < n_dst; i++) {
-                const size_t mx = i << 1, my = mx + 1;
-                B[src + 1][i] = my < n_src ? merge(B[src][mx], B[src][my]) : B[src][mx];
-            }
+            parallel_for(n_dst, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; i++) {
+                    const size_t mx = i << 1, my = mx + 1;
+                    B[src + 1][i] = my < n_src ? merge(B[src][mx], B[src][my]) : B[src][mx];
+                }
+            });
             n_src = n_dst;
         }
     }
