@@ -9,6 +9,9 @@
 // tail; LA records and orbit elements are repacked to 16-byte-aligned records and fetched with
 // 128-bit loads; all exponent alignment is integer ALU work (no MUFU).  The reference launches one
 // 16x8 CTA per screen block with 32-bit field loads and scalbnf-based alignment.
+// Round 2: the AT shortcut stops executing passes once a pixel's state repeats exactly (CycleWatch in fs_at_fast.cuh,
+// StateWatch below: interior pixels, 97 % of the AT passes of View 14), and the HDRx32 / 32-bit LA walk runs on
+// step-shaped 64-byte records fetched with two 256-bit loads (fs_la_step2.cuh, lav2_stages_v2).
 #pragma once
 #include "fs_num.cuh"
 #include "fs_df32.cuh"
