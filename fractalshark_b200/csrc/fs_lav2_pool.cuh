@@ -29,6 +29,10 @@
 #ifndef FS_POOL_MIN_CTAS
 #define FS_POOL_MIN_CTAS 4
 #endif
+#ifndef FS_POOL_TILE_LA
+#define FS_POOL_TILE_LA 0 // 1: LA walk per tile (lav2_stages_v2), only the perturbation tail is pooled (View 14: 4.35 ms against 5.59
+                          // with both pooled and 4.19 for the tile kernel); 0: both pooled
+#endif
 #ifndef FS_POOL_LA_FAST
 #define FS_POOL_LA_FAST 1 // 1: select-free LA step (fs_la_fast.cuh) with the as-written step as its fallback; 0: as-written only
 #endif
@@ -415,14 +419,37 @@ __global__ void __launch_bounds__(256, FS_POOL_MIN_CTAS) lav2_pool_kernel(const 
                     pool::put<IterT>(P.po, slot, e);
                 }
             } else {
-                if (live) {
-                    const Real dcX = Num::delta_x(A.dx, X, A.centerX);
-                    const Real dcY = Num::delta_y(A.dy, Y, A.centerY);
-                    const Cplx dc = Num::c_make(dcX, dcY);
-                    lav2_at<Num, IterT, Count>(A, dc, dz, iter, P.steps_at);
+                const Real dcX = Num::delta_x(A.dx, X, A.centerX);
+                const Real dcY = Num::delta_y(A.dy, Y, A.centerY);
+                const Cplx dc = Num::c_make(dcX, dcY);
+                if (live) lav2_at<Num, IterT, Count>(A, dc, dz, iter, P.steps_at);
+#if FS_POOL_TILE_LA
+                // hybrid: the LA walk stays with the tile (its lanes share records: one L1 wavefront per load), only the
+                // perturbation tail is pooled
+                IterT RefIteration = 0;
+                if constexpr (sizeof(IterT) == 4) {
+                    if (live && iter < A.n_iterations && A.las2 != nullptr) lav2_stages_v2<Count>(A, dc, dz, RefIteration, iter, P.steps_la);
+                    else if (live && iter < A.n_iterations) lav2_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, P.steps_la);
+                } else {
+                    if (live && iter < A.n_iterations) lav2_stages<Num, IterT, Count>(A, dc, dz, RefIteration, iter, P.steps_la);
                 }
+                const bool to_po = live && Mode == Lav2Mode::Full && iter < A.n_iterations;
+                if (live && !to_po) pool::store_pixel<IterT>(A, pix, iter);
+                {
+                    const int pslot = pool::push_slot(to_po, P.po_cnt, P.lt);
+                    if (to_po) {
+                        pool::Entry<IterT> e;
+                        e.pix = pix;
+                        e.a = __float_as_uint(dz.re); e.b = (uint32_t)dz.e; e.c = __float_as_uint(dz.im); e.d = (uint32_t)dz.e;
+                        e.ref = RefIteration; e.iter = iter;
+                        pool::put<IterT>(P.po, pslot, e);
+                    }
+                }
+                const bool to_la = false;
+#else
                 const bool to_la = live && iter < A.n_iterations;
                 if (live && !to_la) pool::store_pixel<IterT>(A, pix, iter);
+#endif
                 const int slot = pool::push_slot(to_la, P.la_cnt, P.lt);
                 if (to_la) {
                     pool::Entry<IterT> e;
