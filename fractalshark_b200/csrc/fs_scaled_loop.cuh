@@ -46,7 +46,10 @@ struct alignas(16) FastElem {
 };
 constexpr float kThExact = 0.0f, kThZero = -1.0f, kThTiny = -2.0f;
 
-constexpr int kChunk = 16;        // speculative steps per commit
+#ifndef FS_PO_CHUNK
+#define FS_PO_CHUNK 16
+#endif
+constexpr int kChunk = FS_PO_CHUNK; // speculative steps per commit
 constexpr int kNorm = 16;         // (re)normalisation puts |w|_inf into [2^16, 2^17)
 constexpr float kLo = 0x1p-6f;    // every component of every committed w must be >= kLo ...
 constexpr float kLoWarn = 0x1p0f; // ... and a chunk that came this close re-centres w before the next one
