@@ -221,8 +221,13 @@ struct fsh_blas {
 
 struct fsh_la {
     std::vector<unsigned char> las, stages, at;
+    void *las_own = nullptr; // the builder's own record array, taken over as is (no copy); nullptr: `las` holds the records
     uint64_t num_las = 0, num_stages = 0, stage_count = 0;
     int use_at = 0, is_valid = 0;
+    fsh_la() = default;
+    fsh_la(const fsh_la &) = delete;
+    fsh_la &operator=(const fsh_la &) = delete;
+    ~fsh_la() { free(las_own); }
 };
 
 namespace {
@@ -385,26 +390,53 @@ class HostPool {
   public:
     static HostPool &get() { static HostPool p; return p; }
     size_t threads() const { return workers.size() + 1; }
-    void run(size_t n, const std::function<void(size_t, size_t)> &fn) {
+    // min_grain: indices per claim at least; heavy items (a record of an upper LA stage is a chain of tens of composites)
+    // want a small one, and are worth the threads from a few dozen items on
+    void run(size_t n, const std::function<void(size_t, size_t)> &fn, size_t min_grain = 64) {
         if (n == 0) return;
-        if (workers.empty() || n < 512) { fn(0, n); return; }
+        if (workers.empty() || n < 8 * min_grain) { fn(0, n); return; }
+        dispatch(n, std::max<size_t>(min_grain, n / (threads() * 8)), fn);
+    }
+    // n tasks, one index each, claimed in index order; a task may wait for a task with a smaller index (which some thread
+    // has claimed before and runs to completion), never for a larger one.  Without workers they run one after the other.
+    void run_tasks(size_t n, const std::function<void(size_t, size_t)> &fn) {
+        if (n == 0) return;
+        if (workers.empty()) { for (size_t k = 0; k < n; k++) fn(k, k + 1); return; }
+        dispatch(n, 1, fn);
+    }
+
+  private:
+    void dispatch(size_t n, size_t g, const std::function<void(size_t, size_t)> &fn) {
         {
             std::lock_guard<std::mutex> lk(mu);
             job = &fn;
             total = n;
-            grain = std::max<size_t>(64, n / (threads() * 8));
+            grain = g;
             next.store(0);
             pending = workers.size();
+            left.store(pending, std::memory_order_relaxed);
             generation++;
+            posted.store(generation, std::memory_order_release);
         }
         wake.notify_all();
         work();
+        // the caller spins as well: the jobs of one build are tens of microseconds long
+        for (int spin = 0; spin < kSpin; spin++) {
+            if (left.load(std::memory_order_acquire) == 0) break;
+            cpu_relax(spin);
+        }
         std::unique_lock<std::mutex> lk(mu);
         done.wait(lk, [&] { return pending == 0; });
         job = nullptr;
     }
-
-  private:
+    // a few hundred pauses, then yields: with fewer cores than threads the thread being waited for gets the core
+    static void cpu_relax(int spin) {
+#if defined(__x86_64__) || defined(__i386__)
+        if (spin < 256) { __builtin_ia32_pause(); return; }
+#endif
+        std::this_thread::yield();
+    }
+    static constexpr int kSpin = 1500;
     HostPool() {
         size_t want = std::thread::hardware_concurrency();
         if (const char *e = getenv("FS_HOST_THREADS")) want = (size_t)atoi(e);
@@ -430,6 +462,12 @@ class HostPool {
     void loop() {
         size_t seen = 0;
         for (;;) {
+            // the jobs of one table build follow each other within microseconds: look for the next one for a while before
+            // going to sleep on the condition variable (a wake-up through the futex costs more than most of these jobs)
+            for (int spin = 0; spin < kSpin; spin++) {
+                if (posted.load(std::memory_order_acquire) != seen) break;
+                cpu_relax(spin);
+            }
             {
                 std::unique_lock<std::mutex> lk(mu);
                 wake.wait(lk, [&] { return generation != seen; });
@@ -437,6 +475,7 @@ class HostPool {
                 if (stop) return;
             }
             work();
+            left.fetch_sub(1, std::memory_order_release);
             std::lock_guard<std::mutex> lk(mu);
             if (--pending == 0) done.notify_one();
         }
@@ -445,11 +484,45 @@ class HostPool {
     std::mutex mu;
     std::condition_variable wake, done;
     const std::function<void(size_t, size_t)> *job = nullptr;
-    std::atomic<size_t> next{0};
+    std::atomic<size_t> next{0}, posted{0}, left{0};
     size_t total = 0, grain = 1, pending = 0, generation = 0;
     bool stop = false;
 };
-template <class F> void parallel_for(size_t n, F &&fn) { HostPool::get().run(n, std::function<void(size_t, size_t)>(fn)); }
+template <class F> void parallel_for(size_t n, F &&fn, size_t min_grain = 64) { HostPool::get().run(n, std::function<void(size_t, size_t)>(fn), min_grain); }
+
+// Array of trivially copyable records in uninitialised storage (no value-initialisation pass over megabytes that are about
+// to be overwritten), which can hand its allocation to the object that outlives the builder.
+template <class T> struct RawVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    RawVec() = default;
+    RawVec(const RawVec &) = delete;
+    RawVec &operator=(const RawVec &) = delete;
+    ~RawVec() { free(p); }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    void reserve(size_t c) {
+        if (c <= cap) return;
+        T *q = static_cast<T *>(malloc(c * sizeof(T)));
+        if (!q) throw std::bad_alloc();
+        if (n) memcpy(static_cast<void *>(q), p, n * sizeof(T));
+        free(p);
+        p = q;
+        cap = c;
+    }
+    void push_back(const T &v) {
+        if (n == cap) reserve(cap ? cap * 2 : 64);
+        p[n++] = v;
+    }
+    void pop_back() { n--; }
+    void clear() { n = 0; }
+    void resize_uninit(size_t c) { reserve(c); n = c; }
+    T *release() { T *q = p; p = nullptr; n = cap = 0; return q; }
+};
 
 template <class N, class IterT> struct LaBuilder {
     using Real = typename N::Real;
@@ -463,7 +536,7 @@ template <class N, class IterT> struct LaBuilder {
     const fsh_orbit *orbit;
     bool small_exp = false; // UseSmallExponents: true when the table is destined for a 2x32 type (RefOrbitCalc.cpp:2329-2346)
     LaParams P;
-    std::vector<LA> las;
+    RawVec<LA> las;
     std::vector<WireStage<IterT>> stages;
     AT at;
     bool use_at = false, is_valid = false;
@@ -564,18 +637,19 @@ template <class N, class IterT> struct LaBuilder {
     struct Note { uint32_t kind; IterT first, count; }; // kind 0: LAInfoDeep(orbit[first]); 1: copy of previous-stage record
                                                         // `first`; 2: LAInfoDeep(0); 3: already complete
     // what phase 1 carries for the record under construction (the walk's `LA`), and what it leaves behind for phase 2
-    struct LAx { Real MinMag; Note n; IterT StepLength, NextStageLAIndex; };
+    struct LAx { Real MinMag; Note n; IterT StepLength, NextStageLAIndex; Real chebRef; }; // chebRef: pipelined walks only
     std::vector<Note> notes; // notes of the records of the stage under construction
     std::vector<Real> chebs; // Chebyshev norm of every orbit element: all that phase 1 of stage 0 reads
     size_t stage_begin = 0;  // index of that stage's first record in `las`
     typename N::Scale thr_stage0, thr_detect; // the two period-detection factors, converted once
 
-    LAx x_new_zero() const { return LAx{N::r_int(4), Note{2, 0, 0}, 0, 0}; } // LAInfoDeep(z): MinMag = 4 (LAInfoDeep.h:109-133)
-    LAx x_new_at(IterT i) const { return LAx{N::r_int(4), Note{0, i, 0}, 0, 0}; }
-    LAx x_copy_prev(IterT prev_idx, IterT j) const { return LAx{las[prev_idx + j].MinMag, Note{1, j, 0}, 0, 0}; }
+    LAx x_new_zero() const { return LAx{N::r_int(4), Note{2, 0, 0}, 0, 0, N::c_cheb(N::c_zero())}; } // LAInfoDeep(z): MinMag = 4 (LAInfoDeep.h:109-133)
+    LAx x_new_at(IterT i) const { return LAx{N::r_int(4), Note{0, i, 0}, 0, 0, chebs[i]}; }
+    LAx x_copy_prev(IterT prev_idx, IterT j) const { return LAx{las[prev_idx + j].MinMag, Note{1, j, 0}, 0, 0, Real{}}; }
     // Step  LAInfoDeep.h:185-259, the MinMag part: one more orbit element (always a.n.first + a.n.count + 1)
     bool x_step(const LAx &a, LAx &out, IterT i) const {
         out.n = Note{a.n.kind, a.n.first, a.n.count + 1};
+        out.chebRef = a.chebRef;
         out.MinMag = N::r_min(chebs[i], a.MinMag);
         return N::r_cmp(out.MinMag, N::r_scale_by(a.MinMag, thr_stage0)) < 0;
     }
@@ -586,6 +660,7 @@ template <class N, class IterT> struct LaBuilder {
     // Composite  LAInfoDeep.h:294-381, the MinMag part: one more previous-stage record, consecutive as well
     bool x_comp(const LAx &a, LAx &out, const LA &b) const {
         out.n = Note{a.n.kind, a.n.first, a.n.count + 1};
+        out.chebRef = a.chebRef;
         const Real temp = N::r_min(N::c_cheb(b.Ref), a.MinMag);
         out.MinMag = N::r_min(temp, b.MinMag);
         return N::r_cmp(temp, N::r_scale_by(a.MinMag, thr_detect)) < 0;
@@ -837,6 +912,428 @@ template <class N, class IterT> struct LaBuilder {
         return true;
     }
 
+
+    // ---- pipelined construction -------------------------------------------------------------------------------------
+    // The walk of stage k + 1 reads three things of a stage-k record: |Ref| (Chebyshev norm), MinMag and StepLength -- all
+    // of them products of stage k's own walk -- plus, once per stage, "is LAThreshold of this record zero"
+    // (LAReference.cpp:829-833), which only the fill knows.  So the walks of all stages run at the same time, each one or
+    // two records behind the walk below it (one thread per stage, records handed over through a published count), on
+    // slim records {MinMag, |Ref|, StepLength, NextStage, note}; the one LAThreshold question is answered "not zero" on
+    // the spot and checked when the fills are done (zero: the table is rebuilt by the stage-after-stage path above).
+    // Stage 0's records are filled by the remaining threads while its walk is still going.  Same walk, same notes, same
+    // fill calls as the two-phase form: same bytes (tests/test_table_construction.py runs both against the reference).
+    struct Slim { Real MinMag, chebRef; IterT StepLength, NextStage; Note n; };
+    static constexpr size_t kMaxPipelinedStages = 12;
+    // (the words other threads poll sit on cache lines of their own: a store to a line that a dozen cores are reading costs
+    // the storing core a coherence round trip each time -- with one line for everything and a publish per record the
+    // pipelined build took 6 ms where the stage-after-stage one takes 2)
+    struct alignas(64) Walk {
+        alignas(64) std::atomic<size_t> pub{0}; // rec[0 .. pub) are final (regular records: a further record follows each)
+        alignas(64) std::atomic<int> follow{0}; // 0 undecided, 1 a next stage follows this one, 2 this is the last stage
+        std::atomic<int> done{0};               // 1: rec[0 .. count] complete (count regular records and the closing one)
+        alignas(64) Slim *rec = nullptr;
+        size_t count = 0, n_rec = 0; // MacroItCount; records in rec[] (count regular ones and the closing one)
+        long long spec = -1;         // previous-stage record whose LAThreshold the walk took to be non-zero
+        bool ran = false, ok = false;
+        double t_begin = 0, t_end = 0; // FS_LA_TIMING: the walk's start and end, ms after the build's start
+    };
+    // The walks' record arrays live as long as the process: a fresh 4 MB allocation per stage and build is a page fault per
+    // 4 KB written (0.5 ms of a 1 ms walk on the 16-core box, more than the walk's arithmetic).  One build at a time.
+    struct Scratch {
+        std::mutex mu;
+        Slim *rec[kMaxPipelinedStages] = {};
+        size_t cap[kMaxPipelinedStages] = {};
+        Slim *get(size_t k, size_t n) {
+            if (cap[k] < n) {
+                free(rec[k]);
+                rec[k] = static_cast<Slim *>(malloc(n * sizeof(Slim)));
+                if (!rec[k]) { cap[k] = 0; throw std::bad_alloc(); }
+                cap[k] = n;
+            }
+            return rec[k];
+        }
+        ~Scratch() { for (auto *r : rec) free(r); }
+    };
+    static Scratch &scratch() { static Scratch s; return s; }
+    // waiting for another thread's progress: a few pauses, then yields (with fewer cores than threads the thread being
+    // waited for must get the core)
+    struct Backoff {
+        int n = 0;
+        void operator()() {
+#if defined(__x86_64__) || defined(__i386__)
+            if (n < 64) { n++; __builtin_ia32_pause(); return; }
+#endif
+            std::this_thread::yield();
+        }
+    };
+    // the walk of the stage above P, as a reader of P's records
+    struct Reader {
+        const Walk &P;
+        size_t seen = 0; // last value of P.pub this thread has loaded
+        // may previous-stage index j be evaluated (reads records j and j + 1)?  false: j >= P.count
+        bool have(size_t j) {
+            if (seen >= j + 2) return true;
+            Backoff relax;
+            for (;;) {
+                seen = P.pub.load(std::memory_order_acquire);
+                if (seen >= j + 2) return true;
+                if (P.done.load(std::memory_order_acquire)) { seen = P.pub.load(std::memory_order_acquire); return j < P.count; }
+                relax();
+            }
+        }
+        // j + 1 >= PrevCount, for a j that `have` has admitted
+        bool is_last(size_t j) const {
+            if (seen >= j + 2) return false;
+            return j + 1 >= P.count; // admitted without the published count reaching it: P is done
+        }
+    };
+    struct Emit {
+        Walk &w;
+        size_t n = 0;
+        size_t batch = 1, told = 0; // records per publish
+        void push(const LAx &a) { w.rec[n++] = Slim{a.MinMag, a.chebRef, a.StepLength, a.NextStageLAIndex, a.n}; }
+        void pop() { n--; }
+        void publish() {
+            if (n - told < batch) return;
+            told = n;
+            w.pub.store(n, std::memory_order_release);
+        }
+        void close(Real cheb_last, bool ok) { // the closing record LAInfoDeep(orbit[maxRef]) with StepLength 0
+            w.count = n;
+            w.rec[n] = Slim{N::r_int(4), cheb_last, 0, 0, Note{3, 0, 0}};
+            w.n_rec = n + 1;
+            w.ok = ok;
+            w.pub.store(n, std::memory_order_release);
+            w.done.store(1, std::memory_order_release);
+        }
+    };
+    LAx xs_copy(const Walk &Pv, IterT j) const { return LAx{Pv.rec[j].MinMag, Note{1, j, 0}, 0, 0, Pv.rec[j].chebRef}; }
+    bool xs_comp(const LAx &a, LAx &out, const Slim &b) const { // x_comp on a slim record
+        out.n = Note{a.n.kind, a.n.first, a.n.count + 1};
+        out.chebRef = a.chebRef;
+        const Real temp = N::r_min(b.chebRef, a.MinMag);
+        out.MinMag = N::r_min(temp, b.MinMag);
+        return N::r_cmp(temp, N::r_scale_by(a.MinMag, thr_detect)) < 0;
+    }
+    LAx xs_comp(const LAx &a, const Slim &b) const { LAx r = a; xs_comp(a, r, b); return r; }
+
+    // stage0_walk on slim records
+    void p_stage0(Walk &W, IterT maxRef) {
+        W.ran = true;
+        Emit E{W};
+        E.batch = 128; // a publish is a store to a line a dozen threads poll: rarely
+        IterT Period = 0;
+        if (N::c_is_zero(la_step(la_new(N::c_zero()), orbit_at(1)).ZCoeff)) {
+            W.follow.store(2, std::memory_order_release);
+            W.count = 0;
+            W.ok = false;
+            W.done.store(1, std::memory_order_release);
+            return;
+        }
+        LAx la = x_step(x_new_zero(), 1);
+        IterT nextIdx = 0;
+        IterT i;
+        for (i = 2; i < maxRef; i++) {
+            LAx nl;
+            if (!x_step(la, nl, i)) { la = nl; continue; }
+            Period = i;
+            la.StepLength = Period; la.NextStageLAIndex = nextIdx;
+            E.push(la);
+            nextIdx = i;
+            if (i + 1 < maxRef) { la = x_step(x_new_at(i), i + 1); i += 2; }
+            else { la = x_new_at(i); i += 1; }
+            break;
+        }
+        IterT PeriodBegin = Period, PeriodEnd = PeriodBegin + Period;
+        if (Period == 0) {
+            if (maxRef > (IterT)lowBound) {
+                la = x_step(x_new_at(0), 1);
+                nextIdx = 0;
+                i = 2;
+                Period = nth_root_period((double)maxRef, (double)maxRef);
+                PeriodBegin = 0;
+                PeriodEnd = Period;
+            } else {
+                la.StepLength = maxRef; la.NextStageLAIndex = nextIdx;
+                E.push(la);
+                W.follow.store(2, std::memory_order_release);
+                E.close(chebs[maxRef], false); // MacroItCount 1: this record and the closing one
+                return;
+            }
+        } else if (Period > (IterT)lowBound) {
+            E.pop();
+            la = x_step(x_new_at(0), 1);
+            nextIdx = 0;
+            i = 2;
+            Period = nth_root_period((double)maxRef, (double)maxRef);
+            PeriodBegin = 0;
+            PeriodEnd = Period;
+        }
+        W.follow.store(1, std::memory_order_release); // nothing pushed from here on is taken back
+        // x_step(la, nl, i) for every element, written so that an element which neither lowers MinMag nor ends the period
+        // costs one comparison: the right-hand side of the period test, MinMag * threshold, and the test's outcome for an
+        // unchanged MinMag stand until MinMag changes.  Same comparisons on the same values, hence the same decisions.
+        Real T = N::r_scale_by(la.MinMag, thr_stage0);
+        bool self_det = N::r_cmp(la.MinMag, T) < 0;
+        for (; i < maxRef; i++) {
+            const Real c = chebs[i];
+            const bool lower = N::r_cmp(c, la.MinMag) < 0; // r_min(c, MinMag): c if it compares less, MinMag otherwise
+            const bool det = lower ? N::r_cmp(c, T) < 0 : self_det;
+            if (!det && i < PeriodEnd) {
+                la.n.count++;
+                if (lower) {
+                    la.MinMag = c;
+                    T = N::r_scale_by(c, thr_stage0);
+                    self_det = N::r_cmp(c, T) < 0;
+                }
+                continue;
+            }
+            LAx nl = la; // the record with this element, which only the look-ahead below reads
+            nl.n.count++;
+            if (lower) nl.MinMag = c;
+            la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
+            E.push(la);
+            E.publish();
+            nextIdx = i;
+            PeriodBegin = i;
+            PeriodEnd = PeriodBegin + Period;
+            const IterT ip1 = i + 1;
+            const bool detected = x_detect(nl, chebs[ip1]);
+            if (detected || ip1 >= maxRef) {
+                la = x_new_at(i);
+            } else {
+                la = x_step(x_new_at(i), ip1);
+                i++;
+            }
+            T = N::r_scale_by(la.MinMag, thr_stage0);
+            self_det = N::r_cmp(la.MinMag, T) < 0;
+        }
+        la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
+        E.push(la);
+        E.close(chebs[maxRef], true);
+    }
+
+    // next_stage_walk on slim records; Pv = the stage below, possibly still being walked
+    void p_next(const Walk &Pv, Walk &W, IterT maxRef, bool may_follow) {
+        W.ran = true;
+        Emit E{W};
+        E.batch = 4;
+        Reader R{Pv};
+        R.have(0); // records 0 and 1 (a stage that is followed has at least one regular record and its closing one)
+        const Slim PrevLA = Pv.rec[0], PrevLAp1 = Pv.rec[1];
+        IterT Period = 0;
+        LAx la = xs_comp(xs_copy(Pv, 0), PrevLAp1);
+        IterT nextIdx = 0;
+        IterT i = PrevLA.StepLength + PrevLAp1.StepLength;
+        IterT j;
+        for (j = 2; R.have(j); j++) {
+            LAx nl;
+            const Slim &Pj = Pv.rec[j];
+            const bool det = xs_comp(la, nl, Pj);
+            if (det) {
+                W.spec = (long long)j; // `if (Pj.LAThreshold == 0) break;` -- taken to be non-zero, checked after the fills
+                Period = i;
+                la.StepLength = Period; la.NextStageLAIndex = nextIdx;
+                E.push(la);
+                nextIdx = j;
+                const Slim &Pjp1 = Pv.rec[j + 1];
+                if (x_detect(nl, Pjp1.chebRef) || R.is_last(j)) {
+                    la = xs_copy(Pv, j);
+                    i += Pj.StepLength;
+                    j++;
+                } else {
+                    la = xs_comp(xs_copy(Pv, j), Pjp1);
+                    i += Pj.StepLength + Pjp1.StepLength;
+                    j += 2;
+                }
+                break;
+            }
+            la = nl;
+            i += Pj.StepLength;
+        }
+        IterT PeriodBegin = Period, PeriodEnd = PeriodBegin + Period;
+        if (Period == 0) {
+            if (maxRef > PrevLA.StepLength * (IterT)lowBound) {
+                la = xs_comp(xs_copy(Pv, 0), PrevLAp1);
+                i = PrevLA.StepLength + PrevLAp1.StepLength;
+                nextIdx = 0;
+                j = 2;
+                const double Ratio = (double)maxRef / (double)PrevLA.StepLength;
+                Period = PrevLA.StepLength * nth_root_period((double)maxRef, Ratio);
+                PeriodBegin = 0;
+                PeriodEnd = Period;
+            } else {
+                la.StepLength = maxRef; la.NextStageLAIndex = nextIdx;
+                E.push(la);
+                W.follow.store(2, std::memory_order_release);
+                E.close(chebs[maxRef], false);
+                return;
+            }
+        } else if (Period > PrevLA.StepLength * (IterT)lowBound) {
+            E.pop();
+            la = xs_comp(xs_copy(Pv, 0), PrevLAp1);
+            i = PrevLA.StepLength + PrevLAp1.StepLength;
+            nextIdx = 0;
+            j = 2;
+            const double Ratio = (double)Period / (double)PrevLA.StepLength;
+            Period = PrevLA.StepLength * nth_root_period((double)maxRef, Ratio);
+            PeriodBegin = 0;
+            PeriodEnd = Period;
+        }
+        W.follow.store(may_follow ? 1 : 2, std::memory_order_release);
+        for (; R.have(j); j++) {
+            LAx nl;
+            const Slim &Pj = Pv.rec[j];
+            const bool det = xs_comp(la, nl, Pj);
+            if (det || i >= PeriodEnd) {
+                la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
+                E.push(la);
+                E.publish();
+                nextIdx = j;
+                PeriodBegin = i;
+                PeriodEnd = PeriodBegin + Period;
+                const Slim &Pjp1 = Pv.rec[j + 1];
+                if (x_detect(nl, Pjp1.chebRef) || R.is_last(j)) {
+                    la = xs_copy(Pv, j);
+                } else {
+                    la = xs_comp(xs_copy(Pv, j), Pjp1);
+                    i += Pv.rec[j].StepLength;
+                    j++;
+                }
+            } else {
+                la = nl;
+            }
+            i += Pv.rec[j].StepLength;
+        }
+        la.StepLength = i - PeriodBegin; la.NextStageLAIndex = nextIdx;
+        E.push(la);
+        E.close(chebs[maxRef], true);
+    }
+
+    // one record from its note (phase 2 of the two-phase form, for one record); prev = the previous stage's first record
+    void fill_one(LA &dst, const Slim &r, const LA *prev, IterT maxRef) const {
+        const Note nt = r.n;
+        LA l;
+        if (nt.kind == 3) l = la_new(orbit_at(maxRef));
+        else if (nt.kind == 1) l = prev[nt.first];
+        else l = la_new(nt.kind == 2 ? N::c_zero() : orbit_at(nt.first));
+        for (IterT c = 1; c <= nt.count; c++) {
+            LA nl = la_blank();
+            if (nt.kind == 1) la_comp(l, nl, prev[(size_t)nt.first + c]);
+            else la_step(l, nl, orbit_at((nt.kind == 2 ? (IterT)0 : nt.first) + c));
+            l = nl;
+        }
+        l.StepLength = r.StepLength;
+        l.NextStageLAIndex = r.NextStage;
+        dst = l;
+    }
+
+    // false: not applicable here (more stages than walkers) or the LAThreshold assumption failed -- build stage after stage
+    bool build_pipelined(IterT maxRef) {
+        thr_stage0 = N::r_scale_pre(P.stage0_thr2);
+        thr_detect = N::r_scale_pre(P.thr2);
+        chebs.resize((size_t)maxRef + 1);
+        parallel_for(chebs.size(), [&](size_t lo, size_t hi) { for (size_t k = lo; k < hi; k++) chebs[k] = N::c_cheb(orbit_at(k)); });
+        const auto t0 = std::chrono::steady_clock::now();
+        std::unique_ptr<Walk[]> W(new Walk[kMaxPipelinedStages]);
+        const size_t cap = (size_t)maxRef + 4; // no stage has more records than the orbit has elements
+        Scratch &scr = scratch();
+        std::lock_guard<std::mutex> one_build(scr.mu);
+        for (size_t k = 0; k < kMaxPipelinedStages; k++) W[k].rec = scr.get(k, cap);
+        las.clear();
+        las.reserve(cap + cap / 2);
+        LA *const out0 = las.data(); // stage 0's place, whatever follows
+        std::atomic<size_t> fill_next{0};
+        std::atomic<bool> overflow{false};
+        constexpr size_t kFillChunk = 16;
+        Walk &S0 = W[0];
+        // stage 0's records are filled behind its walk: take the next chunk of them, wait until the walk has published it
+        // (or has ended), fill it.  false: no chunk left.
+        const bool fill_during = !(getenv("FS_LA_FILL_DURING") && atoi(getenv("FS_LA_FILL_DURING")) == 0);
+        auto fill_chunk = [&]() -> bool {
+            if (!fill_during && !S0.done.load(std::memory_order_acquire)) return false;
+            if (S0.done.load(std::memory_order_acquire) && fill_next.load(std::memory_order_relaxed) >= S0.n_rec) return false;
+            const size_t a = fill_next.fetch_add(kFillChunk), b = a + kFillChunk;
+            size_t end;
+            Backoff relax;
+            for (;;) {
+                if (S0.pub.load(std::memory_order_acquire) >= b) { end = b; break; }
+                if (S0.done.load(std::memory_order_acquire)) { end = std::min(b, S0.n_rec); break; }
+                relax();
+            }
+            for (size_t r = a; r < end; r++) fill_one(out0[r], S0.rec[r], nullptr, maxRef);
+            return end == b;
+        };
+        auto task = [&](size_t k, size_t) {
+            Backoff relax;
+            auto now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+            if (k == 0) {
+                S0.t_begin = now();
+                p_stage0(S0, maxRef);
+                S0.t_end = now();
+            } else if (k < kMaxPipelinedStages) {
+                Walk &Pv = W[k - 1];
+                // whether this stage exists is known once the stage below is past its first period; until then, help
+                while (Pv.follow.load(std::memory_order_acquire) == 0) {
+                    if (S0.follow.load(std::memory_order_acquire) == 0 || !fill_chunk()) relax();
+                }
+                if (Pv.follow.load(std::memory_order_acquire) == 1) {
+                    const bool may_follow = k + 1 < (size_t)MaxLAStages;
+                    W[k].t_begin = now();
+                    p_next(Pv, W[k], maxRef, may_follow);
+                    W[k].t_end = now();
+                    if (k + 1 == kMaxPipelinedStages && W[k].follow.load() == 1) overflow.store(true);
+                } else {
+                    W[k].follow.store(2, std::memory_order_release);
+                }
+            }
+            while (S0.follow.load(std::memory_order_acquire) == 0) relax();
+            if (!fill_during) while (!S0.done.load(std::memory_order_acquire)) relax();
+            while (fill_chunk()) {}
+        };
+        HostPool::get().run_tasks(kMaxPipelinedStages + HostPool::get().threads(), task);
+        const auto t1 = std::chrono::steady_clock::now();
+        if (overflow.load()) return false;
+        stages.assign(MaxLAStages, WireStage<IterT>{0, 0});
+        use_at = false;
+        is_valid = false;
+        walk_ok = S0.ok;
+        if (S0.n_rec == 0) { // the first step's ZCoeff is zero: no table at all (stage0_walk's first return)
+            las.clear();
+            stage_count = 0;
+            return true;
+        }
+        // lay the stages out one behind the other and fill stages 1 ... from the stage below each
+        size_t n_stages = 0, total = 0;
+        while (n_stages < kMaxPipelinedStages && W[n_stages].ran) { total += W[n_stages].n_rec; n_stages++; }
+        las.resize_uninit(S0.n_rec);
+        las.resize_uninit(total);
+        size_t off = 0, prev_off = 0;
+        for (size_t k = 0; k < n_stages; k++) {
+            const Walk &S = W[k];
+            stages[k].LAIndex = (IterT)off;
+            stages[k].MacroItCount = (IterT)S.count;
+            if (k > 0) {
+                if (S.spec >= 0 && N::r_is_zero(las[prev_off + (size_t)S.spec].LAThreshold)) return false;
+                LA *dst = las.data() + off;
+                const LA *prev = las.data() + prev_off;
+                parallel_for(S.n_rec, [&](size_t lo, size_t hi) { for (size_t r = lo; r < hi; r++) fill_one(dst[r], S.rec[r], prev, maxRef); }, 2);
+            }
+            prev_off = off;
+            off += S.n_rec;
+        }
+        stage_count = (IterT)n_stages;
+        if (getenv("FS_LA_TIMING")) {
+            fprintf(stderr, "pipelined: walks + stage-0 fill %.3f ms, other fills %.3f ms, %zu stages, %zu records;",
+                    std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), n_stages, total);
+            for (size_t k = 0; k < n_stages; k++) fprintf(stderr, " walk %zu: %.3f-%.3f ms (%zu)", k, W[k].t_begin, W[k].t_end, W[k].n_rec);
+            fprintf(stderr, "\n");
+        }
+        return true;
+    }
+    bool walk_ok = false; // stage 0's walk returned true (a table with an AT block and is_valid follow)
+
     // LAInfoDeep::CreateAT  LAInfoDeep.h:456-502 ; ATInfo::Usable  ATInfo.h:92-106
     void create_at(const LA &a, const LA &next, bool small_exp) {
         at.ZCoeff = a.ZCoeff;
@@ -871,9 +1368,18 @@ template <class N, class IterT> struct LaBuilder {
         at.factor = N::at_factor();
         const IterT maxRef = (IterT)orbit->count - 1;
         if (maxRef == 0) { is_valid = false; return; }
-        bool ok = stage0(maxRef);
+        // FS_LA_PIPELINE=0: the stage-after-stage (two-phase) form only
+        const char *pe = getenv("FS_LA_PIPELINE");
+        const bool pipeline_off = pe && atoi(pe) == 0;
+        bool ok;
+        if (!pipeline_off && build_pipelined(maxRef)) {
+            ok = walk_ok;
+        } else {
+            las.clear();
+            ok = stage0(maxRef);
+            if (ok) while (next_stage(maxRef)) {}
+        }
         if (ok) {
-            while (next_stage(maxRef)) {}
             Real radius;
             memcpy(&radius, orbit->max_radius, sizeof(radius));
             const Real sqr_radius = N::r_square_reduced(radius);
@@ -1094,13 +1600,12 @@ template <class N, class IterT> fsh_la *build_la(const fsh_orbit *o, int period_
     b.periodDivisor = period_divisor;
     b.build();
     fsh_la *r = new fsh_la();
-    r->las.resize(b.las.size() * sizeof(b.las[0]));
-    if (!b.las.empty()) memcpy(r->las.data(), b.las.data(), r->las.size());
+    r->num_las = b.las.size();
+    r->las_own = b.las.release(); // the builder's array, as is
     r->stages.resize(b.stages.size() * sizeof(b.stages[0]));
     memcpy(r->stages.data(), b.stages.data(), r->stages.size());
     r->at.resize(sizeof(b.at));
     memcpy(r->at.data(), &b.at, sizeof(b.at));
-    r->num_las = b.las.size();
     r->num_stages = b.stages.size();
     r->stage_count = b.stage_count;
     r->use_at = b.use_at;
@@ -1573,7 +2078,7 @@ fsh_la *fsh_la_build(const fsh_orbit *o, uint32_t iter_bytes) {
     }
 }
 void fsh_la_destroy(fsh_la *l) { delete l; }
-const void *fsh_la_las(const fsh_la *l) { return l->las.data(); }
+const void *fsh_la_las(const fsh_la *l) { return l->las_own ? l->las_own : l->las.data(); }
 uint64_t fsh_la_num_las(const fsh_la *l) { return l->num_las; }
 const void *fsh_la_stages(const fsh_la *l) { return l->stages.data(); }
 uint64_t fsh_la_num_stages(const fsh_la *l) { return l->num_stages; }

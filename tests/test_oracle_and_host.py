@@ -241,3 +241,55 @@ def test_at_mantissa_recurrence_matches_float_exponent_loop_in_lockstep(built, v
         # most accepted pixels qualify for the lean chunk test (escape visible in the chunk's last pass); the checker
         # ran 16 passes past every escape of such a pixel and counts a pass that looked un-escaped as a mismatch
         assert st["mono"] > (st["pixels"] - st["refused"]) // 2 and st["escaped"] > 0, st
+
+
+def _la_bytes(la):
+    d = la.descriptor()
+    at = bytes((ctypes.c_ubyte * la.at_bytes).from_address(d.at)) if la.at_bytes else b""
+    las = la.las_numpy().copy()
+    if las.shape[1] in (128, 136):
+        # LAInfoDeep<.., HDRFloat<double>>: four indeterminate padding bytes behind every 32-bit exponent
+        for lo in (20, 44, 68, 84, 100, 116):
+            las[:, lo:lo + 4] = 0
+    return (la.num_las, la.stage_count, la.use_at, la.is_valid, las.tobytes(),
+            la.stages_numpy()[: max(la.stage_count, 1)].tobytes(), at)
+
+
+@pytest.mark.parametrize("alg,view_id,iter_bytes", [
+    (RenderAlgorithm.GpuHDRx32PerturbedLAv2, 14, 4), (RenderAlgorithm.GpuHDRx32PerturbedLAv2, 19, 8),
+    (RenderAlgorithm.GpuHDRx32PerturbedLAv2, 5, 4), (RenderAlgorithm.GpuHDRx32PerturbedLAv2, 1, 4),
+    (RenderAlgorithm.GpuHDRx64PerturbedLAv2, 5, 4), (RenderAlgorithm.Gpu1x64PerturbedLAv2, 1, 4),
+    (RenderAlgorithm.Gpu1x32PerturbedLAv2, 1, 8), (RenderAlgorithm.GpuHDRx2x32PerturbedLAv2, 5, 4),
+    (RenderAlgorithm.GpuHDRx32PerturbedRCLAv2, 5, 4),
+])
+def test_pipelined_la_builder_equals_the_stage_after_stage_one(built, monkeypatch, alg, view_id, iter_bytes):
+    """fs_host.cpp builds the LA table with the walks of all stages running at the same time (build_pipelined) and falls
+    back to one stage after the other (FS_LA_PIPELINE=0 forces that).  Same records, stage table and AT block, byte for
+    byte, for every numeric type and for the coarser period divisor of compressed orbits (RC)."""
+    from fractalshark_b200.host_inputs import LaTable
+    _, _, orbit, la, _ = cases.make_inputs(view_id, 96, 54, alg, None, iter_bytes)
+    monkeypatch.setenv("FS_LA_PIPELINE", "1")
+    a = _la_bytes(LaTable(orbit, iter_bytes))
+    monkeypatch.setenv("FS_LA_PIPELINE", "0")
+    b = _la_bytes(LaTable(orbit, iter_bytes))
+    assert a[:4] == b[:4]
+    assert a[4] == b[4] and a[5] == b[5] and a[6] == b[6]
+    assert a[0] > 0
+
+
+def test_la_builder_with_one_two_and_three_host_threads(built):
+    """The pipelined builder's walkers wait for each other; with fewer threads than stages they must still finish (a walker
+    only ever waits for the stage below, which was claimed before it) and give the same table."""
+    import subprocess, sys
+    code = ("import sys, zlib; sys.path.insert(0, 'tests'); import cases\n"
+            "from fractalshark_b200 import RenderAlgorithm as A\n"
+            "_, _, orbit, la, _ = cases.make_inputs(14, 96, 54, A.GpuHDRx32PerturbedLAv2, None, 4)\n"
+            "print(la.num_las, la.stage_count, zlib.crc32(la.las_numpy().tobytes()))\n")
+    outs = set()
+    for threads in ("1", "2", "3", "16"):
+        env = dict(os.environ, FS_HOST_THREADS=threads)
+        r = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                           env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.add(r.stdout.strip().splitlines()[-1])
+    assert len(outs) == 1 and outs.pop().startswith("33844 5 ")
