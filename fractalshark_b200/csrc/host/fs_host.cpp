@@ -931,7 +931,10 @@ template <class N, class IterT> struct LaBuilder {
         alignas(64) std::atomic<size_t> pub{0}; // rec[0 .. pub) are final (regular records: a further record follows each)
         alignas(64) std::atomic<int> follow{0}; // 0 undecided, 1 a next stage follows this one, 2 this is the last stage
         std::atomic<int> done{0};               // 1: rec[0 .. count] complete (count regular records and the closing one)
+        alignas(64) std::atomic<size_t> fill_next{0}; // first record no thread has claimed for filling yet
         alignas(64) Slim *rec = nullptr;
+        LA *out = nullptr;                    // where this stage's filled records go
+        std::atomic<uint32_t> *stamp = nullptr;
         size_t count = 0, n_rec = 0; // MacroItCount; records in rec[] (count regular ones and the closing one)
         long long spec = -1;         // previous-stage record whose LAThreshold the walk took to be non-zero
         bool ran = false, ok = false;
@@ -939,20 +942,27 @@ template <class N, class IterT> struct LaBuilder {
     };
     // The walks' record arrays live as long as the process: a fresh 4 MB allocation per stage and build is a page fault per
     // 4 KB written (0.5 ms of a 1 ms walk on the 16-core box, more than the walk's arithmetic).  One build at a time.
+    static constexpr size_t kFillChunk = 16; // records per fill claim
     struct Scratch {
         std::mutex mu;
         Slim *rec[kMaxPipelinedStages] = {};
+        LA *out[kMaxPipelinedStages] = {};                      // filled records of stages 1 ... (stage 0 goes straight to `las`)
+        std::atomic<uint32_t> *stamp[kMaxPipelinedStages] = {}; // per fill chunk: the number of the build that completed it
         size_t cap[kMaxPipelinedStages] = {};
-        Slim *get(size_t k, size_t n) {
-            if (cap[k] < n) {
-                free(rec[k]);
-                rec[k] = static_cast<Slim *>(malloc(n * sizeof(Slim)));
-                if (!rec[k]) { cap[k] = 0; throw std::bad_alloc(); }
-                cap[k] = n;
-            }
-            return rec[k];
+        uint32_t build_no = 0;
+        void get(size_t k, size_t n) {
+            if (cap[k] >= n) return;
+            free(rec[k]);
+            free(out[k]);
+            free(stamp[k]);
+            cap[k] = 0;
+            rec[k] = static_cast<Slim *>(malloc(n * sizeof(Slim)));
+            out[k] = k == 0 ? nullptr : static_cast<LA *>(malloc(n * sizeof(LA)));
+            stamp[k] = static_cast<std::atomic<uint32_t> *>(calloc(n / kFillChunk + 2, sizeof(std::atomic<uint32_t>)));
+            if (!rec[k] || (k != 0 && !out[k]) || !stamp[k]) throw std::bad_alloc();
+            cap[k] = n;
         }
-        ~Scratch() { for (auto *r : rec) free(r); }
+        ~Scratch() { for (size_t k = 0; k < kMaxPipelinedStages; k++) { free(rec[k]); free(out[k]); free(stamp[k]); } }
     };
     static Scratch &scratch() { static Scratch s; return s; }
     // waiting for another thread's progress: a few pauses, then yields (with fewer cores than threads the thread being
@@ -1073,6 +1083,7 @@ template <class N, class IterT> struct LaBuilder {
         // x_step(la, nl, i) for every element, written so that an element which neither lowers MinMag nor ends the period
         // costs one comparison: the right-hand side of the period test, MinMag * threshold, and the test's outcome for an
         // unchanged MinMag stand until MinMag changes.  Same comparisons on the same values, hence the same decisions.
+        const Real four = N::r_int(4); // LAInfoDeep(z): MinMag = 4
         Real T = N::r_scale_by(la.MinMag, thr_stage0);
         bool self_det = N::r_cmp(la.MinMag, T) < 0;
         for (; i < maxRef; i++) {
@@ -1102,7 +1113,8 @@ template <class N, class IterT> struct LaBuilder {
             if (detected || ip1 >= maxRef) {
                 la = x_new_at(i);
             } else {
-                la = x_step(x_new_at(i), ip1);
+                // x_step(x_new_at(i), ip1), whose period test nobody reads
+                la = LAx{N::r_min(chebs[ip1], four), Note{0, i, 1}, 0, 0, chebs[i]};
                 i++;
             }
             T = N::r_scale_by(la.MinMag, thr_stage0);
@@ -1239,57 +1251,93 @@ template <class N, class IterT> struct LaBuilder {
         const size_t cap = (size_t)maxRef + 4; // no stage has more records than the orbit has elements
         Scratch &scr = scratch();
         std::lock_guard<std::mutex> one_build(scr.mu);
-        for (size_t k = 0; k < kMaxPipelinedStages; k++) W[k].rec = scr.get(k, cap);
+        const uint32_t build_no = ++scr.build_no == 0 ? ++scr.build_no : scr.build_no;
         las.clear();
         las.reserve(cap + cap / 2);
-        LA *const out0 = las.data(); // stage 0's place, whatever follows
-        std::atomic<size_t> fill_next{0};
+        for (size_t k = 0; k < kMaxPipelinedStages; k++) {
+            scr.get(k, cap);
+            W[k].rec = scr.rec[k];
+            W[k].out = k == 0 ? las.data() : scr.out[k]; // stage 0's place in `las` is its beginning whatever follows
+            W[k].stamp = scr.stamp[k];
+        }
         std::atomic<bool> overflow{false};
-        constexpr size_t kFillChunk = 16;
-        Walk &S0 = W[0];
-        // stage 0's records are filled behind its walk: take the next chunk of them, wait until the walk has published it
-        // (or has ended), fill it.  false: no chunk left.
-        const bool fill_during = !(getenv("FS_LA_FILL_DURING") && atoi(getenv("FS_LA_FILL_DURING")) == 0);
-        auto fill_chunk = [&]() -> bool {
-            if (!fill_during && !S0.done.load(std::memory_order_acquire)) return false;
-            if (S0.done.load(std::memory_order_acquire) && fill_next.load(std::memory_order_relaxed) >= S0.n_rec) return false;
-            const size_t a = fill_next.fetch_add(kFillChunk), b = a + kFillChunk;
-            size_t end;
-            Backoff relax;
+        std::atomic<int> walks_done{0}; // set by the walk of the last stage (the walks below it have ended before)
+        // Filling runs behind the walks, on every thread that is not walking: records are claimed in chunks, stage 0 first.
+        // A record of stage k > 0 is a chain of composites over filled records of stage k - 1; whoever fills it makes sure
+        // those are complete, by filling lower stages itself while it waits (so the wait always ends: stage 0 waits for
+        // nothing).  try_fill(k): fill one chunk of stage k if one can be claimed; false: none right now.
+        std::function<bool(size_t)> try_fill = [&](size_t k) -> bool {
+            Walk &S = W[k];
             for (;;) {
-                if (S0.pub.load(std::memory_order_acquire) >= b) { end = b; break; }
-                if (S0.done.load(std::memory_order_acquire)) { end = std::min(b, S0.n_rec); break; }
-                relax();
+                size_t a = S.fill_next.load(std::memory_order_relaxed);
+                const bool ended = S.done.load(std::memory_order_acquire) != 0;
+                const size_t avail = ended ? S.n_rec : S.pub.load(std::memory_order_acquire);
+                if (a >= avail) return false;
+                size_t b = a + kFillChunk;
+                if (b > avail) {
+                    if (!ended) return false; // chunks stay aligned: a partial one only at the stage's end
+                    b = avail;
+                }
+                if (!S.fill_next.compare_exchange_weak(a, a + kFillChunk, std::memory_order_relaxed)) continue;
+                const LA *prev = k == 0 ? nullptr : W[k - 1].out;
+                for (size_t r = a; r < b; r++) {
+                    const Note nt = S.rec[r].n;
+                    if (nt.kind == 1) {
+                        const std::atomic<uint32_t> *st = W[k - 1].stamp;
+                        for (size_t c = (size_t)nt.first / kFillChunk; c <= ((size_t)nt.first + nt.count) / kFillChunk; c++) {
+                            Backoff relax;
+                            while (st[c].load(std::memory_order_acquire) != build_no) {
+                                bool helped = false;
+                                for (size_t below = 0; below < k && !helped; below++) helped = try_fill(below);
+                                if (!helped) relax();
+                            }
+                        }
+                    }
+                    fill_one(S.out[r], S.rec[r], prev, maxRef);
+                }
+                S.stamp[a / kFillChunk].store(build_no, std::memory_order_release);
+                return true;
             }
-            for (size_t r = a; r < end; r++) fill_one(out0[r], S0.rec[r], nullptr, maxRef);
-            return end == b;
+        };
+        auto try_any = [&]() -> bool {
+            for (size_t k = 0; k < kMaxPipelinedStages; k++)
+                if (try_fill(k)) return true; // (a stage that does not exist never has anything published)
+            return false;
         };
         auto task = [&](size_t k, size_t) {
             Backoff relax;
             auto now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
             if (k == 0) {
-                S0.t_begin = now();
-                p_stage0(S0, maxRef);
-                S0.t_end = now();
+                W[0].t_begin = now();
+                p_stage0(W[0], maxRef);
+                W[0].t_end = now();
+                if (W[0].follow.load() == 2) walks_done.store(1, std::memory_order_release);
             } else if (k < kMaxPipelinedStages) {
                 Walk &Pv = W[k - 1];
                 // whether this stage exists is known once the stage below is past its first period; until then, help
                 while (Pv.follow.load(std::memory_order_acquire) == 0) {
-                    if (S0.follow.load(std::memory_order_acquire) == 0 || !fill_chunk()) relax();
+                    if (!try_any()) relax();
                 }
                 if (Pv.follow.load(std::memory_order_acquire) == 1) {
                     const bool may_follow = k + 1 < (size_t)MaxLAStages;
                     W[k].t_begin = now();
                     p_next(Pv, W[k], maxRef, may_follow);
                     W[k].t_end = now();
-                    if (k + 1 == kMaxPipelinedStages && W[k].follow.load() == 1) overflow.store(true);
+                    if (W[k].follow.load() == 2) walks_done.store(1, std::memory_order_release);
+                    else if (k + 1 == kMaxPipelinedStages) { overflow.store(true); walks_done.store(1, std::memory_order_release); }
                 } else {
                     W[k].follow.store(2, std::memory_order_release);
                 }
             }
-            while (S0.follow.load(std::memory_order_acquire) == 0) relax();
-            if (!fill_during) while (!S0.done.load(std::memory_order_acquire)) relax();
-            while (fill_chunk()) {}
+            // Only a task behind the walkers' may wait for the walks to end: tasks are claimed in order, so by then every
+            // walker has been claimed and runs (or has run) on some thread.  A walker that waited here with fewer threads
+            // than stages would wait for a walk nobody has started.
+            if (k >= kMaxPipelinedStages) {
+                while (!walks_done.load(std::memory_order_acquire)) {
+                    if (!try_any()) relax();
+                }
+            }
+            while (try_any()) {}
         };
         HostPool::get().run_tasks(kMaxPipelinedStages + HostPool::get().threads(), task);
         const auto t1 = std::chrono::steady_clock::now();
@@ -1297,34 +1345,31 @@ template <class N, class IterT> struct LaBuilder {
         stages.assign(MaxLAStages, WireStage<IterT>{0, 0});
         use_at = false;
         is_valid = false;
-        walk_ok = S0.ok;
-        if (S0.n_rec == 0) { // the first step's ZCoeff is zero: no table at all (stage0_walk's first return)
+        walk_ok = W[0].ok;
+        if (W[0].n_rec == 0) { // the first step's ZCoeff is zero: no table at all (stage0_walk's first return)
             las.clear();
             stage_count = 0;
             return true;
         }
-        // lay the stages out one behind the other and fill stages 1 ... from the stage below each
+        // the stages one behind the other: stage 0 is in place, the others come from their own arrays
         size_t n_stages = 0, total = 0;
         while (n_stages < kMaxPipelinedStages && W[n_stages].ran) { total += W[n_stages].n_rec; n_stages++; }
-        las.resize_uninit(S0.n_rec);
+        las.resize_uninit(W[0].n_rec);
         las.resize_uninit(total);
-        size_t off = 0, prev_off = 0;
+        size_t off = 0;
         for (size_t k = 0; k < n_stages; k++) {
             const Walk &S = W[k];
             stages[k].LAIndex = (IterT)off;
             stages[k].MacroItCount = (IterT)S.count;
             if (k > 0) {
-                if (S.spec >= 0 && N::r_is_zero(las[prev_off + (size_t)S.spec].LAThreshold)) return false;
-                LA *dst = las.data() + off;
-                const LA *prev = las.data() + prev_off;
-                parallel_for(S.n_rec, [&](size_t lo, size_t hi) { for (size_t r = lo; r < hi; r++) fill_one(dst[r], S.rec[r], prev, maxRef); }, 2);
+                if (S.spec >= 0 && N::r_is_zero(W[k - 1].out[(size_t)S.spec].LAThreshold)) return false;
+                memcpy(static_cast<void *>(las.data() + off), S.out, S.n_rec * sizeof(LA));
             }
-            prev_off = off;
             off += S.n_rec;
         }
         stage_count = (IterT)n_stages;
         if (getenv("FS_LA_TIMING")) {
-            fprintf(stderr, "pipelined: walks + stage-0 fill %.3f ms, other fills %.3f ms, %zu stages, %zu records;",
+            fprintf(stderr, "pipelined: walks and fills %.3f ms, layout %.3f ms, %zu stages, %zu records;",
                     std::chrono::duration<double, std::milli>(t1 - t0).count(),
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), n_stages, total);
             for (size_t k = 0; k < n_stages; k++) fprintf(stderr, " walk %zu: %.3f-%.3f ms (%zu)", k, W[k].t_begin, W[k].t_end, W[k].n_rec);
