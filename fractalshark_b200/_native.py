@@ -71,6 +71,7 @@ GPU_SYMBOLS = {
     "fs_set_scaled_steps": (_U32, [_V, _I32]),
     "fs_set_split_at": (_U32, [_V, _I32]),
     "fs_set_pool_kernel": (_U32, [_V, _I32]),
+    "fs_selftest_numeric_op": (_U32, [_I32, _U32, _V, _V, _V, _U64]),
     "fs_set_la_step2": (_U32, [_V, _I32]),
     "fs_set_at_cycle_detection": (_U32, [_V, _I32]),
     "fs_device_iter_buffer": (_V, [_V]),

@@ -928,6 +928,54 @@ void CUDART_CB done_trampoline(void *p) {
 
 } // namespace
 
+// ---- per-operation self-test (fs_selftest_numeric_op) -------------------------------------------------------------
+// One operation of the device numeric types on arrays of operands, evaluated with the functions the render kernels
+// call (fs_types.cuh, fs_df32.cuh, fs_qd.cuh).  tests/test_gpu_parity.py compares the results with the oracle's
+// restatement of the reference's HDRFloat / HDRFloatComplex / dblflt / dbldbl routines, bit for bit.
+namespace {
+struct SelfHf { float m; int32_t e; };
+struct SelfHc { float re, im; int32_t e; };
+__global__ void numeric_op_kernel(uint32_t op, const void *a_, const void *b_, void *out_, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto hf = [](const void *p, uint64_t k) { const SelfHf v = static_cast<const SelfHf *>(p)[k]; return hdr_make<float>(v.e, v.m); };
+    auto hc = [](const void *p, uint64_t k) { const SelfHc v = static_cast<const SelfHc *>(p)[k]; HdrC<float> c; c.re = v.re; c.im = v.im; c.e = v.e; return c; };
+    auto put_hf = [&](Hdr<float> v) { static_cast<SelfHf *>(out_)[i] = SelfHf{v.m, v.e}; };
+    auto put_hc = [&](HdrC<float> v) { static_cast<SelfHc *>(out_)[i] = SelfHc{v.re, v.im, v.e}; };
+    const df32 *da = static_cast<const df32 *>(a_), *db = static_cast<const df32 *>(b_);
+    const dd64 *qa = static_cast<const dd64 *>(a_), *qb = static_cast<const dd64 *>(b_);
+    switch (op) {
+    case 0: put_hf(add(hf(a_, i), hf(b_, i))); break;
+    case 1: put_hf(sub(hf(a_, i), hf(b_, i))); break;
+    case 2: put_hf(mul(hf(a_, i), hf(b_, i))); break;
+    case 3: put_hf(square(hf(a_, i))); break;
+    case 4: { Hdr<float> v = hf(a_, i); reduce(v); put_hf(v); break; }
+    case 5: put_hf(div(hf(a_, i), hf(b_, i))); break;
+    case 6: put_hf(hdr_make<float>(cmp_pr(hf(a_, i), hf(b_, i)), 0.0f)); break;
+    case 10: put_hc(add(hc(a_, i), hc(b_, i))); break;
+    case 11: put_hc(mul(hc(a_, i), hc(b_, i))); break;
+    case 12: { HdrC<float> v = hc(a_, i); reduce(v); put_hc(v); break; }
+    case 13: { const Hdr<float> c = cheb(hc(a_, i)); HdrC<float> v; v.re = c.m; v.im = 0.0f; v.e = c.e; put_hc(v); break; }
+    case 14: { const HdrC<float> f = hc(b_, i); put_hc(mul(hc(a_, i), hdr_make<float>(f.e, f.re))); break; }
+    case 20: static_cast<df32 *>(out_)[i] = df_add(da[i], db[i]); break;
+    case 21: static_cast<df32 *>(out_)[i] = df_sub(da[i], db[i]); break;
+    case 22: static_cast<df32 *>(out_)[i] = df_mul(da[i], db[i]); break;
+    case 23: static_cast<df32 *>(out_)[i] = df_sqr(da[i]); break;
+    case 30: static_cast<dd64 *>(out_)[i] = dd_add(qa[i], qb[i]); break;
+    case 31: static_cast<dd64 *>(out_)[i] = dd_sub(qa[i], qb[i]); break;
+    case 32: static_cast<dd64 *>(out_)[i] = dd_mul(qa[i], qb[i]); break;
+    default: break;
+    }
+}
+uint32_t numeric_op_elem_bytes(uint32_t op) {
+    if (op <= 6) return 8;
+    if (op >= 10 && op <= 14) return 12;
+    if (op >= 20 && op <= 23) return 8;
+    if (op >= 30 && op <= 32) return 16;
+    return 0;
+}
+} // namespace
+
 extern "C" {
 
 uint32_t fs_test_cuda_is_working(void) {
@@ -1508,6 +1556,28 @@ uint32_t fs_set_la_step2(fs_renderer *r, int32_t enable) {
     if (!r) return FS_ERROR_UNSUPPORTED;
     r->use_la2 = enable != 0;
     return 0;
+}
+
+uint32_t fs_selftest_numeric_op(int32_t device, uint32_t op, const void *a, const void *b, void *out, uint64_t n) {
+    const uint32_t eb = numeric_op_elem_bytes(op);
+    if (eb == 0 || !a || !b || !out) return FS_ERROR_UNSUPPORTED;
+    if (n == 0) return 0;
+    DeviceGuard g(device);
+    void *da = nullptr, *db = nullptr, *dout = nullptr;
+    cudaError_t e = cudaMalloc(&da, n * eb);
+    if (e == cudaSuccess) e = cudaMalloc(&db, n * eb);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, n * eb);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, n * eb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, n * eb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        numeric_op_kernel<<<(unsigned int)((n + 255) / 256), 256>>>(op, da, db, dout, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * eb, cudaMemcpyDeviceToHost);
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return e;
 }
 
 uint32_t fs_set_pool_kernel(fs_renderer *r, int32_t enable) {

@@ -207,6 +207,13 @@ uint32_t fs_set_la_step2(fs_renderer *r, int32_t enable);
  * perturbation steps and refills idle lanes from them, fs_lav2_pool.cuh); 0 (default: measured faster) = one 8x4 tile
  * per warp from start to finish.  Results are identical.  A/B switch for tests and profiling. */
 uint32_t fs_set_pool_kernel(fs_renderer *r, int32_t enable);
+/* Self-test: evaluates one operation of the device numeric types (the functions the render kernels call) on n operand
+ * pairs from host arrays and writes n results to a host array.  op: 0-6 HDRFloat<float> add, sub, mul, square, Reduce,
+ * divide, compareToBothPositiveReduced (result in .exp); 10-14 HDRFloatComplex<float> add, mul, Reduce, chebychevNorm,
+ * times HDRFloat; 20-23 dblflt add, sub, mul, sqr; 30-32 dbldbl add, sub, mul.  Elements: {float mantissa; int32 exp}
+ * (8 B), {float re, im; int32 exp} (12 B), {float head, tail} (8 B), {double head, tail} (16 B).  Reference: HDRFloat.h,
+ * HDRFloatComplex.h, dblflt.cuh, dbldbl.cuh (the per-type operator tables SURVEY.md section 8 row a8 lists). */
+uint32_t fs_selftest_numeric_op(int32_t device, uint32_t op, const void *a, const void *b, void *out, uint64_t n);
 /* Device pointer of the iteration buffer (for NCCL gather by the host plumbing). */
 void *fs_device_iter_buffer(fs_renderer *r);
 /* Number of kernels this renderer has launched so far. */

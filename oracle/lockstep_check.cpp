@@ -502,4 +502,36 @@ void lockstep_la2_fuzz(uint64_t count, uint64_t seed, uint64_t *out) {
     out[0] = count; out[1] = accepted; out[2] = refused; out[3] = mismatches;
 }
 
+
+// The host build of the product's HDRFloat<float> / HDRFloatComplex<float> operations (fs_types.cuh, FS_HD) on operand arrays:
+// the CPU pre-image of fs_selftest_numeric_op, so that the per-operation vectors of the GPU suite can be checked against
+// orc_numeric_op without a GPU as well (tests/test_oracle_and_host.py).  Ops as in include/fs_gpu.h; -1: not a host op.
+int lockstep_numeric_op(uint32_t op, const void *a_, const void *b_, void *out_, uint64_t n) {
+    struct Hf { float m; int32_t e; };
+    struct Hc { float re, im; int32_t e; };
+    const Hf *fa = (const Hf *)a_, *fb = (const Hf *)b_; Hf *fo = (Hf *)out_;
+    const Hc *ca = (const Hc *)a_, *cb = (const Hc *)b_; Hc *co = (Hc *)out_;
+    auto hf = [](Hf v) { return fs::hdr_make<float>(v.e, v.m); };
+    auto hc = [](Hc v) { fs::HdrC<float> c; c.re = v.re; c.im = v.im; c.e = v.e; return c; };
+    for (uint64_t i = 0; i < n; i++) {
+        fs::Hdr<float> r; fs::HdrC<float> c;
+        switch (op) {
+        case 0: r = fs::add(hf(fa[i]), hf(fb[i])); fo[i] = Hf{r.m, r.e}; break;
+        case 1: r = fs::sub(hf(fa[i]), hf(fb[i])); fo[i] = Hf{r.m, r.e}; break;
+        case 2: r = fs::mul(hf(fa[i]), hf(fb[i])); fo[i] = Hf{r.m, r.e}; break;
+        case 3: r = fs::square(hf(fa[i])); fo[i] = Hf{r.m, r.e}; break;
+        case 4: r = hf(fa[i]); fs::reduce(r); fo[i] = Hf{r.m, r.e}; break;
+        case 5: r = fs::div(hf(fa[i]), hf(fb[i])); fo[i] = Hf{r.m, r.e}; break;
+        case 6: fo[i] = Hf{0.0f, fs::cmp_pr(hf(fa[i]), hf(fb[i]))}; break;
+        case 10: c = fs::add(hc(ca[i]), hc(cb[i])); co[i] = Hc{c.re, c.im, c.e}; break;
+        case 11: c = fs::mul(hc(ca[i]), hc(cb[i])); co[i] = Hc{c.re, c.im, c.e}; break;
+        case 12: c = hc(ca[i]); fs::reduce(c); co[i] = Hc{c.re, c.im, c.e}; break;
+        case 13: r = fs::cheb(hc(ca[i])); co[i] = Hc{r.m, 0.0f, r.e}; break;
+        case 14: c = fs::mul(hc(ca[i]), fs::hdr_make<float>(cb[i].e, cb[i].re)); co[i] = Hc{c.re, c.im, c.e}; break;
+        default: return -1;
+        }
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -40,6 +40,20 @@ def hardware_threads() -> int:
     return int(lib().orc_hardware_threads())
 
 
+def numeric_op(op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """One operation of the reference's device numeric types on operand arrays (oracle_cpu.cpp orc_numeric_op); operands and
+    results as raw bytes in structured arrays of the element layout of `op`."""
+    L = lib()
+    L.orc_numeric_op.restype = C.c_int
+    L.orc_numeric_op.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    out = np.zeros_like(a)
+    rc = L.orc_numeric_op(op, a.ctypes.data, b.ctypes.data, out.ctypes.data, a.shape[0])
+    assert rc == 0, rc
+    return out
+
+
 def render_lav2(alg, w, h, coords, orbit, la, n_iter, iter_bytes=4, rows=None, col_step=1, row_step=1, threads=1, out=None):
     """Returns (iters[hp, wp], executed_steps). Only rows in `rows` / every col_step-th column are computed."""
     t = traits(alg)
@@ -257,3 +271,19 @@ def lockstep_la2_fuzz(count, seed=1):
     out = (C.c_uint64 * 4)()
     fn(count, seed, out)
     return dict(zip(("cases", "accepted", "refused", "mismatches"), (int(v) for v in out)))
+
+
+def lockstep_numeric_op(op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """The host build of the product's HDRFloat<float> / HDRFloatComplex<float> operations (fs_types.cuh) on operand arrays."""
+    global _lock
+    if _lock is None:
+        _lock = C.CDLL(LOCKSTEP_LIB)
+    fn = _lock.lockstep_numeric_op
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    out = np.zeros_like(a)
+    rc = fn(op, a.ctypes.data, b.ctypes.data, out.ctypes.data, a.shape[0])
+    assert rc == 0, rc
+    return out

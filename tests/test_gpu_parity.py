@@ -635,3 +635,27 @@ def test_native_library_is_the_one_loaded():
     """The CUDA path is the one that ran: libfsgpu.so is mapped into this process."""
     maps = open("/proc/self/maps").read()
     assert "libfsgpu.so" in maps
+
+
+# ---- per-operation vectors of the device numeric types (SURVEY section 8 row a8) ---------------------------------------
+import numeric_vectors
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,name", numeric_vectors.OPS)
+def test_device_numeric_operations_match_the_reference_restatement(built, op, name):
+    """Row a8 on its own: every operation of HDRFloat<float>, HDRFloatComplex<float>, dblflt and dbldbl the kernels are built
+    from, evaluated on the GPU by the very functions the kernels call (fs_selftest_numeric_op) on 400,000 operand pairs
+    aimed at the code's case distinctions (numeric_vectors.operands) against oracle_cpu.cpp's restatement of
+    HDRFloat.h:432-448, 624-636, 829-884, 974-1065, 1150-1167, HDRFloatComplex.h:219-283, 334-348, 473-527, 691-695,
+    dblflt.cuh:91-219 and dbldbl.cuh:86-203.  Bit for bit (numeric_vectors.mismatches says what is not compared)."""
+    import oracle_cpu
+    from fractalshark_b200 import _native
+    n = 400_000
+    a, b = numeric_vectors.operands(op, n)
+    out = np.zeros_like(a)
+    rc = _native.gpu_lib().fs_selftest_numeric_op(0, op, a.ctypes.data, b.ctypes.data, out.ctypes.data, n)
+    assert rc == 0, rc
+    want = oracle_cpu.numeric_op(op, a, b)
+    bad = numeric_vectors.mismatches(out, want)
+    assert bad.size == 0, (name, int(bad.size), a[bad[:3]], b[bad[:3]], out[bad[:3]], want[bad[:3]])

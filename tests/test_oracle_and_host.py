@@ -293,3 +293,17 @@ def test_la_builder_with_one_two_and_three_host_threads(built):
         assert r.returncode == 0, r.stderr[-2000:]
         outs.add(r.stdout.strip().splitlines()[-1])
     assert len(outs) == 1 and outs.pop().startswith("33844 5 ")
+
+
+@pytest.mark.parametrize("op,name", [o for o in __import__("numeric_vectors").OPS if o[0] <= 14])
+def test_host_build_of_the_numeric_operations_matches_the_reference_restatement(built, op, name):
+    """The HDRFloat<float> / HDRFloatComplex<float> operations of fs_types.cuh are host+device functions: compiled for the
+    host (oracle/lockstep_check.cpp lockstep_numeric_op) they must give what oracle_cpu.cpp's restatement of HDRFloat.h /
+    HDRFloatComplex.h gives on the operand vectors the GPU suite runs through fs_selftest_numeric_op."""
+    import numeric_vectors
+    n = 200_000
+    a, b = numeric_vectors.operands(op, n)
+    got = oracle_cpu.lockstep_numeric_op(op, a, b)
+    want = oracle_cpu.numeric_op(op, a, b)
+    bad = numeric_vectors.mismatches(got, want)
+    assert bad.size == 0, (name, int(bad.size), a[bad[:3]], b[bad[:3]], got[bad[:3]], want[bad[:3]])
