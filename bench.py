@@ -132,13 +132,20 @@ class Workload:
         fam = self.traits.family
         self.coords = self.view.coords(self.traits.numeric, direct=(fam == "direct"))
         self.orbit = self.table = None
-        self.gen_times = {"orbit_s": 0.0, "table_s": 0.0}
+        self.gen_times = {"orbit_s": 0.0, "table_s": 0.0, "table_again_s": 0.0}
         if fam in ("lav2", "bla"):
             t0 = time.time()
             self.orbit = Orbit(self.view, self.traits.numeric, self.n_iter, True)
             t1 = time.time()
             self.table = LaTable(self.orbit, 4) if fam == "lav2" else BlaTable(self.orbit)
-            self.gen_times = {"orbit_s": t1 - t0, "table_s": time.time() - t1}
+            t2 = time.time()
+            # the first build of a process also starts the host thread pool; a view change in a running application does not
+            again = []
+            for _ in range(3):
+                t3 = time.time()
+                LaTable(self.orbit, 4) if fam == "lav2" else BlaTable(self.orbit)
+                again.append(time.time() - t3)
+            self.gen_times = {"orbit_s": t1 - t0, "table_s": t2 - t1, "table_again_s": min(again)}
         self.label = f"{self.where}_{spec['alg']}_{self.w}x{self.h}_aa1_u32_maxiter{self.n_iter}"
 
     def launch(self, r):
@@ -657,7 +664,8 @@ def main():
             assert r.InitializePerturb(gen, orbit_pinned, 0, None, la_pinned) == 0
             assert r.SyncComputeStream() == 0
             ups.append((time.time() - t0) * 1e3)
-        first_frame = {"orbit_s": gen_times["orbit_s"], "table_s": gen_times["table_s"], "upload_ms": min(ups),
+        first_frame = {"orbit_s": gen_times["orbit_s"], "table_s": gen_times["table_s"],
+                       "table_again_s": gen_times.get("table_again_s"), "upload_ms": min(ups),
                        "frame_ms": ms_per_step,
                        "what": "reference orbit (in-tree single-threaded GMP loop) and LA table (in-tree builder, byte-identical to "
                                "the reference's) on the host, InitializePerturb from page-locked memory incl. the device-side "
