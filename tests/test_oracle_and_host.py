@@ -307,3 +307,20 @@ def test_host_build_of_the_numeric_operations_matches_the_reference_restatement(
     want = oracle_cpu.numeric_op(op, a, b)
     bad = numeric_vectors.mismatches(got, want)
     assert bad.size == 0, (name, int(bad.size), a[bad[:3]], b[bad[:3]], got[bad[:3]], want[bad[:3]])
+
+
+def test_three_thread_orbit_producer_equals_the_single_threaded_loop(built, monkeypatch):
+    """From 4,096 bits of precision on, the reference orbit's three products per iteration run on three threads (the
+    reference's MT3 producer, RefOrbitCalc.cpp:1532-2157).  Same mpf products on the same operands: the orbit must be the
+    single-threaded loop's, byte for byte (View 14: 22,095 bits), for both element layouts."""
+    from fractalshark_b200.host_inputs import Orbit, View
+    from fractalshark_b200.views import PRESETS
+    p = PRESETS[14]
+    v = View(p.min_x, p.min_y, p.max_x, p.max_y, 96, 54)
+    for numeric in (Numeric.HDR32, Numeric.HDR64):
+        got = []
+        for mode in ("3", "1"):
+            monkeypatch.setenv("FS_ORBIT_THREADS", mode)
+            o = Orbit(v, numeric, 2500, True)
+            got.append((o.count, zlib.crc32(o.as_numpy().tobytes())))
+        assert got[0] == got[1] and got[0][0] == 2501
