@@ -667,7 +667,7 @@ def main():
         first_frame = {"orbit_s": gen_times["orbit_s"], "table_s": gen_times["table_s"],
                        "table_again_s": gen_times.get("table_again_s"), "upload_ms": min(ups),
                        "frame_ms": ms_per_step,
-                       "what": "reference orbit (in-tree single-threaded GMP loop) and LA table (in-tree builder, byte-identical to "
+                       "what": "reference orbit (in-tree GMP loop, three threads from 4,096 bits of precision) and LA table (in-tree builder, byte-identical to "
                                "the reference's) on the host, InitializePerturb from page-locked memory incl. the device-side "
                                "repacks, one frame"}
 
