@@ -475,6 +475,7 @@ class HostPool {
 
   private:
     void dispatch(size_t n, size_t g, const std::function<void(size_t, size_t)> &fn) {
+        std::lock_guard<std::mutex> one_job(job_mu); // callers on different threads take turns (jobs never nest)
         {
             std::lock_guard<std::mutex> lk(mu);
             job = &fn;
@@ -549,7 +550,7 @@ class HostPool {
         }
     }
     std::vector<std::thread> workers;
-    std::mutex mu;
+    std::mutex mu, job_mu;
     std::condition_variable wake, done;
     const std::function<void(size_t, size_t)> *job = nullptr;
     std::atomic<size_t> next{0}, posted{0}, left{0};
