@@ -1005,6 +1005,8 @@ template <class N, class IterT> struct LaBuilder {
         LA *out = nullptr;                    // where this stage's filled records go
         std::atomic<uint32_t> *stamp = nullptr;
         size_t count = 0, n_rec = 0; // MacroItCount; records in rec[] (count regular ones and the closing one)
+        size_t cap = 0;              // room in rec[] / out[]
+        bool overflowed = false;     // the stage has more records than room was set aside for: the build is redone stage after stage
         long long spec = -1;         // previous-stage record whose LAThreshold the walk took to be non-zero
         bool ran = false, ok = false;
         double t_begin = 0, t_end = 0; // FS_LA_TIMING: the walk's start and end, ms after the build's start
@@ -1070,8 +1072,11 @@ template <class N, class IterT> struct LaBuilder {
         Walk &w;
         size_t n = 0;
         size_t batch = 1, told = 0; // records per publish
-        void push(const LAx &a) { w.rec[n++] = Slim{a.MinMag, a.chebRef, a.StepLength, a.NextStageLAIndex, a.n}; }
-        void pop() { n--; }
+        void push(const LAx &a) {
+            if (n + 2 > w.cap) { w.overflowed = true; return; } // (room for the closing record stays)
+            w.rec[n++] = Slim{a.MinMag, a.chebRef, a.StepLength, a.NextStageLAIndex, a.n};
+        }
+        void pop() { if (n) n--; }
         void publish() {
             if (n - told < batch) return;
             told = n;
@@ -1324,7 +1329,12 @@ template <class N, class IterT> struct LaBuilder {
         las.clear();
         las.reserve(cap + cap / 2);
         for (size_t k = 0; k < kMaxPipelinedStages; k++) {
-            scr.get(k, cap);
+            // a stage is a fraction of the one below it (View 14: 31,219 / 1,827 / 782 / 14 / 2 records); should one outgrow
+            // half of it, the walk notes it and the table is built stage after stage instead
+            size_t cap_k = (cap >> std::min<size_t>(k, 20)) + 1024;
+            if (k > 0 && getenv("FS_LA_TEST_SMALL_STAGES")) cap_k = std::min<size_t>(cap_k, 64); // test hook: forces the overflow path
+            scr.get(k, cap_k);
+            W[k].cap = cap_k;
             W[k].rec = scr.rec[k];
             W[k].out = k == 0 ? las.data() : scr.out[k]; // stage 0's place in `las` is its beginning whatever follows
             W[k].stamp = scr.stamp[k];
@@ -1411,6 +1421,8 @@ template <class N, class IterT> struct LaBuilder {
         HostPool::get().run_tasks(kMaxPipelinedStages + HostPool::get().threads(), task);
         const auto t1 = std::chrono::steady_clock::now();
         if (overflow.load()) return false;
+        for (size_t k = 0; k < kMaxPipelinedStages; k++)
+            if (W[k].overflowed) return false;
         stages.assign(MaxLAStages, WireStage<IterT>{0, 0});
         use_at = false;
         is_valid = false;
@@ -1486,7 +1498,15 @@ template <class N, class IterT> struct LaBuilder {
         const char *pe = getenv("FS_LA_PIPELINE");
         const bool pipeline_off = pe && atoi(pe) == 0;
         bool ok;
-        if (!pipeline_off && build_pipelined(maxRef)) {
+        bool pipelined = false;
+        if (!pipeline_off) {
+            try {
+                pipelined = build_pipelined(maxRef);
+            } catch (const std::bad_alloc &) {
+                pipelined = false; // no room for the walks' arrays: the stage-after-stage form needs a fraction of it
+            }
+        }
+        if (pipelined) {
             ok = walk_ok;
         } else {
             las.clear();

@@ -324,3 +324,15 @@ def test_three_thread_orbit_producer_equals_the_single_threaded_loop(built, monk
             o = Orbit(v, numeric, 2500, True)
             got.append((o.count, zlib.crc32(o.as_numpy().tobytes())))
         assert got[0] == got[1] and got[0][0] == 2501
+
+
+def test_la_builder_falls_back_when_a_stage_outgrows_its_room(built, monkeypatch):
+    """The pipelined builder sets aside room for stage k as a fraction of stage k - 1's; a stage that outgrows it is noted by
+    its walk and the table is rebuilt stage after stage.  FS_LA_TEST_SMALL_STAGES shrinks the room to 64 records so that
+    View 14's 1,827-record stage 1 takes that path: same table."""
+    from fractalshark_b200.host_inputs import LaTable
+    _, _, orbit, la, _ = cases.make_inputs(14, 96, 54, RenderAlgorithm.GpuHDRx32PerturbedLAv2, None, 4)
+    want = _la_bytes(la)
+    monkeypatch.setenv("FS_LA_TEST_SMALL_STAGES", "1")
+    got = _la_bytes(LaTable(orbit, 4))
+    assert got == want and got[0] == 33844
