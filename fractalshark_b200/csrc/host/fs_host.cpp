@@ -2191,7 +2191,15 @@ const void *fsh_orbit_x_low(const fsh_orbit *o) { return o->x_low; }
 const void *fsh_orbit_y_low(const fsh_orbit *o) { return o->y_low; }
 const void *fsh_orbit_max_radius(const fsh_orbit *o) { return o->max_radius; }
 
+static fsh_la *la_build_unguarded(const fsh_orbit *o, uint32_t iter_bytes);
 fsh_la *fsh_la_build(const fsh_orbit *o, uint32_t iter_bytes) {
+    try { // nothing is thrown across the C boundary: out of memory reads as "no table"
+        return la_build_unguarded(o, iter_bytes);
+    } catch (const std::exception &) {
+        return nullptr;
+    }
+}
+static fsh_la *la_build_unguarded(const fsh_orbit *o, uint32_t iter_bytes) {
     const bool u64 = iter_bytes == 8;
     // compressed orbit: the table is built from what the host-side RuntimeDecompressor replays
     // (LAReference.cpp reads the orbit through GetComplex), with the coarser period divisor
