@@ -961,6 +961,13 @@ __global__ void numeric_op_kernel(uint32_t op, const void *a_, const void *b_, v
     case 21: static_cast<df32 *>(out_)[i] = df_sub(da[i], db[i]); break;
     case 22: static_cast<df32 *>(out_)[i] = df_mul(da[i], db[i]); break;
     case 23: static_cast<df32 *>(out_)[i] = df_sqr(da[i]); break;
+    case 40: { // the perturbation step of the HDRx32 kernels: a = {dX, dY, Zx}, b = {Zy, cX, cY}
+        Hdr<float> dx = hf(a_, 3 * i), dy = hf(a_, 3 * i + 1);
+        NumHdr<float>::perturb(dx, dy, hf(a_, 3 * i + 2), hf(b_, 3 * i), hf(b_, 3 * i + 1), hf(b_, 3 * i + 2));
+        SelfHf *o = static_cast<SelfHf *>(out_) + 3 * i;
+        o[0] = SelfHf{dx.m, dx.e}; o[1] = SelfHf{dy.m, dy.e}; o[2] = SelfHf{0.0f, 0};
+        break;
+    }
     case 30: static_cast<dd64 *>(out_)[i] = dd_add(qa[i], qb[i]); break;
     case 31: static_cast<dd64 *>(out_)[i] = dd_sub(qa[i], qb[i]); break;
     case 32: static_cast<dd64 *>(out_)[i] = dd_mul(qa[i], qb[i]); break;
@@ -972,6 +979,7 @@ uint32_t numeric_op_elem_bytes(uint32_t op) {
     if (op >= 10 && op <= 14) return 12;
     if (op >= 20 && op <= 23) return 8;
     if (op >= 30 && op <= 32) return 16;
+    if (op == 40) return 24;
     return 0;
 }
 } // namespace

@@ -18,6 +18,7 @@
 #include "../fractalshark_b200/csrc/fs_at_fast.cuh"
 #include "../fractalshark_b200/csrc/fs_la_fast.cuh"
 #include "../fractalshark_b200/csrc/fs_la_step2.cuh"
+#include "../fractalshark_b200/csrc/fs_num.cuh"
 
 namespace {
 
@@ -528,6 +529,12 @@ int lockstep_numeric_op(uint32_t op, const void *a_, const void *b_, void *out_,
         case 12: c = hc(ca[i]); fs::reduce(c); co[i] = Hc{c.re, c.im, c.e}; break;
         case 13: r = fs::cheb(hc(ca[i])); co[i] = Hc{r.m, 0.0f, r.e}; break;
         case 14: c = fs::mul(hc(ca[i]), fs::hdr_make<float>(cb[i].e, cb[i].re)); co[i] = Hc{c.re, c.im, c.e}; break;
+        case 40: {
+            fs::Hdr<float> dx = hf(fa[3 * i]), dy = hf(fa[3 * i + 1]);
+            fs::NumHdr<float>::perturb(dx, dy, hf(fa[3 * i + 2]), hf(fb[3 * i]), hf(fb[3 * i + 1]), hf(fb[3 * i + 2]));
+            fo[3 * i] = Hf{dx.m, dx.e}; fo[3 * i + 1] = Hf{dy.m, dy.e}; fo[3 * i + 2] = Hf{0.0f, 0};
+            break;
+        }
         default: return -1;
         }
     }

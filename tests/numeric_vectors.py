@@ -72,13 +72,31 @@ OPS = [
     (13, "HDRFloatComplex chebychevNorm"), (14, "HDRFloatComplex times HDRFloat"),
     (20, "dblflt add"), (21, "dblflt sub"), (22, "dblflt mul"), (23, "dblflt sqr"),
     (30, "dbldbl add"), (31, "dbldbl sub"), (32, "dbldbl mul"),
+    (40, "HDRx32 perturbation step (custom_perturb2)"),
 ]
+_STEP = np.dtype([("m0", "<f4"), ("e0", "<i4"), ("m1", "<f4"), ("e1", "<i4"), ("m2", "<f4"), ("e2", "<i4")])
 
 
 def operands(op, n):
     """Operand pairs for `op`, aimed at the code's case distinctions: exponent gaps 0, +-1, +-119..121, +-126..129, far apart,
     the MIN_BIG exponent, zeros with and without it, unreduced and subnormal mantissas."""
     rng = np.random.default_rng(1000 + op)
+    if op == 40:
+        # reduced dX, dY, Zx, Zy, cX, cY (what the kernels hold at a step): exponents so that the two product sums and the
+        # added c meet at every gap the alignment distinguishes, including the 127 rule of custom_perturb2
+        a, b = np.zeros(n, _STEP), np.zeros(n, _STEP)
+        for arr in (a, b):
+            for k in range(3):
+                h = _hf_operands(rng, n, True)
+                arr["m%d" % k] = h["m"]
+                arr["e%d" % k] = h["e"]
+        # orbit elements Zx, Zy live near exponent 0..-60; deltas and c far below or near them
+        a["e2"] = rng.integers(-60, 2, n).astype(np.int32)
+        b["e0"] = rng.integers(-60, 2, n).astype(np.int32)
+        near = rng.integers(0, 2, n) == 0
+        for arr, f in ((a, "e0"), (a, "e1"), (b, "e1"), (b, "e2")):
+            arr[f] = np.where(near, rng.integers(-140, 2, n), arr[f]).astype(np.int32)
+        return a, b
     if op <= 6:
         reduced = op == 6  # the comparison is specified for reduced operands only
         a, b = _hf_operands(rng, n, reduced), _hf_operands(rng, n, reduced)
