@@ -25,6 +25,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <unistd.h>
 
 #include "../fs_types.cuh"
 #include "fs_gmp_min.h"
@@ -462,18 +463,20 @@ class HostPool {
     // want a small one, and are worth the threads from a few dozen items on
     void run(size_t n, const std::function<void(size_t, size_t)> &fn, size_t min_grain = 64) {
         if (n == 0) return;
-        if (workers.empty() || n < 8 * min_grain) { fn(0, n); return; }
+        if (!have_workers() || n < 8 * min_grain) { fn(0, n); return; }
         dispatch(n, std::max<size_t>(min_grain, n / (threads() * 8)), fn);
     }
     // n tasks, one index each, claimed in index order; a task may wait for a task with a smaller index (which some thread
     // has claimed before and runs to completion), never for a larger one.  Without workers they run one after the other.
     void run_tasks(size_t n, const std::function<void(size_t, size_t)> &fn) {
         if (n == 0) return;
-        if (workers.empty()) { for (size_t k = 0; k < n; k++) fn(k, k + 1); return; }
+        if (!have_workers()) { for (size_t k = 0; k < n; k++) fn(k, k + 1); return; }
         dispatch(n, 1, fn);
     }
 
   private:
+    // a forked child has the pool object but none of its threads: it works alone
+    bool have_workers() const { return !workers.empty() && getpid() == owner; }
     void dispatch(size_t n, size_t g, const std::function<void(size_t, size_t)> &fn) {
         std::lock_guard<std::mutex> one_job(job_mu); // callers on different threads take turns (jobs never nest)
         {
@@ -510,9 +513,14 @@ class HostPool {
         size_t want = std::thread::hardware_concurrency();
         if (const char *e = getenv("FS_HOST_THREADS")) want = (size_t)atoi(e);
         want = std::min<size_t>(std::max<size_t>(want, 1), 16);
+        owner = getpid();
         for (size_t t = 1; t < want; t++) workers.emplace_back([this] { loop(); });
     }
     ~HostPool() {
+        if (getpid() != owner) {
+            for (auto &t : workers) t.detach();
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(mu);
             stop = true;
@@ -550,6 +558,7 @@ class HostPool {
         }
     }
     std::vector<std::thread> workers;
+    pid_t owner = 0;
     std::mutex mu, job_mu;
     std::condition_variable wake, done;
     const std::function<void(size_t, size_t)> *job = nullptr;
