@@ -968,6 +968,23 @@ __global__ void numeric_op_kernel(uint32_t op, const void *a_, const void *b_, v
         o[0] = SelfHf{dx.m, dx.e}; o[1] = SelfHf{dy.m, dy.e}; o[2] = SelfHf{0.0f, 0};
         break;
     }
+    case 50: case 51: case 52: case 53: case 54: case 55: case 56: { // HDRFloat<double>: {double mantissa; int32 exp; pad}
+        struct Wire { double m; int32_t e; int32_t pad; };
+        const Wire wa = static_cast<const Wire *>(a_)[i], wb = static_cast<const Wire *>(b_)[i];
+        const Hdr<double> x = hdr_make<double>(wa.e, wa.m), y = hdr_make<double>(wb.e, wb.m);
+        Hdr<double> r = hdr_make<double>(0, 0.0);
+        switch (op) {
+        case 50: r = add(x, y); break;
+        case 51: r = sub(x, y); break;
+        case 52: r = mul(x, y); break;
+        case 53: r = square(x); break;
+        case 54: r = x; reduce(r); break;
+        case 55: r = div(x, y); break;
+        default: r = hdr_make<double>(cmp_pr(x, y), 0.0); break;
+        }
+        static_cast<Wire *>(out_)[i] = Wire{r.m, r.e, 0};
+        break;
+    }
     case 30: static_cast<dd64 *>(out_)[i] = dd_add(qa[i], qb[i]); break;
     case 31: static_cast<dd64 *>(out_)[i] = dd_sub(qa[i], qb[i]); break;
     case 32: static_cast<dd64 *>(out_)[i] = dd_mul(qa[i], qb[i]); break;
@@ -980,6 +997,7 @@ uint32_t numeric_op_elem_bytes(uint32_t op) {
     if (op >= 20 && op <= 23) return 8;
     if (op >= 30 && op <= 32) return 16;
     if (op == 40) return 24;
+    if (op >= 50 && op <= 56) return 16;
     return 0;
 }
 } // namespace

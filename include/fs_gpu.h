@@ -211,7 +211,8 @@ uint32_t fs_set_pool_kernel(fs_renderer *r, int32_t enable);
  * pairs from host arrays and writes n results to a host array.  op: 0-6 HDRFloat<float> add, sub, mul, square, Reduce,
  * divide, compareToBothPositiveReduced (result in .exp); 10-14 HDRFloatComplex<float> add, mul, Reduce, chebychevNorm,
  * times HDRFloat; 20-23 dblflt add, sub, mul, sqr; 30-32 dbldbl add, sub, mul; 40 the HDRx32 perturbation step (a = {dX, dY, Zx},
- * b = {Zy, cX, cY}, out = {dX', dY', 0}: 24 B each).  Elements: {float mantissa; int32 exp}
+ * b = {Zy, cX, cY}, out = {dX', dY', 0}: 24 B each); 50-56 HDRFloat<double> add, sub, mul, square, Reduce, divide, compare
+ * ({double mantissa; int32 exp; int32 pad}, 16 B).  Elements: {float mantissa; int32 exp}
  * (8 B), {float re, im; int32 exp} (12 B), {float head, tail} (8 B), {double head, tail} (16 B).  Reference: HDRFloat.h,
  * HDRFloatComplex.h, dblflt.cuh, dbldbl.cuh (the per-type operator tables SURVEY.md section 8 row a8 lists). */
 uint32_t fs_selftest_numeric_op(int32_t device, uint32_t op, const void *a, const void *b, void *out, uint64_t n);

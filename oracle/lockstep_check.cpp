@@ -529,6 +529,23 @@ int lockstep_numeric_op(uint32_t op, const void *a_, const void *b_, void *out_,
         case 12: c = hc(ca[i]); fs::reduce(c); co[i] = Hc{c.re, c.im, c.e}; break;
         case 13: r = fs::cheb(hc(ca[i])); co[i] = Hc{r.m, 0.0f, r.e}; break;
         case 14: c = fs::mul(hc(ca[i]), fs::hdr_make<float>(cb[i].e, cb[i].re)); co[i] = Hc{c.re, c.im, c.e}; break;
+        case 50: case 51: case 52: case 53: case 54: case 55: case 56: {
+            struct Wire { double m; int32_t e; int32_t pad; };
+            const Wire wa = ((const Wire *)a_)[i], wb = ((const Wire *)b_)[i];
+            const fs::Hdr<double> x = fs::hdr_make<double>(wa.e, wa.m), y = fs::hdr_make<double>(wb.e, wb.m);
+            fs::Hdr<double> q = fs::hdr_make<double>(0, 0.0);
+            switch (op) {
+            case 50: q = fs::add(x, y); break;
+            case 51: q = fs::sub(x, y); break;
+            case 52: q = fs::mul(x, y); break;
+            case 53: q = fs::square(x); break;
+            case 54: q = x; fs::reduce(q); break;
+            case 55: q = fs::div(x, y); break;
+            default: q = fs::hdr_make<double>(fs::cmp_pr(x, y), 0.0); break;
+            }
+            ((Wire *)out_)[i] = Wire{q.m, q.e, 0};
+            break;
+        }
         case 40: {
             fs::Hdr<float> dx = hf(fa[3 * i]), dy = hf(fa[3 * i + 1]);
             fs::NumHdr<float>::perturb(dx, dy, hf(fa[3 * i + 2]), hf(fb[3 * i]), hf(fb[3 * i + 1]), hf(fb[3 * i + 2]));

@@ -73,7 +73,29 @@ OPS = [
     (20, "dblflt add"), (21, "dblflt sub"), (22, "dblflt mul"), (23, "dblflt sqr"),
     (30, "dbldbl add"), (31, "dbldbl sub"), (32, "dbldbl mul"),
     (40, "HDRx32 perturbation step (custom_perturb2)"),
+    (50, "HDRFloat<double> add"), (51, "HDRFloat<double> subtract"), (52, "HDRFloat<double> multiply"),
+    (53, "HDRFloat<double> square"), (54, "HDRFloat<double> Reduce"), (55, "HDRFloat<double> divide"),
+    (56, "HDRFloat<double> compareToBothPositiveReduced"),
 ]
+_HD = np.dtype([("m", "<f8"), ("e", "<i4"), ("pad", "<i4")])
+
+
+def _hd_operands(rng, n, reduced):
+    """HDRFloat<double> operands: as _hf_operands, with 53-bit mantissas (unreduced ones from 2^-300 to 2^300, subnormals)."""
+    a = np.zeros(n, _HD)
+    m = rng.uniform(1.0, 2.0, n)
+    if not reduced:
+        m = m * np.exp2(rng.integers(-300, 301, n).astype(np.float64))
+        k = rng.integers(0, 16, n)
+        m[k == 0] = 0.0
+        m[k == 1] = 5e-320                                   # subnormal
+        m[k == 2] = 1.0
+        m[k == 3] = np.nextafter(2.0, 0.0)
+    a["m"] = m * rng.choice(np.array([-1.0, 1.0]), n)
+    a["e"] = _hdr_exponents(rng, n, int(rng.integers(-5000, 5000)))
+    z = a["m"] == 0
+    a["e"][z & (rng.integers(0, 2, n) == 0)] = _MIN_BIG
+    return a
 _STEP = np.dtype([("m0", "<f4"), ("e0", "<i4"), ("m1", "<f4"), ("e1", "<i4"), ("m2", "<f4"), ("e2", "<i4")])
 
 
@@ -81,6 +103,16 @@ def operands(op, n):
     """Operand pairs for `op`, aimed at the code's case distinctions: exponent gaps 0, +-1, +-119..121, +-126..129, far apart,
     the MIN_BIG exponent, zeros with and without it, unreduced and subnormal mantissas."""
     rng = np.random.default_rng(1000 + op)
+    if 50 <= op <= 56:
+        reduced = op == 56
+        a, b = _hd_operands(rng, n, reduced), _hd_operands(rng, n, reduced)
+        if op == 55:
+            b["m"][b["m"] == 0] = 1.5
+        if op == 56:
+            a["m"], b["m"] = np.abs(a["m"]), np.abs(b["m"])
+            same = rng.integers(0, 3, n) == 0
+            b["e"][same] = a["e"][same]
+        return a, b
     if op == 40:
         # reduced dX, dY, Zx, Zy, cX, cY (what the kernels hold at a step): exponents so that the two product sums and the
         # added c meet at every gap the alignment distinguishes, including the 127 rule of custom_perturb2

@@ -295,7 +295,7 @@ def test_la_builder_with_one_two_and_three_host_threads(built):
     assert len(outs) == 1 and outs.pop().startswith("33844 5 ")
 
 
-@pytest.mark.parametrize("op,name", [o for o in __import__("numeric_vectors").OPS if o[0] <= 14 or o[0] == 40])
+@pytest.mark.parametrize("op,name", [o for o in __import__("numeric_vectors").OPS if o[0] <= 14 or o[0] >= 40])
 def test_host_build_of_the_numeric_operations_matches_the_reference_restatement(built, op, name):
     """The HDRFloat<float> / HDRFloatComplex<float> operations of fs_types.cuh are host+device functions: compiled for the
     host (oracle/lockstep_check.cpp lockstep_numeric_op) they must give what oracle_cpu.cpp's restatement of HDRFloat.h /
